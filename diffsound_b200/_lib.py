@@ -1,0 +1,91 @@
+"""ctypes binding of libdiffsound_sm100.so (the C-ABI in include/diffsound_sm100.h).
+
+There is no fallback: if the shared library is missing the import raises, and
+every wrapper raises RuntimeError(ds_last_error()) on a non-zero return code.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdiffsound_sm100.so")
+
+_lib = None
+
+i32p = C.c_void_p
+f64p = C.c_void_p
+f32p = C.c_void_p
+i64p = C.c_void_p
+ptr = C.c_void_p
+i64 = C.c_int64
+cint = C.c_int
+dbl = C.c_double
+
+
+class LobpcgOpts(C.Structure):
+    _fields_ = [("nev", C.c_int), ("maxit", C.c_int), ("cheb_degree", C.c_int), ("tol", C.c_double),
+                ("sigma", C.c_double), ("cheb_ratio", C.c_double), ("n_rigid", C.c_int), ("verbose", C.c_int)]
+
+
+# name -> (restype, argtypes); mirrors include/diffsound_sm100.h one to one
+SIGNATURES = {
+    "ds_version": (cint, []),
+    "ds_last_error": (C.c_char_p, []),
+    "ds_workspace_create": (cint, [C.POINTER(C.c_void_p)]),
+    "ds_workspace_destroy": (cint, [ptr]),
+    "ds_workspace_bytes": (i64, [ptr]),
+    "ds_pattern_count": (cint, [ptr, i32p, i64, cint, i64, C.POINTER(C.c_int64), ptr]),
+    "ds_pattern_fill": (cint, [ptr, i64, i32p, i32p, i32p, i32p, i32p, ptr]),
+    "ds_pattern_expand_csr": (cint, [i32p, i32p, i64, i64, i64p, i64p, ptr]),
+    "ds_assemble_km": (cint, [f32p, i32p, i64, cint, i64, dbl, dbl, f64p, f64p, i32p, i32p, i32p, i32p, i64,
+                              f64p, f64p, f64p, ptr]),
+    "ds_mass_expand": (cint, [i32p, i64, i64, f64p, f64p, ptr]),
+    "ds_assemble_mass_coo": (cint, [f64p, i32p, i64, cint, f64p, dbl, f64p, i32p, i32p, ptr]),
+    "ds_spmm_km": (cint, [i32p, i32p, i64, f64p, f64p, dbl, f64p, i64, cint, dbl, dbl, f64p, i64, f64p, i64, ptr]),
+    "ds_spmm_k_and_m": (cint, [i32p, i32p, i64, f64p, f64p, f64p, i64, cint, f64p, i64, f64p, i64, ptr]),
+    "ds_gram_scratch_elems": (i64, [cint, cint]),
+    "ds_gram_f64": (cint, [f64p, i64, cint, f64p, i64, cint, i64, f64p, i64, f64p, ptr]),
+    "ds_block_gemm_f64": (cint, [f64p, i64, cint, f64p, i64, cint, i64, dbl, f64p, i64, ptr]),
+    "ds_eigh_generalized_f64": (cint, [f64p, f64p, cint, i64, dbl, f64p, f64p, i64, f64p, ptr, ptr]),
+    "ds_lobpcg": (cint, [ptr, i32p, i32p, i64, f64p, f64p, f64p, cint, C.POINTER(LobpcgOpts), f64p, f64p,
+                         C.POINTER(C.c_int64), ptr]),
+    "ds_corner_incidence": (cint, [ptr, i32p, i64, cint, cint, i64, i32p, i32p, ptr]),
+    "ds_eigval_grad_shape": (cint, [f32p, i32p, i64, cint, i64, dbl, dbl, f64p, f64p, i64, cint, f64p, f64p,
+                                    i32p, i32p, f64p, f32p, ptr]),
+    "ds_quadform_scratch_elems": (i64, [cint]),
+    "ds_eigval_quadforms_material": (cint, [f32p, i32p, i64, cint, f64p, f64p, i64, cint, f64p, f64p, ptr]),
+    "ds_synth_scratch_elems": (i64, [i64, cint, i64]),
+    "ds_modal_synth_fwd": (cint, [f32p, f32p, f32p, i64, cint, i64, dbl, f32p, f32p, ptr]),
+    "ds_modal_synth_bwd": (cint, [f32p, f32p, f32p, f32p, i64, cint, i64, dbl, f32p, f32p, f32p, f32p, ptr]),
+}
+
+
+def load():
+    """Load the shared library (once) and set the ctypes prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m diffsound_b200.build` "
+            "(nvcc, sm_100a). There is no CPU or PyTorch fallback for this path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        except AttributeError:
+            if os.environ.get("DIFFSOUND_PARTIAL_LIB") == "1":   # bring-up only
+                continue
+            raise
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().ds_last_error().decode(errors="replace")
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (code {rc}): {last_error()}")

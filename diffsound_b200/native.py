@@ -1,0 +1,242 @@
+"""Thin torch-tensor wrappers over the C-ABI (include/diffsound_sm100.h).
+
+torch is used only for device memory and streams; every function here ends in
+exactly one call into libdiffsound_sm100.so on the current CUDA stream.  There
+is no CPU path: CPU tensors raise.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("diffsound_b200: expected a CUDA tensor (there is no CPU path)")
+    if not t.is_contiguous():
+        raise RuntimeError("diffsound_b200: tensor must be contiguous")
+    return C.c_void_p(t.data_ptr())
+
+
+def _pv(t):
+    """pointer of a possibly strided 2-D row-major view (last stride 1)."""
+    if not t.is_cuda:
+        raise RuntimeError("diffsound_b200: expected a CUDA tensor (there is no CPU path)")
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise RuntimeError("diffsound_b200: block must be a row-major 2-D view")
+    return C.c_void_p(t.data_ptr()), t.stride(0)
+
+
+class Workspace:
+    """Owns a ds_workspace (device scratch arena)."""
+
+    def __init__(self):
+        lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(lib.ds_workspace_create(C.byref(h)), "ds_workspace_create")
+        self._h = h
+
+    @property
+    def handle(self):
+        return self._h
+
+    def nbytes(self):
+        return _lib.load().ds_workspace_bytes(self._h)
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.load().ds_workspace_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+_ws_cache = {}
+
+
+def workspace(device=None):
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index
+    if dev not in _ws_cache:
+        with torch.cuda.device(dev):
+            _ws_cache[dev] = Workspace()
+    return _ws_cache[dev]
+
+
+class Pattern:
+    """Block-CSR sparsity pattern of K and M plus per-slot contributor lists."""
+
+    def __init__(self, tets_i32, n_nodes, want_slot=False):
+        lib = _lib.load()
+        assert tets_i32.dtype == torch.int32 and tets_i32.is_cuda and tets_i32.is_contiguous()
+        T, npe = tets_i32.shape
+        dev = tets_i32.device
+        self.device = dev
+        self.T, self.npe, self.n_nodes = T, npe, int(n_nodes)
+        ws = workspace(dev)
+        nnzb = C.c_int64(0)
+        with torch.cuda.device(dev):
+            _lib.check(lib.ds_pattern_count(ws.handle, _p(tets_i32), T, npe, self.n_nodes, C.byref(nnzb), _stream()),
+                       "ds_pattern_count")
+            self.nnzb = int(nnzb.value)
+            i32 = dict(dtype=torch.int32, device=dev)
+            self.brow = torch.empty(self.n_nodes + 1, **i32)
+            self.bcol = torch.empty(self.nnzb, **i32)
+            self.contrib_ptr = torch.empty(self.nnzb + 1, **i32)
+            self.contrib = torch.empty(T * npe * npe, **i32)
+            self.slot = torch.empty(T * npe * npe, **i32) if want_slot else None
+            _lib.check(lib.ds_pattern_fill(ws.handle, self.n_nodes, _p(self.brow), _p(self.bcol), _p(self.contrib_ptr),
+                                           _p(self.contrib), _p(self.slot), _stream()), "ds_pattern_fill")
+        self._csr = None
+
+    @property
+    def nnz(self):
+        return 9 * self.nnzb
+
+    @property
+    def n(self):
+        return 3 * self.n_nodes
+
+    def csr(self):
+        """(crow, col) int64 -- the reference's coalesced (row, col) order."""
+        if self._csr is None:
+            lib = _lib.load()
+            crow = torch.empty(self.n + 1, dtype=torch.int64, device=self.device)
+            col = torch.empty(self.nnz, dtype=torch.int64, device=self.device)
+            with torch.cuda.device(self.device):
+                _lib.check(lib.ds_pattern_expand_csr(_p(self.brow), _p(self.bcol), self.n_nodes, self.nnzb, _p(crow),
+                                                     _p(col), _stream()), "ds_pattern_expand_csr")
+            self._csr = (crow, col)
+        return self._csr
+
+    def coo_indices(self):
+        """(2, nnz) int64 like `stiff_matrix.indices()` of the reference."""
+        crow, col = self.csr()
+        rows = torch.repeat_interleave(torch.arange(self.n, device=self.device), crow[1:] - crow[:-1])
+        return torch.stack([rows, col], dim=0)
+
+
+def assemble_km(verts_f32, tets_i32, order, pattern, mu, lam, ctab, mtab, Kval=None, Mblk=None, geom=None):
+    lib = _lib.load()
+    dev = verts_f32.device
+    assert verts_f32.dtype == torch.float32 and tets_i32.dtype == torch.int32
+    T = tets_i32.shape[0]
+    f64 = dict(dtype=torch.float64, device=dev)
+    if Kval is None:
+        Kval = torch.empty(pattern.nnz, **f64)
+    if Mblk is None:
+        Mblk = torch.empty(pattern.nnzb, **f64)
+    if geom is None:
+        geom = torch.empty(T * 14, **f64)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ds_assemble_km(_p(verts_f32), _p(tets_i32), T, order, pattern.n_nodes, float(mu), float(lam),
+                                      _p(ctab), _p(mtab), _p(pattern.brow), _p(pattern.bcol), _p(pattern.contrib_ptr),
+                                      _p(pattern.contrib), pattern.nnzb, _p(geom), _p(Kval), _p(Mblk), _stream()),
+                   "ds_assemble_km")
+    return Kval, Mblk
+
+
+def mass_expand(pattern, Mblk):
+    lib = _lib.load()
+    Mval = torch.empty(pattern.nnz, dtype=torch.float64, device=Mblk.device)
+    with torch.cuda.device(Mblk.device):
+        _lib.check(lib.ds_mass_expand(_p(pattern.brow), pattern.n_nodes, pattern.nnzb, _p(Mblk), _p(Mval), _stream()),
+                   "ds_mass_expand")
+    return Mval
+
+
+def assemble_mass_coo(vertices, tets, values, rows, cols, element_mm, density, order):
+    """Same argument order as the reference's `assemble_mass_matrix` export."""
+    lib = _lib.load()
+    vnum = {1: 4, 2: 10, 3: 20}[order]
+    T = tets.numel() // vnum
+    with torch.cuda.device(vertices.device):
+        _lib.check(lib.ds_assemble_mass_coo(_p(vertices), _p(tets), T, order, _p(element_mm), float(density),
+                                            _p(values), _p(rows), _p(cols), _stream()), "ds_assemble_mass_coo")
+
+
+def spmm(pattern, Kval, Mblk, X, shift=0.0, alpha=1.0, beta=0.0, Y0=None, out=None):
+    """out = alpha (K + shift M) X + beta Y0  (X: (n, ncols) fp64 row-major view)."""
+    lib = _lib.load()
+    xp, ldx = _pv(X)
+    ncols = X.shape[1]
+    if out is None:
+        out = torch.empty(X.shape[0], ncols, dtype=torch.float64, device=X.device)
+    yp, ldy = _pv(out)
+    y0p, ldy0 = (None, 0) if Y0 is None else _pv(Y0)
+    with torch.cuda.device(X.device):
+        _lib.check(lib.ds_spmm_km(_p(pattern.brow), _p(pattern.bcol), pattern.n_nodes, _p(Kval), _p(Mblk), float(shift),
+                                  xp, ldx, ncols, float(alpha), float(beta), y0p, ldy0, yp, ldy, _stream()),
+                   "ds_spmm_km")
+    return out
+
+
+def spmm_k_and_m(pattern, Kval, Mblk, X, YK=None, YM=None):
+    lib = _lib.load()
+    xp, ldx = _pv(X)
+    ncols = X.shape[1]
+    if YK is None:
+        YK = torch.empty_like(X, memory_format=torch.contiguous_format)
+    if YM is None:
+        YM = torch.empty_like(X, memory_format=torch.contiguous_format)
+    kp, ldk = _pv(YK)
+    mp, ldm = _pv(YM)
+    with torch.cuda.device(X.device):
+        _lib.check(lib.ds_spmm_k_and_m(_p(pattern.brow), _p(pattern.bcol), pattern.n_nodes, _p(Kval), _p(Mblk), xp, ldx,
+                                       ncols, kp, ldk, mp, ldm, _stream()), "ds_spmm_k_and_m")
+    return YK, YM
+
+
+def gram(A, B, out=None):
+    """A^T B for row-major (n, p), (n, q) fp64 blocks."""
+    lib = _lib.load()
+    ap, lda = _pv(A)
+    bp, ldb = _pv(B)
+    p, q = A.shape[1], B.shape[1]
+    if out is None:
+        out = torch.empty(p, q, dtype=torch.float64, device=A.device)
+    gp, ldg = _pv(out)
+    scratch = torch.empty(lib.ds_gram_scratch_elems(p, q), dtype=torch.float64, device=A.device)
+    with torch.cuda.device(A.device):
+        _lib.check(lib.ds_gram_f64(ap, lda, p, bp, ldb, q, A.shape[0], gp, ldg, _p(scratch), _stream()), "ds_gram_f64")
+    return out
+
+
+def block_gemm(A, Cm, beta=0.0, out=None):
+    """out = beta*out + A Cm, A (n, p), Cm (p, q)."""
+    lib = _lib.load()
+    ap, lda = _pv(A)
+    cp, ldc = _pv(Cm)
+    p, q = Cm.shape
+    if out is None:
+        out = torch.empty(A.shape[0], q, dtype=torch.float64, device=A.device)
+        beta = 0.0
+    yp, ldy = _pv(out)
+    with torch.cuda.device(A.device):
+        _lib.check(lib.ds_block_gemm_f64(ap, lda, p, cp, ldc, q, A.shape[0], float(beta), yp, ldy, _stream()),
+                   "ds_block_gemm_f64")
+    return out
+
+
+def eigh_generalized(GK, GM, sigma):
+    lib = _lib.load()
+    N = GK.shape[0]
+    dev = GK.device
+    kp, ldg = _pv(GK)
+    mp, ldg2 = _pv(GM)
+    assert ldg == ldg2
+    theta = torch.empty(N, dtype=torch.float64, device=dev)
+    Cm = torch.empty(N, N, dtype=torch.float64, device=dev)
+    scratch = torch.empty(2 * N * N, dtype=torch.float64, device=dev)
+    info = torch.zeros(2, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ds_eigh_generalized_f64(kp, mp, N, ldg, float(sigma), _p(theta), _p(Cm), N, _p(scratch),
+                                               _p(info), _stream()), "ds_eigh_generalized_f64")
+    return theta, Cm, info

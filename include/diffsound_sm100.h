@@ -1,0 +1,182 @@
+/*
+ * libdiffsound_sm100.so -- C-ABI of the B200-native modal-analysis hot path.
+ *
+ * This is the drop-in boundary.  The reference's only native plugin is the
+ * torch extension `diffFEM` (src/cuda_module.py:7-41) exporting one op,
+ * `assemble_mass_matrix` (src/cuda/massMatrixDouble.h:14-15, bind.cu:11); the
+ * rest of the path is torch-eager + SciPy inside src/diffelastic, src/lobpcg
+ * and src/ddsp.  Each entry point below names the reference code it replaces.
+ *
+ * Conventions (all functions):
+ *   - return 0 on success, <0 on error; message via ds_last_error() (thread-local)
+ *   - every pointer is a DEVICE pointer owned by the caller (torch) unless the
+ *     parameter is documented as "host"; nothing is allocated except inside an
+ *     explicit ds_workspace
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); calls are
+ *     asynchronous unless documented as synchronising
+ *   - callable from any host thread (autograd runs backward on its own thread);
+ *     the caller has made the right device current
+ *   - dense block vectors are ROW-MAJOR (n x ncols) with a leading dimension ld
+ */
+#ifndef DIFFSOUND_SM100_H
+#define DIFFSOUND_SM100_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ds_workspace ds_workspace;
+
+/* ---- library ------------------------------------------------------------ */
+int ds_version(void);
+const char* ds_last_error(void);
+/* scratch arena; replaces the implicit temporaries torch allocates inside
+ * coalesce()/sparse.mm on the reference path (diff_model.py:217-220). */
+int ds_workspace_create(ds_workspace** ws);
+int ds_workspace_destroy(ds_workspace* ws);
+int64_t ds_workspace_bytes(const ds_workspace* ws);
+
+/* ---- sparsity pattern (integer, bit-exact) --------------------------------
+ * Replaces the pattern that `sparse_coo_tensor(...).coalesce()` derives by
+ * sort-and-reduce on every batch (diff_model.py:214-220, 305-312).
+ * tets: int32 [T*npe] node ids (npe = 4 or 10).  The pattern is the node-level
+ * block CSR (brow/bcol, dense 3x3 blocks); ds_pattern_expand_csr emits the
+ * scalar CSR (crow, col int64) that equals the reference's coalesced indices.
+ * ds_pattern_count synchronises the stream (it returns nnzb to the host). */
+int ds_pattern_count(ds_workspace* ws, const int32_t* tets, int64_t T, int npe,
+                     int64_t n_nodes, int64_t* nnzb_host, void* stream);
+/* contrib_ptr[nnzb+1], contrib[T*npe*npe]: for every block slot the element
+ * entries e*npe*npe + a*npe + b that sum into it (ascending); slot (optional,
+ * may be NULL) is the inverse map [T*npe*npe] -> block slot. */
+int ds_pattern_fill(ds_workspace* ws, int64_t n_nodes, int32_t* brow, int32_t* bcol,
+                    int32_t* contrib_ptr, int32_t* contrib, int32_t* slot, void* stream);
+int ds_pattern_expand_csr(const int32_t* brow, const int32_t* bcol, int64_t n_nodes,
+                          int64_t nnzb, int64_t* crow, int64_t* col, void* stream);
+
+/* ---- assembly --------------------------------------------------------------
+ * Fused K and M assembly straight into the fixed pattern; replaces
+ * DiffSoundObj.update_stiff_matrix + update_mass_matrix (diff_model.py:184-312),
+ * Deform.precompute_* (deform.py:35-68, 136-147) and the dead-code kernel
+ * compute_mass_matrix_kernel (src/cuda/massMatrixDouble.cu:3-78).
+ * verts: fp32 [n_nodes*3]; order 1|2; ctab: fp64 [npe*npe*16] = sum_g w_g
+ * dN_a/dL_l dN_b/dL_m from the reference's fp32 Gauss rule; mtab: fp64
+ * [npe*npe] = double(float(m_ab)*float(rho)) (diff_model.py:299-303).
+ * Kval: fp64 [9*nnzb] in the reference's scalar-CSR (row, col) order.
+ * Mblk: fp64 [nnzb], M = Mblk (x) I3 (the expanded reference values come from
+ * ds_mass_expand).  geom: fp64 scratch [T*14].  Owner-computes: one thread per
+ * block slot sums its contributors in ascending order -- no atomics,
+ * deterministic. */
+int ds_assemble_km(const float* verts, const int32_t* tets, int64_t T, int order,
+                   int64_t n_nodes, double mu, double lam, const double* ctab,
+                   const double* mtab, const int32_t* brow, const int32_t* bcol,
+                   const int32_t* contrib_ptr, const int32_t* contrib, int64_t nnzb,
+                   double* geom, double* Kval, double* Mblk, void* stream);
+int ds_mass_expand(const int32_t* brow, int64_t n_nodes, int64_t nnzb, const double* Mblk,
+                   double* Mval, void* stream);
+/* Legacy twin of the reference export `assemble_mass_matrix` (massMatrixDouble.cu:138-158):
+ * COO triples, msize*msize per tet, same layout/dtypes (vertices fp64 flat, tets int32 flat,
+ * element_mm fp64 flat msize*msize). */
+int ds_assemble_mass_coo(const double* vertices, const int32_t* tets, int64_t T, int order,
+                         const double* element_mm, double density, double* values,
+                         int32_t* rows, int32_t* cols, void* stream);
+
+/* ---- sparse x dense block --------------------------------------------------
+ * Replaces torch sparse COO `K @ U`, `M @ U` (diff_model.py:395-397, 385;
+ * _linalg_utils.py:27-39).  Y = alpha*(K + shift*M) X + beta*Y0 on the block
+ * pattern; any of Kval / Mblk may be NULL (treated as zero).  ncols multiple of
+ * 16, <= 128.  X must not alias Y. */
+int ds_spmm_km(const int32_t* brow, const int32_t* bcol, int64_t n_nodes,
+               const double* Kval, const double* Mblk, double shift,
+               const double* X, int64_t ldx, int ncols,
+               double alpha, double beta, const double* Y0, int64_t ldy0,
+               double* Y, int64_t ldy, void* stream);
+/* YK = K X and YM = M X in one pass over X (both needed by LOBPCG). */
+int ds_spmm_k_and_m(const int32_t* brow, const int32_t* bcol, int64_t n_nodes,
+                    const double* Kval, const double* Mblk, const double* X, int64_t ldx,
+                    int ncols, double* YK, int64_t ldyk, double* YM, int64_t ldym, void* stream);
+
+/* ---- dense tall-skinny pieces of Rayleigh-Ritz ------------------------------
+ * Replace torch.matmul / qform / linalg.cholesky / linalg.eigh calls in
+ * src/lobpcg/_lobpcg.py:433-525 and _linalg_utils.py:63-96. */
+/* G[p x q] (row-major, ldg) = A^T B, A (n x p, lda), B (n x q, ldb); FP64 DMMA,
+ * split over row chunks, deterministic two-pass reduction.  partial: scratch
+ * fp64 [ds_gram_scratch_elems(p,q)]. */
+int64_t ds_gram_scratch_elems(int p, int q);
+int ds_gram_f64(const double* A, int64_t lda, int p, const double* B, int64_t ldb, int q,
+                int64_t n, double* G, int64_t ldg, double* partial, void* stream);
+/* Y (n x q) = beta*Y + A (n x p) C (p x q, row-major ldc) */
+int ds_block_gemm_f64(const double* A, int64_t lda, int p, const double* C, int64_t ldc, int q,
+                      int64_t n, double beta, double* Y, int64_t ldy, void* stream);
+/* Generalised symmetric eigenproblem GK c = theta GM c, N <= 144, one CTA:
+ * Cholesky of GM and of GK + sigma*GM, one-sided Jacobi in shared memory.
+ * theta ascending [N], C [N x N] row-major (columns = GM-orthonormal vectors).
+ * scratch: fp64 [2*N*N].  info (device int[2]): {0 ok | failing pivot index+1 (+1000 when
+ * the failure is in GK + sigma*GM), sweeps used}. */
+int ds_eigh_generalized_f64(const double* GK, const double* GM, int N, int64_t ldg, double sigma,
+                            double* theta, double* C, int64_t ldc, double* scratch, int* info,
+                            void* stream);
+
+/* ---- eigensolver -----------------------------------------------------------
+ * Lowest `nev` eigenpairs of K u = lambda M u; replaces eigen_decomposition_arpack
+ * (diff_model.py:335-369: scipy eigsh shift-invert on the CPU) and is the engine
+ * behind the lobpcg / lobpcg_func API mirror (src/lobpcg/_lobpcg.py:8-212).
+ * X: fp64 [n x m] row-major start block on entry (m >= nev, multiple of 16),
+ * M-orthonormal Ritz vectors on exit; lambda_out [m]; resid_out [m] relative
+ * residuals; stats_host (host int64[4]) = {iterations, converged, spmm_count, status}.
+ * Preconditioner: `cheb_degree` steps of block-Jacobi Chebyshev on K + sigma*M.
+ * Synchronises the stream. */
+typedef struct ds_lobpcg_opts {
+    int nev;            /* number of pairs that must converge (lowest nev) */
+    int maxit;
+    int cheb_degree;
+    double tol;         /* ||K x - lam M x|| / (lam ||M x||) */
+    double sigma;       /* shift for the preconditioner / RR (<=0: automatic) */
+    double cheb_ratio;  /* lmax / lmin of the Chebyshev interval */
+    int n_rigid;        /* leading columns that hold (near-)null-space vectors */
+    int verbose;
+} ds_lobpcg_opts;
+int ds_lobpcg(ds_workspace* ws, const int32_t* brow, const int32_t* bcol, int64_t n_nodes,
+              const double* Kval, const double* Mblk, double* X, int m,
+              const ds_lobpcg_opts* opts, double* lambda_out, double* resid_out,
+              int64_t* stats_host, void* stream);
+
+/* ---- eigenvalue derivative --------------------------------------------------
+ * Shape: grad_verts += d/dx sum_i g_i (u_i^T K u_i - lam_i u_i^T M u_i); replaces
+ * autograd through get_vals (diff_model.py:390-399 -> coalesce/bmm/inverse graph).
+ * U fp64 [3*n_nodes x ldu] (k columns used), lam/g fp64 [k]; tet_grad scratch
+ * fp64 [T*12]; inc_ptr/inc: node -> (tet*4+corner) incidence (ds_corner_incidence);
+ * grad_verts fp32 [n_nodes*3] (overwritten). */
+int ds_corner_incidence(ds_workspace* ws, const int32_t* tets, int64_t T, int npe, int order,
+                        int64_t n_nodes, int32_t* inc_ptr, int32_t* inc, void* stream);
+int ds_eigval_grad_shape(const float* verts, const int32_t* tets, int64_t T, int order,
+                         int64_t n_nodes, double mu, double lam_lame, const double* mtab,
+                         const double* U, int64_t ldu, int k, const double* lam, const double* g,
+                         const int32_t* inc_ptr, const int32_t* inc, double* tet_grad,
+                         float* grad_verts, void* stream);
+/* Material: q_mu[i] = u_i^T K(mu=1,lam=0) u_i, q_lam[i] = u_i^T K(0,1) u_i,
+ * q_m[i] = u_i^T M u_i; replaces the matrix-free stiff_func path
+ * (diff_model.py:314-328, 371-388; deform.py:70-87, 149-165).  out fp64 [3*k];
+ * partial scratch fp64 [ds_quadform_scratch_elems(k)]. */
+int64_t ds_quadform_scratch_elems(int k);
+int ds_eigval_quadforms_material(const float* verts, const int32_t* tets, int64_t T, int order,
+                                 const double* mtab, const double* U, int64_t ldu, int k,
+                                 double* partial, double* out, void* stream);
+
+/* ---- modal synthesis --------------------------------------------------------
+ * y[b,t] = sum_m a[b,m] exp(-d[m] (t+1)/sr) sin(2 pi f[m] (t+1)/sr); replaces the
+ * cumsum/exp/sin/sum chain of oscillator.py:297-304 (and :128-138, :160-171).
+ * amp fp32 [B*k]; damp, freq fp32 [k] (shared over the batch) ; y fp32 [B*T].
+ * Backward: gy [B*T] -> gamp [B*k], gdamp [k], gfreq [k]. */
+int64_t ds_synth_scratch_elems(int64_t B, int k, int64_t T);
+int ds_modal_synth_fwd(const float* amp, const float* damp, const float* freq, int64_t B, int k,
+                       int64_t T, double sr, float* y, float* scratch, void* stream);
+int ds_modal_synth_bwd(const float* amp, const float* damp, const float* freq, const float* gy,
+                       int64_t B, int k, int64_t T, double sr, float* gamp, float* gdamp,
+                       float* gfreq, float* scratch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFSOUND_SM100_H */
