@@ -240,3 +240,23 @@ def eigh_generalized(GK, GM, sigma):
         _lib.check(lib.ds_eigh_generalized_f64(kp, mp, N, ldg, float(sigma), _p(theta), _p(Cm), N, _p(scratch),
                                                _p(info), _stream()), "ds_eigh_generalized_f64")
     return theta, Cm, info
+
+
+def lobpcg(pattern, Kval, Mblk, X, nev, tol=1e-4, maxit=200, cheb_degree=8, sigma=0.0, cheb_ratio=30.0, n_rigid=6,
+           verbose=0):
+    """Lowest `nev` pairs of K u = lam M u from the start block X (n, m) fp64 (overwritten with the
+    M-orthonormal Ritz vectors).  Returns (lam (m,), resid (m,), stats dict)."""
+    lib = _lib.load()
+    assert X.dtype == torch.float64 and X.is_contiguous()
+    n, m = X.shape
+    dev = X.device
+    lam = torch.empty(m, dtype=torch.float64, device=dev)
+    res = torch.empty(m, dtype=torch.float64, device=dev)
+    opts = _lib.LobpcgOpts(nev=int(nev), maxit=int(maxit), cheb_degree=int(cheb_degree), tol=float(tol),
+                           sigma=float(sigma), cheb_ratio=float(cheb_ratio), n_rigid=int(n_rigid), verbose=int(verbose))
+    stats = (C.c_int64 * 4)()
+    ws = workspace(dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ds_lobpcg(ws.handle, _p(pattern.brow), _p(pattern.bcol), pattern.n_nodes, _p(Kval), _p(Mblk),
+                                 _p(X), m, C.byref(opts), _p(lam), _p(res), stats, _stream()), "ds_lobpcg")
+    return lam, res, dict(iterations=int(stats[0]), converged=int(stats[1]), spmm=int(stats[2]), status=int(stats[3]))
