@@ -49,10 +49,10 @@ SIGNATURES = {
     "ds_lobpcg": (cint, [ptr, i32p, i32p, i64, f64p, f64p, f64p, cint, C.POINTER(LobpcgOpts), f64p, f64p,
                          C.POINTER(C.c_int64), ptr]),
     "ds_corner_incidence": (cint, [ptr, i32p, i64, cint, cint, i64, i32p, i32p, ptr]),
-    "ds_eigval_grad_shape": (cint, [f32p, i32p, i64, cint, i64, dbl, dbl, f64p, f64p, i64, cint, f64p, f64p,
+    "ds_eigval_grad_shape": (cint, [f32p, i32p, i64, cint, i64, dbl, dbl, f64p, f64p, f64p, i64, cint, f64p, f64p,
                                     i32p, i32p, f64p, f32p, ptr]),
     "ds_quadform_scratch_elems": (i64, [cint]),
-    "ds_eigval_quadforms_material": (cint, [f32p, i32p, i64, cint, f64p, f64p, i64, cint, f64p, f64p, ptr]),
+    "ds_eigval_quadforms_material": (cint, [f32p, i32p, i64, cint, f64p, dbl, f64p, i64, cint, f64p, f64p, ptr]),
     "ds_synth_scratch_elems": (i64, [i64, cint, i64]),
     "ds_modal_synth_fwd": (cint, [f32p, f32p, f32p, i64, cint, i64, dbl, f32p, f32p, ptr]),
     "ds_modal_synth_bwd": (cint, [f32p, f32p, f32p, f32p, i64, cint, i64, dbl, f32p, f32p, f32p, f32p, ptr]),

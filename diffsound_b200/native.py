@@ -260,3 +260,82 @@ def lobpcg(pattern, Kval, Mblk, X, nev, tol=1e-4, maxit=200, cheb_degree=8, sigm
         _lib.check(lib.ds_lobpcg(ws.handle, _p(pattern.brow), _p(pattern.bcol), pattern.n_nodes, _p(Kval), _p(Mblk),
                                  _p(X), m, C.byref(opts), _p(lam), _p(res), stats, _stream()), "ds_lobpcg")
     return lam, res, dict(iterations=int(stats[0]), converged=int(stats[1]), spmm=int(stats[2]), status=int(stats[3]))
+
+
+def corner_incidence(tets_i32, order, n_nodes):
+    """node -> (tet*4 + corner) incidence lists (inc_ptr (n_nodes+1,), inc (4T,)) int32."""
+    lib = _lib.load()
+    T, npe = tets_i32.shape
+    dev = tets_i32.device
+    inc_ptr = torch.empty(n_nodes + 1, dtype=torch.int32, device=dev)
+    inc = torch.empty(4 * T, dtype=torch.int32, device=dev)
+    ws = workspace(dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ds_corner_incidence(ws.handle, _p(tets_i32), T, npe, order, n_nodes, _p(inc_ptr), _p(inc),
+                                           _stream()), "ds_corner_incidence")
+    return inc_ptr, inc
+
+
+def eigval_grad_shape(verts_f32, tets_i32, order, mu, lam_lame, ctab, mtab, U, lam, g, inc_ptr, inc, tet_grad=None):
+    """d/d(verts) sum_i g_i (u_i^T K u_i - lam_i u_i^T M u_i) -> (n_nodes, 3) fp32.
+    U: (n, k) fp64 row-major view; lam, g: (k,) fp64."""
+    lib = _lib.load()
+    dev = verts_f32.device
+    T = tets_i32.shape[0]
+    n_nodes = verts_f32.shape[0]
+    up, ldu = _pv(U)
+    k = U.shape[1]
+    assert lam.dtype == torch.float64 and g.dtype == torch.float64 and lam.numel() == k and g.numel() == k
+    if tet_grad is None:
+        tet_grad = torch.empty(T * 12, dtype=torch.float64, device=dev)
+    out = torch.empty(n_nodes, 3, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ds_eigval_grad_shape(_p(verts_f32), _p(tets_i32), T, order, n_nodes, float(mu), float(lam_lame),
+                                            _p(ctab), _p(mtab), up, ldu, k, _p(lam.contiguous()), _p(g.contiguous()),
+                                            _p(inc_ptr), _p(inc), _p(tet_grad), _p(out), _stream()),
+                   "ds_eigval_grad_shape")
+    return out
+
+
+def eigval_quadforms_material(verts_f32, tets_i32, order, mtab, wsum, U):
+    """(q_mu, q_lam, q_m), each (k,) fp64: u_i^T K(1,0) u_i, u_i^T K(0,1) u_i, u_i^T M u_i."""
+    lib = _lib.load()
+    dev = verts_f32.device
+    T = tets_i32.shape[0]
+    up, ldu = _pv(U)
+    k = U.shape[1]
+    partial = torch.empty(lib.ds_quadform_scratch_elems(k), dtype=torch.float64, device=dev)
+    out = torch.empty(3, k, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ds_eigval_quadforms_material(_p(verts_f32), _p(tets_i32), T, order, _p(mtab), float(wsum), up,
+                                                    ldu, k, _p(partial), _p(out), _stream()),
+                   "ds_eigval_quadforms_material")
+    return out[0], out[1], out[2]
+
+
+def modal_synth_fwd(amp, damp, freq, T, sr):
+    """y (B, T) fp32 = sum_m amp[b,m] exp(-damp[m] tau) sin(2 pi freq[m] tau), tau = (t+1)/sr."""
+    lib = _lib.load()
+    B, k = amp.shape
+    assert amp.dtype == damp.dtype == freq.dtype == torch.float32 and damp.numel() == k and freq.numel() == k
+    y = torch.empty(B, T, dtype=torch.float32, device=amp.device)
+    with torch.cuda.device(amp.device):
+        _lib.check(lib.ds_modal_synth_fwd(_p(amp), _p(damp), _p(freq), B, k, T, float(sr), _p(y), None, _stream()),
+                   "ds_modal_synth_fwd")
+    return y
+
+
+def modal_synth_bwd(amp, damp, freq, gy, sr):
+    lib = _lib.load()
+    B, k = amp.shape
+    T = gy.shape[1]
+    assert gy.dtype == torch.float32 and gy.shape[0] == B
+    dev = amp.device
+    gamp = torch.empty(B, k, dtype=torch.float32, device=dev)
+    gdamp = torch.empty(k, dtype=torch.float32, device=dev)
+    gfreq = torch.empty(k, dtype=torch.float32, device=dev)
+    scratch = torch.empty(lib.ds_synth_scratch_elems(B, k, T), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ds_modal_synth_bwd(_p(amp), _p(damp), _p(freq), _p(gy), B, k, T, float(sr), _p(gamp), _p(gdamp),
+                                          _p(gfreq), _p(scratch), _stream()), "ds_modal_synth_bwd")
+    return gamp, gdamp, gfreq

@@ -145,23 +145,26 @@ int ds_lobpcg(ds_workspace* ws, const int32_t* brow, const int32_t* bcol, int64_
 /* ---- eigenvalue derivative --------------------------------------------------
  * Shape: grad_verts += d/dx sum_i g_i (u_i^T K u_i - lam_i u_i^T M u_i); replaces
  * autograd through get_vals (diff_model.py:390-399 -> coalesce/bmm/inverse graph).
+ * ctab/mtab: the assembly tables (ds_assemble_km).
  * U fp64 [3*n_nodes x ldu] (k columns used), lam/g fp64 [k]; tet_grad scratch
  * fp64 [T*12]; inc_ptr/inc: node -> (tet*4+corner) incidence (ds_corner_incidence);
  * grad_verts fp32 [n_nodes*3] (overwritten). */
 int ds_corner_incidence(ds_workspace* ws, const int32_t* tets, int64_t T, int npe, int order,
                         int64_t n_nodes, int32_t* inc_ptr, int32_t* inc, void* stream);
 int ds_eigval_grad_shape(const float* verts, const int32_t* tets, int64_t T, int order,
-                         int64_t n_nodes, double mu, double lam_lame, const double* mtab,
+                         int64_t n_nodes, double mu, double lam_lame, const double* ctab,
+                         const double* mtab,
                          const double* U, int64_t ldu, int k, const double* lam, const double* g,
                          const int32_t* inc_ptr, const int32_t* inc, double* tet_grad,
                          float* grad_verts, void* stream);
 /* Material: q_mu[i] = u_i^T K(mu=1,lam=0) u_i, q_lam[i] = u_i^T K(0,1) u_i,
  * q_m[i] = u_i^T M u_i; replaces the matrix-free stiff_func path
- * (diff_model.py:314-328, 371-388; deform.py:70-87, 149-165).  out fp64 [3*k];
+ * (diff_model.py:314-328, 371-388; deform.py:70-87, 149-165).  wsum = sum of the
+ * reference's fp32 Gauss weights (used by linear tets only).  out fp64 [3*k];
  * partial scratch fp64 [ds_quadform_scratch_elems(k)]. */
 int64_t ds_quadform_scratch_elems(int k);
 int ds_eigval_quadforms_material(const float* verts, const int32_t* tets, int64_t T, int order,
-                                 const double* mtab, const double* U, int64_t ldu, int k,
+                                 const double* mtab, double wsum, const double* U, int64_t ldu, int k,
                                  double* partial, double* out, void* stream);
 
 /* ---- modal synthesis --------------------------------------------------------

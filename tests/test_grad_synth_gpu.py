@@ -1,0 +1,170 @@
+"""GPU parity tests: eigenvalue-derivative kernels and modal synthesis vs the CPU oracle and the
+reference goldens.
+
+Tolerances: d(lambda)/dx <= 1e-5 relative L2 vs reference autograd; material quadratic
+forms <= 1e-5 relative; audio <= 1e-4 relative L2 vs the reference evaluated in fp64.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle import modal_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _mesh(meshes, name, order):
+    v, t = meshes[name]
+    pv, pt = mo.promote(torch.tensor(v), torch.tensor(t), order)
+    return pv, pt
+
+
+def _tables(order, density):
+    from diffsound_b200.diffelastic import mass_matrix as mmx
+    return mmx.stiffness_contraction_table(order).to(DEV), mmx.mass_density_table(order, density).to(DEV)
+
+
+@pytest.mark.parametrize("name,order", [("cube2", 1), ("cube2", 2), ("cube3", 1), ("cube3", 2), ("grid16", 1)])
+def test_shape_gradient_vs_reference_golden(meshes, name, order):
+    """Same U, lambda, upstream gradient as the reference run that produced the golden."""
+    from diffsound_b200 import native
+    g = golden(f"modal_{name}_o{order}")
+    rho, E, nu = g["material"][:3]
+    pv, pt = _mesh(meshes, name, order)
+    verts = pv.to(DEV).contiguous()
+    tets = pt.to(torch.int32).to(DEV).contiguous()
+    ctab, mtab = _tables(order, float(rho))
+    mu, lam = mo.lame(E, nu)
+    U = torch.tensor(g["U_hat"], device=DEV)
+    lamv = torch.tensor(g["eigenvalues"], device=DEV)
+    up = torch.tensor(g["upstream"].astype(np.float64), device=DEV)
+    inc_ptr, inc = native.corner_incidence(tets, order, verts.shape[0])
+    got = native.eigval_grad_shape(verts, tets, order, mu, lam, ctab, mtab, U, lamv, up, inc_ptr, inc).cpu().numpy()
+    # the reference's gradient is w.r.t. the ORIGINAL vertices; promoted node j came from allv[first[j]]
+    # (mesh.py:174-179): corner nodes map back to original vertices, mid-edge nodes carry no gradient.
+    ref = g["grad_verts"]
+    v0 = meshes[name][0]
+    if order == 1:
+        mapped = got
+    else:
+        # promoted corner node -> original vertex with identical coordinates
+        key = {tuple(x): i for i, x in enumerate(v0.tolist())}
+        mapped = np.zeros_like(ref)
+        pvn = pv.numpy()
+        for j in range(pvn.shape[0]):
+            i = key.get(tuple(pvn[j].tolist()))
+            if i is not None:
+                mapped[i] += got[j]
+            else:
+                assert np.all(got[j] == 0)
+    err = np.linalg.norm(mapped - ref) / np.linalg.norm(ref)
+    assert err <= 1e-5, err
+
+
+@pytest.mark.parametrize("name,order,k", [("cube3", 2, 16), ("grid16", 2, 16), ("bowl", 1, 16), ("grid16", 1, 38)])
+def test_shape_gradient_vs_oracle(meshes, name, order, k):
+    from diffsound_b200 import native
+    rho, E, nu = 7850.0, 2.0e11, 0.29
+    pv, pt = _mesh(meshes, name, order)
+    K, M = mo.assemble(pv, pt, order, E, nu, rho)
+    lam_h, U_h, _, _ = mo.eig_arpack(K, M, k)
+    gvec = 1.0 / lam_h
+    ref = mo.eigval_grad_shape(pv, pt, order, E, nu, rho, U_h, lam_h, gvec).numpy()
+    verts = pv.to(DEV).contiguous()
+    tets = pt.to(torch.int32).to(DEV).contiguous()
+    ctab, mtab = _tables(order, rho)
+    mu, lam = mo.lame(E, nu)
+    inc_ptr, inc = native.corner_incidence(tets, order, verts.shape[0])
+    # U as a column block of a wider buffer (the way the eigensolver hands it over)
+    wide = torch.zeros(U_h.shape[0], k + 10, dtype=torch.float64, device=DEV)
+    wide[:, 6:6 + k] = torch.tensor(U_h)
+    got = native.eigval_grad_shape(verts, tets, order, mu, lam, ctab, mtab, wide[:, 6:6 + k],
+                                   torch.tensor(lam_h, device=DEV), torch.tensor(gvec, device=DEV), inc_ptr,
+                                   inc).cpu().numpy()
+    err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+    assert err <= 1e-5, err
+    # incidence lists: every (tet, corner) exactly once, grouped by node
+    incn = inc.cpu().numpy()
+    assert np.array_equal(np.sort(incn), np.arange(4 * pt.shape[0]))
+
+
+@pytest.mark.parametrize("name,order,k", [("cube3", 1, 16), ("cube3", 2, 16), ("grid16", 2, 16), ("bowl", 1, 40)])
+def test_material_quadforms_vs_oracle(meshes, name, order, k):
+    from diffsound_b200 import native
+    from diffsound_b200.diffelastic import mass_matrix as mmx
+    rho = 2700.0
+    pv, pt = _mesh(meshes, name, order)
+    rng = np.random.default_rng(5)
+    U_h = rng.standard_normal((3 * pv.shape[0], k))
+    qmu, qla = mo.material_quadforms(pv, pt, order, U_h)
+    _, M = mo.assemble(pv, pt, order, 1.0, 0.3, rho)
+    qm = np.einsum("ik,ik->k", U_h, M @ U_h)
+    verts = pv.to(DEV).contiguous()
+    tets = pt.to(torch.int32).to(DEV).contiguous()
+    _, mtab = _tables(order, rho)
+    wsum = float(mmx.stiffness_contraction_table(1)[0, 0, 0, 0])
+    a, b, c = native.eigval_quadforms_material(verts, tets, order, mtab, wsum, torch.tensor(U_h, device=DEV))
+    assert np.abs(a.cpu().numpy() - qmu).max() <= 1e-5 * np.abs(qmu).max()
+    assert np.abs(b.cpu().numpy() - qla).max() <= 1e-5 * np.abs(qla).max()
+    assert np.abs(c.cpu().numpy() - qm).max() <= 1e-10 * np.abs(qm).max()
+
+
+def _rand_modes(k, seed=0):
+    rng = np.random.default_rng(seed)
+    f = np.sort(rng.uniform(100, 18000, k)).astype(np.float32)
+    alpha = np.exp(rng.uniform(np.log(0.6), np.log(60), k))
+    beta = np.exp(rng.uniform(np.log(1e-8), np.log(1e-6), k))
+    d, fd = mo.rayleigh_damping(f.astype(np.float64), alpha, beta)
+    return d.astype(np.float32), fd.astype(np.float32)
+
+
+@pytest.mark.parametrize("B,k,T,sr", [(1, 16, 8000, 32000), (3, 40, 5000, 44100), (4, 256, 88200, 44100),
+                                       (70, 33, 1001, 44100)])
+def test_synth_forward_vs_closed_form(B, k, T, sr):
+    from diffsound_b200 import native
+    d, fd = _rand_modes(k, seed=k)
+    rng = np.random.default_rng(1)
+    amp = rng.uniform(0.5, 1.5, (B, k)).astype(np.float32)
+    ref = mo.synth_closed_form(amp.astype(np.float64), d.astype(np.float64), fd.astype(np.float64), T, sr)
+    y = native.modal_synth_fwd(torch.tensor(amp, device=DEV), torch.tensor(d, device=DEV), torch.tensor(fd, device=DEV),
+                               T, sr).cpu().numpy()
+    err = np.linalg.norm(y - ref) / np.linalg.norm(ref)
+    assert err <= 1e-4, err
+    assert err <= 5e-6, err   # the kernel itself is far inside the budget
+
+
+@pytest.mark.parametrize("B,k,T,sr", [(2, 16, 4000, 32000), (5, 40, 9000, 44100), (66, 33, 700, 44100)])
+def test_synth_backward_vs_autograd(B, k, T, sr):
+    from diffsound_b200 import native
+    d, fd = _rand_modes(k, seed=3)
+    rng = np.random.default_rng(2)
+    amp = rng.uniform(0.5, 1.5, (B, k)).astype(np.float32)
+    gy = rng.standard_normal((B, T)).astype(np.float32)
+    a64 = torch.tensor(amp, dtype=torch.float64, requires_grad=True)
+    d64 = torch.tensor(d, dtype=torch.float64, requires_grad=True)
+    f64 = torch.tensor(fd, dtype=torch.float64, requires_grad=True)
+    tau = (torch.arange(T, dtype=torch.float64) + 1) / sr
+    y = (a64[:, :, None] * torch.exp(-d64[None, :, None] * tau) * torch.sin(2 * np.pi * f64[None, :, None] * tau)).sum(1)
+    (y * torch.tensor(gy, dtype=torch.float64)).sum().backward()
+    ga, gd, gf = native.modal_synth_bwd(torch.tensor(amp, device=DEV), torch.tensor(d, device=DEV),
+                                        torch.tensor(fd, device=DEV), torch.tensor(gy, device=DEV), sr)
+    for got, ref in ((ga, a64.grad), (gd, d64.grad), (gf, f64.grad)):
+        r = ref.numpy()
+        assert np.linalg.norm(got.cpu().numpy() - r) / np.linalg.norm(r) <= 1e-4
+
+
+def test_synth_vs_reference_golden():
+    """TraditionalDampedOscillator (reference, fp64) on the bowl frequencies, unit-impulse force."""
+    from diffsound_b200 import native
+    g = golden("oscillator")
+    k, T, sr, F = (int(x) for x in g["trad_meta"])
+    f = g["trad_freq"].reshape(-1).astype(np.float64)
+    d, fd = mo.rayleigh_damping(f, 6.0, 1e-7)          # MatSet.Ceramic alpha, beta
+    amp = np.ones((1, k), np.float32)
+    y = native.modal_synth_fwd(torch.tensor(amp, device=DEV), torch.tensor(d.astype(np.float32), device=DEV),
+                               torch.tensor(fd.astype(np.float32), device=DEV), T, sr).cpu().numpy()
+    ref = g["trad_audio_f64"]
+    assert np.linalg.norm(y - ref) / np.linalg.norm(ref) <= 1e-4
