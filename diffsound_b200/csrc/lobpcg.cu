@@ -223,7 +223,8 @@ int Driver::cheb_step_raw(double shift, const double* z, double* zprev_new, int 
 }
 
 int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats) {
-    const int nev = o.nev, nr = o.n_rigid;
+    const int nev = o.nev;
+    int nr = o.n_rigid < 0 ? 0 : o.n_rigid;
     DS_TRY(alloc());
     const double shift = o.sigma > 0.0 ? o.sigma : 0.0;
     DS_TRY(block_jacobi(brow, bcol, n_nodes, Kval, Mblk, shift, invD, st));
@@ -302,6 +303,11 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
         DS_CUDA(cudaMemcpyAsync(hn.data(), norms, 2 * m * sizeof(double), cudaMemcpyDeviceToHost, st));
         DS_CUDA(cudaMemcpyAsync(lam.data(), lam_d, m * sizeof(double), cudaMemcpyDeviceToHost, st));
         DS_CUDA(cudaStreamSynchronize(st));
+        if (o.n_rigid < 0) {   // automatic: leading eigenvalues that are numerically zero next to the block's largest
+            const double big = std::fabs(lam[m - 1]);
+            nr = 0;
+            while (nr < m - 1 && std::fabs(lam[nr]) < 1e-9 * big) ++nr;
+        }
         double lref = std::fabs(lam[std::min(nr, m - 1)]);
         act.clear();
         nconv = 0;
@@ -409,7 +415,7 @@ extern "C" int ds_lobpcg(ds_workspace* ws, const int32_t* brow, const int32_t* b
     DS_REQUIRE(3 * n_nodes >= 3 * (int64_t)m, "ds_lobpcg: matrix too small for block size (n=%lld, 3m=%d)",
                (long long)(3 * n_nodes), 3 * m);
     DS_REQUIRE(opts->cheb_degree >= 1 && opts->maxit >= 1 && opts->tol > 0, "ds_lobpcg: bad options");
-    DS_REQUIRE(opts->n_rigid >= 0 && opts->n_rigid <= opts->nev, "ds_lobpcg: bad n_rigid");
+    DS_REQUIRE(opts->n_rigid >= -1 && opts->n_rigid <= opts->nev, "ds_lobpcg: bad n_rigid");
     Driver d;
     d.ws = ws;
     d.st = (cudaStream_t)stream;

@@ -134,7 +134,7 @@ typedef struct ds_lobpcg_opts {
     double tol;         /* ||K x - lam M x|| / (lam ||M x||) */
     double sigma;       /* shift for the preconditioner / RR (<=0: automatic) */
     double cheb_ratio;  /* lmax / lmin of the Chebyshev interval */
-    int n_rigid;        /* leading columns that hold (near-)null-space vectors */
+    int n_rigid;        /* leading columns that hold (near-)null-space vectors; -1: detect */
     int verbose;
 } ds_lobpcg_opts;
 int ds_lobpcg(ds_workspace* ws, const int32_t* brow, const int32_t* bcol, int64_t n_nodes,

@@ -1,0 +1,221 @@
+"""GPU parity tests of the reference-facing API (DiffSoundObj, oscillators, lobpcg, cuda_module)
+against goldens produced by the unmodified reference (oracle/make_goldens.py).
+
+Tolerances (BASELINE.json north_star / SURVEY.md A.6):
+  pattern / node numbering   bit-exact (sha256 of the int64 arrays)
+  eigenvalues                <= 1e-6 relative
+  get_vals (fp32)            <= 2e-7 relative (one fp32 rounding) + eigenvalue tolerance
+  d(lambda)/d(vertices)      <= 1e-5 relative L2
+  d f / d(E, nu logits)      <= 1e-5 relative L2 (2e-4 where the reference's own fp32 path limits it)
+  audio                      <= 1e-4 relative L2 vs the reference in fp64
+"""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _obj(meshes, name, order, g, requires_grad=True):
+    from diffsound_b200.diffelastic.diff_model import DiffSoundObj
+    v, t = meshes[name]
+    leaf = torch.tensor(v, device=DEV).requires_grad_(requires_grad)
+    obj = DiffSoundObj(leaf, torch.tensor(t, device=DEV).long(), mode_num=int(g["k"]), order=order,
+                       mat=tuple(g["material"]))
+    return leaf, obj
+
+
+@pytest.mark.parametrize("name,order", [("cube2", 1), ("cube2", 2), ("cube3", 1), ("cube3", 2), ("grid16", 1),
+                                        ("grid16", 2), ("bowl", 1), ("bowl", 2)])
+def test_diffsoundobj_matches_reference(meshes, name, order):
+    g = golden(f"modal_{name}_o{order}")
+    has_grad = g["grad_verts"].size > 0
+    leaf, obj = _obj(meshes, name, order, g, requires_grad=has_grad)
+    # node numbering of the promoted mesh and the coalesced sparsity pattern: bit-exact
+    assert _sha(obj.tetmesh.vertices.detach().cpu().numpy()) == str(g["pverts_sha"])
+    assert _sha(obj.tetmesh.tets.cpu().numpy().astype(np.int64)) == str(g["ptets_sha"])
+    obj.eigen_decomposition()
+    K, M = obj.stiff_matrix, obj.mass_matrix
+    assert K.is_coalesced() and K.dtype == torch.float64 and K.indices().dtype == torch.int64
+    idx = K.indices().cpu().numpy()
+    n = K.shape[0]
+    crow = np.concatenate([[0], np.cumsum(np.bincount(idx[0], minlength=n))]).astype(np.int64)
+    assert _sha(crow) == str(g["crow_sha"]) and _sha(idx[1].astype(np.int64)) == str(g["col_sha"])
+    assert torch.equal(M.indices(), K.indices())
+    kv, mv = K.values().cpu().numpy(), M.values().cpu().numpy()
+    s = g["sample_idx"]
+    assert np.abs(kv[s] - g["K_sample"]).max() <= 2e-6 * float(g["K_absmax"])
+    assert np.allclose(mv[s], g["M_sample"], rtol=1e-12, atol=0)
+    assert abs(mv.sum() - float(g["M_sum"])) <= 1e-10 * float(g["M_sum"])
+    # eigenvalues
+    lam = obj.eigenvalues.cpu().numpy()
+    assert obj.eigenvalues.dtype == torch.float64 and lam.shape == (int(g["k"]),)
+    assert (np.abs(lam - g["eigenvalues"]) / g["eigenvalues"]).max() <= 1e-6
+    U = obj.U_hat
+    assert U.shape == (n, int(g["k"])) and obj.U_hat_full.shape == (n, int(g["k"]) + 6)
+    MU = (M @ U)
+    assert float((U.T @ MU - torch.eye(U.shape[1], device=DEV, dtype=torch.float64)).abs().max()) <= 1e-8
+    # differentiable eigenvalues
+    vals = obj.get_vals()
+    assert vals.shape == (int(g["k"]), 1) and vals.dtype == torch.float32
+    assert (np.abs(vals.detach().cpu().numpy() - g["get_vals"]) / g["get_vals"]).max() <= 1.2e-6
+    if has_grad:
+        up = torch.tensor(g["upstream"], device=DEV)
+        (vals[:, 0] * up).sum().backward()
+        got, ref = leaf.grad.cpu().numpy(), g["grad_verts"]
+        assert got.dtype == np.float32 and got.shape == ref.shape
+        assert np.linalg.norm(got - ref) / np.linalg.norm(ref) <= 1e-5
+
+
+def test_eigenvectors_span_reference_subspace(meshes):
+    """U_hat vs ARPACK's U_hat of the reference: compare projectors per cluster of close eigenvalues."""
+    g = golden("modal_cube3_o2")
+    _, obj = _obj(meshes, "cube3", 2, g, requires_grad=False)
+    obj.eigen_decomposition()
+    U, Uref = obj.U_hat.cpu().numpy(), g["U_hat"]
+    M = obj.mass_matrix.to_dense().cpu().numpy()
+    lam = g["eigenvalues"]
+    start = 0
+    for i in range(1, len(lam) + 1):
+        if i == len(lam) or (lam[i] - lam[i - 1]) > 1e-3 * lam[i]:
+            A, B = U[:, start:i], Uref[:, start:i]
+            # singular values of A^T M B are the cosines of the principal angles
+            s = np.linalg.svd(A.T @ M @ B, compute_uv=False)
+            assert s.min() >= 1 - 1e-6, (start, i, s)
+            start = i
+
+
+@pytest.mark.parametrize("name,order", [("cube3", 2), ("grid16", 1), ("bowl", 1)])
+def test_material_path_matches_reference(meshes, name, order):
+    from diffsound_b200.diffelastic.diff_model import DiffSoundObj, TrainableLinear
+    g = golden(f"material_{name}_o{order}")
+    v, t = meshes[name]
+    obj = DiffSoundObj(torch.tensor(v, device=DEV), torch.tensor(t, device=DEV).long(), mode_num=int(g["k"]),
+                       order=order, mat=tuple(g["material"]), mat_model=TrainableLinear, task="material")
+    mm = obj.material_model
+    assert np.allclose(mm.youngs_list.numpy(), g["youngs_list"], rtol=1e-6)
+    assert np.allclose(mm.poisson_list.numpy(), g["poisson_list"], rtol=1e-6)
+    with torch.no_grad():
+        mm.youngs.probablity.copy_(torch.tensor(g["youngs_logits0"]))
+        mm.poisson.probablity.copy_(torch.tensor(g["poisson_logits0"]))
+    assert abs(float(mm.youngs()) - float(g["E0"])) <= 1e-6 * float(g["E0"])
+    obj.eigen_decomposition()
+    lam = obj.eigenvalues.cpu().numpy()
+    assert (np.abs(lam - g["eigenvalues0"]) / g["eigenvalues0"]).max() <= 1e-6
+    f0 = obj.get_undamped_freqs()
+    assert f0.shape == (int(g["k"]), 1) and f0.dtype == torch.float32
+    assert (np.abs(f0.detach().cpu().numpy() - g["freqs0"]) / g["freqs0"]).max() <= 2e-6
+    with torch.no_grad():
+        mm.youngs.probablity.copy_(torch.tensor(g["youngs_logits1"]))
+        mm.poisson.probablity.copy_(torch.tensor(g["poisson_logits1"]))
+    f1 = obj.get_undamped_freqs()
+    assert (np.abs(f1.detach().cpu().numpy() - g["freqs1"]) / g["freqs1"]).max() <= 2e-6
+    w = torch.tensor(g["weights"], device=DEV)
+    (f1 * w / f1.detach()).sum().backward()
+    for got, ref in ((mm.youngs.probablity.grad, g["grad_youngs_logits"]), (mm.poisson.probablity.grad, g["grad_poisson_logits"])):
+        assert np.linalg.norm(got.numpy() - ref) / np.linalg.norm(ref) <= 2e-4
+    # stiff_func keeps the reference semantics: K(theta) x for (n,) and (n, k) inputs
+    x = obj.U_hat[:, :3].float()
+    y = obj.stiff_func(x)
+    assert y.shape == x.shape and y.dtype == torch.float32
+    y1 = obj.stiff_func(x[:, 0])
+    assert y1.shape == (x.shape[0],)
+    assert torch.allclose(y1, y[:, 0], rtol=1e-5, atol=1e-5 * float(y.abs().max()))
+
+
+def test_oscillators_match_reference():
+    from diffsound_b200.ddsp import oscillator as osc
+    from diffsound_b200.diffelastic.material_model import Material, MatSet
+    g = golden("oscillator")
+    k, T, sr, F = (int(x) for x in g["trad_meta"])
+    f = torch.tensor(g["trad_freq"], device=DEV)
+    force = torch.zeros(1, F, device=DEV)
+    force[0, 0] = 1
+    o = osc.TraditionalDampedOscillator(force, 1, k, T, sr, Material(MatSet.Ceramic))
+    fi = f.clone().requires_grad_(True)
+    y = o(fi)
+    assert y.shape == (1, T) and y.dtype == torch.float32
+    ref = g["trad_audio_f64"]
+    assert np.linalg.norm(y.detach().cpu().numpy() - ref) / np.linalg.norm(ref) <= 1e-4
+    (0.5 * (y ** 2).sum()).backward()
+    gr = g["trad_gradf_f64"]
+    assert np.linalg.norm(fi.grad.cpu().numpy() - gr) / np.linalg.norm(gr) <= 1e-3
+    assert o.damped_freq.shape == (1, k, T)
+    assert np.allclose(o.damped_freq[:, :, 0].detach().cpu().numpy(), g["trad_damped_freq_f64"], rtol=1e-6)
+    # non-trivial force on two audios
+    force2 = torch.tensor(g["trad2_force"], device=DEV, dtype=torch.float32)
+    o2 = osc.TraditionalDampedOscillator(force2, 2, k, T, sr, Material(MatSet.Glass))
+    y2 = o2(f).detach().cpu().numpy()
+    assert np.linalg.norm(y2 - g["trad2_audio_f64"]) / np.linalg.norm(g["trad2_audio_f64"]) <= 1e-4
+    # DampedOscillator with learnable amplitude / alpha / beta
+    B = 3
+    forceB = torch.zeros(B, F, device=DEV)
+    forceB[:, 0] = 1
+    o3 = osc.DampedOscillator(forceB, B, k, T, sr, [0.0, 1.0], Material(MatSet.Ceramic))
+    with torch.no_grad():
+        o3.amp.value.copy_(torch.tensor(g["damped_amp_param"], dtype=torch.float32))
+        o3.alpha.params.copy_(torch.tensor(g["damped_alpha_param"], dtype=torch.float32))
+        o3.beta.params.copy_(torch.tensor(g["damped_beta_param"], dtype=torch.float32))
+    fi = f.clone().requires_grad_(True)
+    y3 = o3(fi)
+    ref = g["damped_audio_f64"]
+    assert np.linalg.norm(y3.detach().cpu().numpy() - ref) / np.linalg.norm(ref) <= 1e-4
+    (0.5 * (y3 ** 2).sum()).backward()
+    for got, key, tol in ((fi.grad, "damped_gradf", 1e-3), (o3.amp.value.grad, "damped_grad_amp", 1e-4),
+                          (o3.alpha.params.grad, "damped_grad_alpha", 1e-3), (o3.beta.params.grad, "damped_grad_beta", 1e-3)):
+        r = g[key]
+        assert np.linalg.norm(got.cpu().numpy() - r) / np.linalg.norm(r) <= tol, key
+    assert np.allclose(o3.damped_freq[0, :, 0].detach().cpu().numpy(), g["damped_damped_freq"], rtol=1e-6)
+
+
+def test_lobpcg_api_on_torch_sparse(meshes):
+    """lobpcg_func(K, M, k + 6, largest=False) as src/utils/utils.py:80-90 calls it."""
+    from diffsound_b200.lobpcg import lobpcg, lobpcg_func
+    g = golden("modal_grid16_o1")
+    _, obj = _obj(meshes, "grid16", 1, g, requires_grad=False)
+    obj._assemble(float(g["material"][0]))
+    K, M = obj.stiff_matrix, obj.mass_matrix
+    k = int(g["k"])
+    vals, vecs = lobpcg_func(K, M, k + 6, niter=500, tol=1e-5, largest=False)
+    assert vals.shape == (k + 6,) and vecs.shape == (K.shape[0], k + 6)
+    lam = vals[6:].cpu().numpy()
+    assert (np.abs(lam - g["eigenvalues"]) / g["eigenvalues"]).max() <= 1e-6
+    assert np.all(np.diff(vals.cpu().numpy()) >= -1e-3)
+    vals2, vecs2, rerr = lobpcg(K.float(), k + 6, M.float(), niter=500, tol=1e-5, largest=False, return_rerr=True)
+    assert vals2.dtype == torch.float32 and rerr.shape == (k + 6,)
+    assert (np.abs(vals2[6:].cpu().numpy() - g["eigenvalues"]) / g["eigenvalues"]).max() <= 1e-5
+    with pytest.raises(NotImplementedError):
+        lobpcg(K, k, M)          # largest defaults to True in the reference API
+    with pytest.raises(ValueError):
+        bad = torch.sparse_coo_tensor(K.indices(), torch.ones_like(K.values()), K.shape).coalesce()
+        lobpcg(K, k, bad, largest=False)
+
+
+def test_cuda_module_names(meshes):
+    from diffsound_b200 import cuda_module
+    from diffsound_b200.diffelastic.mass_matrix import get_elememt_mass_matrix
+    fn = cuda_module.CUDA_MODULE.get("assemble_mass_matrix")
+    assert fn is cuda_module.mass_matrix_assembler
+    assert cuda_module.CUDA_MODULE.load(Debug=True, MemoryCheck=True, Verbose=False) is cuda_module.CUDA_MODULE._module
+    v, t = meshes["cube2"]
+    T = t.shape[0]
+    vertices = torch.tensor(v, device=DEV).double().reshape(-1)
+    tets = torch.tensor(t, device=DEV).to(torch.int32).reshape(-1)
+    emm = get_elememt_mass_matrix(1).double().to(DEV)
+    values = torch.zeros(144 * T, dtype=torch.float64, device=DEV)
+    rows = torch.zeros(144 * T, dtype=torch.int32, device=DEV)
+    cols = torch.zeros_like(rows)
+    fn(vertices, tets, values, rows, cols, emm, 1000.0, 1)
+    # total mass: sum of all entries / 3 = rho * volume (unit cube)
+    assert abs(float(values.sum()) / 3 - 1000.0) <= 1e-3
+    with pytest.raises(RuntimeError):
+        fn(vertices, tets, values, rows, cols, emm, 1000.0, 7)
