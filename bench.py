@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""Headline benchmark: modal solves/s on the synthetic 200k quadratic-tet cube (BASELINE.json
+configs[2]).
+
+One step = one modal solve of the hot path, from vertex positions already on the device:
+    sparsity pattern + fused K/M assembly  ->  LOBPCG, 32 elastic modes (+6 rigid), cold start
+    ->  get_vals() forward  ->  backward to all vertex positions (upstream grad 1/lambda).
+`value` times that with CUDA events (inputs resident in HBM); `e2e` times the same through the public
+API (`DiffSoundObj`) from pinned HOST buffers: H2D of the linear mesh, linear->quadratic promotion,
+solve, D2H of eigenvalues and the vertex gradient.
+
+N > 1 (torchrun): the path shards by independent candidates (the thickness / material sweeps of the
+reference) -- every rank solves its own mesh, no data-path collective; NCCL is
+used for the barriers and the max-over-ranks timing only ("scaling": "weak").
+
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/, kind "port": the
+reference itself is Python + SciPy ARPACK and cannot travel to the GPU box) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "modal solves/s (assemble+LOBPCG k=32+dlambda/dtheta) @200k ord-2 tets"
+UNIT = "solves/s"
+STEEL = (7850.0, 2.0e11, 0.29, 20, 3e-8)
+CUBE_N = 32          # 32^3 cells x 6 Kuhn tets = 196 608 tets
+MODES = 32
+
+
+def kuhn_cube(N):
+    """Synthetic procedurally tetrahedralised cube: (N+1)^3 grid on [0,1]^3,
+    six Kuhn tets per cell, permutation-major.  numpy, host side."""
+    import itertools
+    import numpy as np
+    lin = np.linspace(0.0, 1.0, N + 1, dtype=np.float32)
+    gx, gy, gz = np.meshgrid(lin, lin, lin, indexing="ij")
+    verts = np.stack([gx, gy, gz], axis=-1).reshape(-1, 3).astype(np.float32)
+    ii, jj, kk = np.meshgrid(np.arange(N), np.arange(N), np.arange(N), indexing="ij")
+    base = np.stack([ii, jj, kk], axis=-1).reshape(-1, 3)
+    tets = []
+    for perm in itertools.permutations(range(3)):
+        p = base.copy()
+        ids = [(p[:, 0] * (N + 1) + p[:, 1]) * (N + 1) + p[:, 2]]
+        for ax in perm:
+            p = p.copy()
+            p[:, ax] += 1
+            ids.append((p[:, 0] * (N + 1) + p[:, 1]) * (N + 1) + p[:, 2])
+        tets.append(np.stack(ids, axis=1))
+    return verts, np.concatenate(tets, axis=0).astype(np.int64)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        import statistics
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        reasons = []
+        for i, name in ((3, "hw_slowdown"), (4, "hw_thermal_slowdown"), (5, "sw_thermal_slowdown"), (6, "sw_power_cap")):
+            if any(len(s) > i and s[i].lower().startswith("active") for s in self.samples):
+                reasons.append(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle's restatement of the reference algorithm on the host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_solve(N, order, k, threads):
+    """One modal solve with the reference algorithm on the CPU: fp64 COO-free assembly, SciPy ARPACK
+    shift-invert (sigma = 20000, as diff_model.py:356-358), eigenvalue gradient by autograd."""
+    import numpy as np
+    import torch
+    from oracle import modal_oracle as mo
+    torch.set_num_threads(threads)
+    v, t = mo.kuhn_cube(N)
+    t0 = time.perf_counter()
+    pv, pt = mo.promote(v, t, order)
+    K, M = mo.assemble(pv, pt, order, STEEL[1], STEEL[2], STEEL[0])
+    lam, U, _, _ = mo.eig_arpack(K, M, k)
+    g = mo.eigval_grad_shape(pv, pt, order, STEEL[1], STEEL[2], STEEL[0], U, lam, 1.0 / lam)
+    dt = time.perf_counter() - t0
+    return dt, pt.shape[0], float(np.abs(g.numpy()).sum())
+
+
+def cpu_baseline(sample_N, steps=1, warmup=0):
+    threads = os.cpu_count() or 1
+    for _ in range(warmup):
+        cpu_reference_solve(sample_N, 2, MODES, threads)
+    ts = []
+    tets = 0
+    for _ in range(steps):
+        dt, tets, _ = cpu_reference_solve(sample_N, 2, MODES, threads)
+        ts.append(dt)
+    full_tets = 6 * CUBE_N ** 3
+    per_step = sum(ts) / len(ts)
+    # scaled to the metric's unit: time assumed linear in the number of tets (optimistic for the CPU
+    # path: SuperLU fill-in of a 3-D FEM matrix grows faster than linearly)
+    est_full = per_step * full_tets / tets
+    return {"value": 1.0 / est_full, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": (f"oracle (numpy/torch-CPU assembly + SciPy ARPACK shift-invert + autograd gradient) on a "
+                       f"{sample_N}^3x6 = {tets}-tet quadratic Kuhn cube, k={MODES}: {per_step:.2f} s/solve measured; "
+                       f"scaled linearly in tets to {full_tets} tets")}, per_step
+
+
+def run_reference_arm(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    sample_N = 8
+    t0 = time.perf_counter()
+    base, per_step = cpu_baseline(sample_N, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"synthetic {6 * CUBE_N ** 3}-tet quadratic Kuhn cube, {MODES} modes, shape gradient",
+                       "note": "CPU arm runs a bounded sample (see cpu_baseline.sample); ms_per_step is the sample's"},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--cube", type=int, default=CUBE_N, help="cells per side (default 32 -> 196 608 tets)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from diffsound_b200 import native
+    from diffsound_b200.diffelastic.diff_model import DiffSoundObj
+    from diffsound_b200.diffelastic.deform import Deform
+
+    # ---- synthetic input (host, pinned) and the device-resident copy for the kernel-only number
+    v_np, t_np = kuhn_cube(args.cube)
+    if world > 1:      # every rank owns a different candidate: same topology, perturbed geometry
+        rng = np.random.default_rng(rank)
+        v_np = (v_np + rng.uniform(-0.15, 0.15, v_np.shape).astype(np.float32) / args.cube *
+                ((v_np > 0) & (v_np < 1))).astype(np.float32)
+    v_host = torch.from_numpy(v_np).pin_memory()
+    t_host = torch.from_numpy(t_np).pin_memory()
+
+    def build(vh, th):
+        leaf = vh.to(dev, non_blocking=True).requires_grad_(True)
+        obj = DiffSoundObj(leaf, th.to(dev, non_blocking=True), mode_num=MODES, order=2, mat=STEEL)
+        return leaf, obj
+
+    leaf, obj = build(v_host, t_host)          # promoted mesh resident in HBM
+
+    def solve(obj, leaf):
+        """the hot path on device-resident inputs"""
+        obj.deform = Deform(obj.tetmesh)        # pattern + incidence lists rebuilt: nothing topological is cached
+        obj._X = None                           # cold start of the eigensolver
+        obj._Kval = obj._Mblk = None
+        obj.eigen_decomposition()
+        vals = obj.get_vals()
+        up = (1.0 / obj.eigenvalues).float()
+        leaf.grad = None
+        (vals[:, 0] * up).sum().backward()
+        return vals, leaf.grad
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        solve(obj, leaf)
+    lib = native._lib.load()
+    # ---- timed region (device time, CUDA events on the current stream = the kernels' stream)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = lib.ds_launch_count()
+    with native.prof() as pf:
+        e0.record()
+        for _ in range(args.steps):
+            vals, grad = solve(obj, leaf)
+        e1.record()
+        barrier()
+    prof = pf.read()
+    launches = int(lib.ds_launch_count() - launches0)
+    sampler.stop_flag = True
+    ms = e0.elapsed_time(e1)
+    tms = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+    ms_per_step = ms_max / args.steps
+    value = world * args.steps / (ms_max * 1e-3)
+    stats = obj.eig_stats
+
+    # ---- end to end through the public API from host buffers
+    e2e_steps = max(2, min(args.steps, 3))
+    barrier()
+    t_e2e = time.perf_counter()
+    for _ in range(e2e_steps):
+        lf, ob = build(v_host, t_host)
+        ob.eigen_decomposition()
+        vv = ob.get_vals()
+        (vv[:, 0] * (1.0 / ob.eigenvalues).float()).sum().backward()
+        lam_h = ob.eigenvalues.cpu()
+        grad_h = lf.grad.cpu()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_steps / float(e2e_s.item())
+    h2d = v_host.numel() * 4 + t_host.numel() * 8
+    d2h = lam_h.numel() * 8 + grad_h.numel() * 4
+
+    # ---- roofline of the dominant kernel class, from the event times of the timed region
+    pat = obj.deform.pattern
+    n, nnzb, n_nodes = pat.n, pat.nnzb, pat.n_nodes
+    roof = None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    dom = max(prof.items(), key=lambda kv: kv[1]["ms"])[0] if prof else None
+    if stats and "cheb_step" in prof:
+        # one Chebyshev step streams K (72 B), M (8 B) and bcol (4 B) per 3x3 block, brow and the 3x3
+        # block-Jacobi inverse per node, reads Z, Zprev, R and writes Znew (4 x n x c x 8 B).
+        c_avg = stats.get("cheb_cols_avg", 48)
+        steps_total = stats.get("cheb_steps", None)
+        if steps_total:
+            per_step_bytes = nnzb * 84 + n_nodes * (4 + 72) + 4 * n * c_avg * 8
+            t_avg = prof["cheb_step"]["ms"] / steps_total * 1e-3
+            roof = {"bound": "hbm", "kernel": "k_cheb_step (block-CSR SpMM fused with the Chebyshev update)",
+                    "achieved": per_step_bytes / t_avg / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": per_step_bytes / t_avg / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                    "launches": steps_total, "avg_cols": c_avg, "bytes_per_launch": per_step_bytes,
+                    "share_of_step": prof["cheb_step"]["ms"] / ms}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"synthetic {t_np.shape[0]}-tet quadratic Kuhn cube ({args.cube}^3 x 6), n={n} dofs, "
+                                   f"nnz={9 * nnzb}, {MODES} elastic modes (+6 rigid), shape gradient; "
+                                   "one independent mesh per GPU",
+                       "l2_policy": "inputs larger than L2 (K values alone 553 MB vs 126 MB L2); no flush needed",
+                       "eig_tol": DiffSoundObj.eig_tol, "lobpcg_iterations": stats["iterations"] if stats else None,
+                       "pattern_rebuilt_each_step": True, "eigensolver_cold_start": True},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps},
+            "gpu_launches": launches, "clocks": sampler.summary(),
+            "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
+            "roofline": roof}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"], _ = cpu_baseline(7)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -55,6 +55,12 @@ SIGNATURES = {
     "ds_eigval_quadforms_material": (cint, [f32p, i32p, i64, cint, f64p, dbl, f64p, i64, cint, f64p, f64p, ptr]),
     "ds_synth_scratch_elems": (i64, [i64, cint, i64]),
     "ds_modal_synth_fwd": (cint, [f32p, f32p, f32p, i64, cint, i64, dbl, f32p, f32p, ptr]),
+    "ds_prof_enable": (cint, [cint]),
+    "ds_prof_reset": (cint, []),
+    "ds_prof_num_classes": (cint, []),
+    "ds_launch_count": (i64, []),
+    "ds_prof_class_name": (C.c_char_p, [cint]),
+    "ds_prof_read": (cint, [cint, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "ds_modal_synth_bwd": (cint, [f32p, f32p, f32p, f32p, i64, cint, i64, dbl, f32p, f32p, f32p, f32p, ptr]),
 }
 

@@ -239,6 +239,7 @@ extern "C" int ds_assemble_km(const float* verts, const int32_t* tets, int64_t T
                "ds_assemble_km: null argument");
     DS_REQUIRE(T > 0 && n_nodes > 0, "ds_assemble_km: empty mesh");
     int npe = order == 1 ? 4 : 10;
+    ProfScope prof(PROF_ASSEMBLE, stream);
     k_tet_geometry<<<(unsigned)ceil_div(T, 128), 128, 0, stream>>>(verts, tets, T, npe, order, geom);
     DS_LAUNCH_CHECK();
     unsigned blocks = (unsigned)ceil_div(n_nodes * 32, 256);

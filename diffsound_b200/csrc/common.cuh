@@ -14,6 +14,7 @@
 namespace ds {
 
 void set_error(const char* fmt, ...);
+void count_launch();
 
 inline int check_cuda(cudaError_t e, const char* what, const char* file, int line) {
     if (e == cudaSuccess) return DS_OK;
@@ -27,7 +28,12 @@ inline int check_cuda(cudaError_t e, const char* what, const char* file, int lin
         if (_rc != DS_OK) return _rc;                                          \
     } while (0)
 
-#define DS_LAUNCH_CHECK() DS_CUDA(cudaGetLastError())
+// every kernel launch of the library is followed by this: error check + launch counter
+#define DS_LAUNCH_CHECK()                                                      \
+    do {                                                                       \
+        ::ds::count_launch();                                                  \
+        DS_CUDA(cudaGetLastError());                                           \
+    } while (0)
 
 #define DS_REQUIRE(cond, ...)                                                  \
     do {                                                                       \
@@ -62,6 +68,21 @@ struct Arena {
         return reinterpret_cast<T*>(base + off);
     }
     void release();
+};
+
+// Per-kernel-class device timing (CUDA events on the launch stream), off by default.
+// bench.py turns it on to attribute the step to kernels without a profiler attached.
+enum ProfClass {
+    PROF_PATTERN = 0, PROF_GEOMETRY, PROF_ASSEMBLE, PROF_SPMM, PROF_CHEB, PROF_GRAM, PROF_GEMM, PROF_EIGH,
+    PROF_RESIDUAL, PROF_COPY, PROF_GRAD, PROF_QUADFORM, PROF_SYNTH, PROF_OTHER, PROF_NCLASS
+};
+bool prof_enabled();
+void prof_begin(int cls, cudaStream_t s);
+void prof_end(int cls, cudaStream_t s);
+struct ProfScope {
+    int cls; cudaStream_t s; bool on;
+    ProfScope(int c, cudaStream_t st) : cls(c), s(st), on(prof_enabled()) { if (on) prof_begin(cls, s); }
+    ~ProfScope() { if (on) prof_end(cls, s); }
 };
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -208,6 +208,7 @@ int gram_f64(const double* A, int64_t lda, int p, const double* B, int64_t ldb, 
     int ps = pad8mod16(p), qs = pad8mod16(q);
     size_t smem = (size_t)GRAM_STAGES * GRAM_ROWS * (ps + qs) * sizeof(double) + 2 * GRAM_STAGES * sizeof(uint64_t);
     int ctas = gram_ctas(n);
+    ProfScope prof(PROF_GRAM, stream);
     int ntile = (p / 8) * (q / 8);
     int maxt = (ntile + 7) / 8;
     auto launch = [&](auto kern) -> int {
@@ -287,6 +288,7 @@ int block_gemm_f64(const double* A, int64_t lda, int p, const double* C, int64_t
     DS_REQUIRE(ldy % 2 == 0 && ((uintptr_t)Y % 16 == 0), "block_gemm: Y must be 16-byte aligned, even ldy");
     DS_REQUIRE(A != Y, "block_gemm: A must not alias Y");
     int qs = pad8mod16(q);
+    ProfScope prof(PROF_GEMM, stream);
     size_t smem = (size_t)p * qs * sizeof(double);
     int64_t strips = (n + 7) / 8;
     int ctas = (int)std::min<int64_t>((strips + 7) / 8, 148 * 4);
@@ -516,6 +518,7 @@ int eigh_generalized_f64(const double* GK, const double* GM, int N, int64_t ldg,
                          double* theta, double* C, int64_t ldc, double* scratch, int* info, cudaStream_t stream) {
     DS_REQUIRE(N >= 2 && N <= EIG_MAXN, "eigh_generalized: N=%d must be in [2,%d]", N, EIG_MAXN);
     DS_REQUIRE(GK && GM && theta && C && scratch && info, "eigh_generalized: null argument");
+    ProfScope prof(PROF_EIGH, stream);
     EigIdx ix;
     for (int i = 0; i < EIG_MAXN; ++i) ix.v[i] = (short)(i < N ? (idx_host ? idx_host[i] : i) : 0);
     size_t smem = ((size_t)N * (N + 2) + 2 * N) * sizeof(double) + (N + 4) * sizeof(int);

@@ -482,6 +482,7 @@ extern "C" int ds_corner_incidence(ds_workspace* ws, const int32_t* tets, int64_
     DS_REQUIRE((order == 1 && npe == 4) || (order == 2 && npe == 10), "ds_corner_incidence: order/npe mismatch");
     DS_REQUIRE(T > 0 && n_nodes > 0 && 4 * T < (int64_t)2147483647, "ds_corner_incidence: bad sizes");
     int64_t nq = 4 * T;
+    ProfScope prof(PROF_PATTERN, stream);
     int end_bit = 1;
     while (end_bit < 32 && ((int64_t)1 << end_bit) < n_nodes) ++end_bit;
     size_t tmp = 0;
@@ -514,6 +515,7 @@ extern "C" int ds_eigval_grad_shape(const float* verts, const int32_t* tets, int
                "ds_eigval_grad_shape: null argument");
     DS_REQUIRE(T > 0 && n_nodes > 0 && k > 0 && k <= 1024 && ldu >= k, "ds_eigval_grad_shape: bad sizes");
     const int kpad = (k + 15) & ~15;
+    ProfScope prof(PROF_GRAD, stream);
     int64_t ctas64 = ceil_div(T, GS_WARPS);
     int ctas = (int)(ctas64 < 148 * 8 ? ctas64 : 148 * 8);
     if (order == 1) {
@@ -543,6 +545,7 @@ extern "C" int ds_eigval_quadforms_material(const float* verts, const int32_t* t
     DS_REQUIRE(verts && tets && mtab && U && partial && out, "ds_eigval_quadforms_material: null argument");
     DS_REQUIRE(T > 0 && k > 0 && ldu >= k, "ds_eigval_quadforms_material: bad sizes");
     int ctas = qf_ctas(T);
+    ProfScope prof(PROF_QUADFORM, stream);
     if (order == 1)
         k_quadforms<1><<<ctas, QF_WARPS * 32, 0, stream>>>(verts, tets, T, mtab, wsum, U, ldu, k, partial);
     else

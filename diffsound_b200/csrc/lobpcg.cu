@@ -119,7 +119,7 @@ struct Driver {
     double *GK, *GM, *Cm, *theta, *eig_scratch, *gram_partial, *norm_partial, *norms, *lam_d;
     int* info_d;
     int cur = 0;
-    int64_t spmm_count = 0;
+    int64_t spmm_count = 0, cheb_launches = 0, cheb_cols = 0;
     int norm_ctas = 296;
 
     int alloc() {
@@ -296,10 +296,11 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
     const size_t res_smem = (size_t)(res_threads / m) * 2 * m * sizeof(double);
     for (it = 0; it <= o.maxit; ++it) {
         // ---- residual and convergence
+        { ProfScope prof(PROF_RESIDUAL, st);
         k_residual<<<norm_ctas, res_threads, res_smem, st>>>(KS[cur], MS[cur], ld, m, n, lam_d, R, m, norm_partial);
         DS_LAUNCH_CHECK();
         k_colsum_reduce<<<1, 256, 0, st>>>(norm_partial, norm_ctas, 2 * m, norms);
-        DS_LAUNCH_CHECK();
+        DS_LAUNCH_CHECK(); }
         DS_CUDA(cudaMemcpyAsync(hn.data(), norms, 2 * m * sizeof(double), cudaMemcpyDeviceToHost, st));
         DS_CUDA(cudaMemcpyAsync(lam.data(), lam_d, m * sizeof(double), cudaMemcpyDeviceToHost, st));
         DS_CUDA(cudaStreamSynchronize(st));
@@ -333,13 +334,17 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
         ColIdx ci;
         for (int s = 0; s < 128; ++s) ci.v[s] = (short)(s < na ? act[s] : 0);
         // ---- W = T(R[:, act])
+        { ProfScope prof(PROF_COPY, st);
         k_gather_cols<<<(unsigned)ceil_div(n * wpad, 256), 256, 0, st>>>(R, m, ci, na, wpad, n, Rc, wpad);
-        DS_LAUNCH_CHECK();
+        DS_LAUNCH_CHECK(); }
         double* Zres = nullptr;
         DS_TRY(cheb_precond(brow, bcol, n_nodes, Kval, Mblk, shift, invD, lmin, lmax, o.cheb_degree, Rc, wpad, wpad, Z0,
                             Z1, wpad, &Zres, st));
         spmm_count += o.cheb_degree - 1;
-        DS_CUDA(cudaMemcpy2DAsync(Wb(cur), ld * 8, Zres, wpad * 8, wpad * 8, n, cudaMemcpyDeviceToDevice, st));
+        cheb_launches += o.cheb_degree;
+        cheb_cols += (int64_t)o.cheb_degree * wpad;
+        { ProfScope prof(PROF_COPY, st);
+        DS_CUDA(cudaMemcpy2DAsync(Wb(cur), ld * 8, Zres, wpad * 8, wpad * 8, n, cudaMemcpyDeviceToDevice, st)); }
         // ---- W <- W - X (MX^T W)
         DS_TRY(gram_f64(MS[cur], ld, m, Wb(cur), ld, wpad, n, GK, 144, gram_partial, st));
         DS_TRY(block_gemm_f64(Xb(cur), ld, m, GK, 144, wpad, n, -1.0, 1.0, Wb(cur), ld, st));
@@ -398,6 +403,9 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
     stats[1] = nconv;
     stats[2] = spmm_count;
     stats[3] = status;
+    stats[4] = cheb_launches;
+    stats[5] = cheb_cols;
+    stats[6] = stats[7] = 0;
     return DS_OK;
 }
 

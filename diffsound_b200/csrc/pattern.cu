@@ -149,6 +149,7 @@ extern "C" int ds_pattern_count(ds_workspace* ws, const int32_t* tets, int64_t T
     DS_REQUIRE(T > 0 && n_nodes > 0, "ds_pattern_count: empty mesh (T=%lld, n_nodes=%lld)", (long long)T,
                (long long)n_nodes);
     int64_t n_pairs = T * npe * npe;
+    ProfScope prof(PROF_PATTERN, stream);
     DS_REQUIRE(n_pairs < (int64_t)2147483647, "ds_pattern_count: T*npe^2 = %lld exceeds int32", (long long)n_pairs);
     DS_REQUIRE(9 * n_pairs < (int64_t)1 << 40, "too large");
     int end_bit = 1;

@@ -247,6 +247,7 @@ int spmm_km(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, const dou
     if (beta == 0.0) { Y0 = Y; ldy0 = ldy; }
     unsigned g = row_blocks(n_nodes);
     int cpl = ncols / 16;
+    ProfScope prof(PROF_SPMM, stream);
     if (Kval && Mblk) {
         DS_DISPATCH_CPL(cpl, (k_spmm<CPL, true, true><<<g, 256, 0, stream>>>(brow, bcol, n_nodes, Kval, Mblk, shift, X,
                                                                             ldx, alpha, beta, Y0, ldy0, Y, ldy)));
@@ -269,6 +270,7 @@ int spmm_dual(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, const d
     DS_REQUIRE(brow && bcol && Kval && Mblk && X && YK && YM, "spmm_k_and_m: null argument");
     unsigned g = row_blocks(n_nodes);
     int cpl = ncols / 16;
+    ProfScope prof(PROF_SPMM, stream);
     DS_DISPATCH_CPL(cpl, (k_spmm_dual<CPL><<<g, 256, 0, stream>>>(brow, bcol, n_nodes, Kval, Mblk, X, ldx, YK, ldyk, YM,
                                                                   ldym)));
     DS_LAUNCH_CHECK();
@@ -291,6 +293,7 @@ int cheb_precond(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, cons
     int cpl = ncols / 16;
     double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sig = theta / delta;
     double rho = 1.0 / sig;
+    ProfScope prof(PROF_CHEB, stream);
     // z1 = (1/theta) invD R  -> Z0
     DS_DISPATCH_CPL(cpl, (k_cheb_step<CPL><<<g, 256, 0, stream>>>(brow, bcol, n_nodes, Kval, Mblk, shift, invD, R, ldr,
                                                                   Z0, Z0, ldz, 0.0, 1.0 / theta, 1)));
@@ -318,6 +321,7 @@ int cheb_single_step(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, 
     DS_REQUIRE(ncols > 0 && ncols % 16 == 0 && ncols <= 128, "cheb: ncols=%d must be a multiple of 16 <= 128", ncols);
     unsigned g = row_blocks(n_nodes);
     int cpl = ncols / 16;
+    ProfScope prof(PROF_CHEB, stream);
     DS_DISPATCH_CPL(cpl, (k_cheb_step<CPL><<<g, 256, 0, stream>>>(brow, bcol, n_nodes, Kval, Mblk, shift, invD, R, ldr, Z,
                                                                   Zprev_new, ldz, ab, cc, 0)));
     DS_LAUNCH_CHECK();

@@ -300,6 +300,7 @@ extern "C" int ds_modal_synth_fwd(const float* amp, const float* damp, const flo
     DS_REQUIRE(B > 0 && k > 0 && T > 0 && sr > 0, "ds_modal_synth_fwd: bad sizes (B=%lld k=%d T=%lld)", (long long)B, k,
                (long long)T);
     dim3 grid((unsigned)ceil_div(T, SY_BT), (unsigned)ceil_div(B, SY_BB));
+    ProfScope prof(PROF_SYNTH, stream);
     DS_REQUIRE(grid.y <= 65535, "ds_modal_synth_fwd: batch too large");
     k_synth_fwd<<<grid, SY_THREADS, 0, stream>>>(amp, damp, freq, B, k, T, 1.0 / sr, y);
     DS_LAUNCH_CHECK();
@@ -313,6 +314,7 @@ extern "C" int ds_modal_synth_bwd(const float* amp, const float* damp, const flo
     DS_REQUIRE(amp && damp && freq && gy && gamp && gdamp && gfreq && scratch, "ds_modal_synth_bwd: null argument");
     DS_REQUIRE(B > 0 && k > 0 && T > 0 && sr > 0, "ds_modal_synth_bwd: bad sizes");
     const int chunks = amp_chunks(T);
+    ProfScope prof(PROF_SYNTH, stream);
     const int64_t n_tiles = ceil_div(T, SY_BT);
     const int tiles_per_chunk = (int)ceil_div(n_tiles, chunks);
     dim3 g1((unsigned)chunks, (unsigned)ceil_div(B, SY_BB), (unsigned)ceil_div(k, SY_MK));

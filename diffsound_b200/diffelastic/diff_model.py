@@ -229,7 +229,7 @@ class DiffSoundObj:
     def _coo(self, values):
         idx = self.deform.pattern.coo_indices()
         n = self.deform.pattern.n
-        return torch.sparse_coo_tensor(idx, values, (n, n), is_coalesced=True)
+        return torch.sparse_coo_tensor(idx, values, (n, n), is_coalesced=True, check_invariants=False)
 
     @property
     def stiff_matrix(self):
@@ -317,6 +317,7 @@ class DiffSoundObj:
         self._X = X
         self.U_hat_full = X[:, :need]
         self.eigenvalues = lam[6:need].clone()
+        self.ritz_values = lam          # all block columns (rigid six, wanted modes, guard columns)
         self.U_hat = X[:, 6:need]
         self._q = None
 

@@ -254,12 +254,13 @@ def lobpcg(pattern, Kval, Mblk, X, nev, tol=1e-4, maxit=200, cheb_degree=8, sigm
     res = torch.empty(m, dtype=torch.float64, device=dev)
     opts = _lib.LobpcgOpts(nev=int(nev), maxit=int(maxit), cheb_degree=int(cheb_degree), tol=float(tol),
                            sigma=float(sigma), cheb_ratio=float(cheb_ratio), n_rigid=int(n_rigid), verbose=int(verbose))
-    stats = (C.c_int64 * 4)()
+    stats = (C.c_int64 * 8)()
     ws = workspace(dev)
     with torch.cuda.device(dev):
         _lib.check(lib.ds_lobpcg(ws.handle, _p(pattern.brow), _p(pattern.bcol), pattern.n_nodes, _p(Kval), _p(Mblk),
                                  _p(X), m, C.byref(opts), _p(lam), _p(res), stats, _stream()), "ds_lobpcg")
-    return lam, res, dict(iterations=int(stats[0]), converged=int(stats[1]), spmm=int(stats[2]), status=int(stats[3]))
+    return lam, res, dict(iterations=int(stats[0]), converged=int(stats[1]), spmm=int(stats[2]), status=int(stats[3]),
+                          cheb_steps=int(stats[4]), cheb_cols_avg=(stats[5] / stats[4] if stats[4] else 0.0))
 
 
 def corner_incidence(tets_i32, order, n_nodes):
@@ -339,3 +340,28 @@ def modal_synth_bwd(amp, damp, freq, gy, sr):
         _lib.check(lib.ds_modal_synth_bwd(_p(amp), _p(damp), _p(freq), _p(gy), B, k, T, float(sr), _p(gamp), _p(gdamp),
                                           _p(gfreq), _p(scratch), _stream()), "ds_modal_synth_bwd")
     return gamp, gdamp, gfreq
+
+
+class prof:
+    """Per-kernel-class device timing (ds_prof_*): `with native.prof() as p: ...; p.read()`."""
+
+    def __enter__(self):
+        lib = _lib.load()
+        lib.ds_prof_reset()
+        lib.ds_prof_enable(1)
+        return self
+
+    def __exit__(self, *exc):
+        _lib.load().ds_prof_enable(0)
+        return False
+
+    @staticmethod
+    def read():
+        lib = _lib.load()
+        out = {}
+        for c in range(lib.ds_prof_num_classes()):
+            ms, cnt = C.c_double(0), C.c_int64(0)
+            _lib.check(lib.ds_prof_read(c, C.byref(ms), C.byref(cnt)), "ds_prof_read")
+            if cnt.value:
+                out[lib.ds_prof_class_name(c).decode()] = {"ms": ms.value, "count": cnt.value}
+        return out

@@ -124,7 +124,8 @@ int ds_eigh_generalized_f64(const double* GK, const double* GM, int N, int64_t l
  * behind the lobpcg / lobpcg_func API mirror (src/lobpcg/_lobpcg.py:8-212).
  * X: fp64 [n x m] row-major start block on entry (m >= nev, multiple of 16),
  * M-orthonormal Ritz vectors on exit; lambda_out [m]; resid_out [m] relative
- * residuals; stats_host (host int64[4]) = {iterations, converged, spmm_count, status}.
+ * residuals; stats_host (host int64[8]) = {iterations, converged, spmm_count, status,
+ * chebyshev kernel launches, sum over those launches of the column count, 0, 0}.
  * Preconditioner: `cheb_degree` steps of block-Jacobi Chebyshev on K + sigma*M.
  * Synchronises the stream. */
 typedef struct ds_lobpcg_opts {
@@ -178,6 +179,19 @@ int ds_modal_synth_fwd(const float* amp, const float* damp, const float* freq, i
 int ds_modal_synth_bwd(const float* amp, const float* damp, const float* freq, const float* gy,
                        int64_t B, int k, int64_t T, double sr, float* gamp, float* gdamp,
                        float* gfreq, float* scratch, void* stream);
+
+/* ---- device-side timing per kernel class ---------------------------------------
+ * Replaces the reference's opt-in torch.profiler hook of lobpcg (src/lobpcg/_lobpcg.py:357-369)
+ * and the TICK/TOCK macros (src/include/macro.h:31-44): CUDA events around every launch site,
+ * accumulated per class ("spmm", "cheb_step", "gram", ...).  Off by default.  ds_prof_read
+ * synchronises on the recorded events. */
+int ds_prof_enable(int on);
+int ds_prof_reset(void);
+int ds_prof_num_classes(void);
+/* kernels launched by this library in this process so far (cub and memcpy/memset excluded) */
+int64_t ds_launch_count(void);
+const char* ds_prof_class_name(int cls);
+int ds_prof_read(int cls, double* ms, int64_t* count);
 
 #ifdef __cplusplus
 }

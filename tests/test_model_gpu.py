@@ -68,7 +68,13 @@ def test_diffsoundobj_matches_reference(meshes, name, order):
     vals = obj.get_vals()
     assert vals.shape == (int(g["k"]), 1) and vals.dtype == torch.float32
     assert (np.abs(vals.detach().cpu().numpy() - g["get_vals"]) / g["get_vals"]).max() <= 1.2e-6
-    if has_grad:
+    # sum_i g_i dlambda_i is basis-independent only if no cluster of equal eigenvalues is cut at k
+    # (cube2 order 1, k=6: lambda_6 = lambda_7); that case is covered with the reference's own U in
+    # test_grad_synth_gpu.py::test_shape_gradient_vs_reference_golden.
+    k = int(g["k"])
+    rv = obj.ritz_values.cpu().numpy()
+    cut = abs(rv[6 + k] - rv[6 + k - 1]) <= 1e-5 * rv[6 + k]
+    if has_grad and not cut:
         up = torch.tensor(g["upstream"], device=DEV)
         (vals[:, 0] * up).sum().backward()
         got, ref = leaf.grad.cpu().numpy(), g["grad_verts"]
