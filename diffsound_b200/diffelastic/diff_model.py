@@ -151,7 +151,9 @@ class _EigvalShape(torch.autograd.Function):
 
 class DiffSoundObj:
     #: options of the eigensolver (see ds_lobpcg_opts in include/diffsound_sm100.h)
-    eig_tol = 1e-4        # relative residual; eigenvalue error ~ tol^2
+    # relative residual ||K u - lam M u|| / (lam ||M u||).  Eigenvalue error ~ tol^2, eigenvector (and
+    # therefore d(lambda)/d(theta)) error ~ tol * lam / gap: 1e-5 keeps the gradient inside 1e-5.
+    eig_tol = 1e-5
     eig_maxit = 400
 
     def __init__(self, vertices=None, tets=None, mode_num=16, mat=MatSet.Ceramic, order=1, mat_model=FixedLinear,

@@ -1,0 +1,139 @@
+"""CPU tests of the host-side logic: the C-ABI library loads and exports every declared symbol, the
+constant tables, mesh promotion and I/O, and the product package never touches the oracle."""
+import ctypes
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, golden
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "diffsound_sm100.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ds_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from diffsound_b200 import _lib
+    syms = _header_symbols()
+    assert len(syms) >= 25
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/diffsound_sm100.h but not exported"
+    assert sorted(_lib.SIGNATURES) == syms, "ctypes table and header disagree"
+    loaded = _lib.load()
+    assert loaded.ds_version() >= 100
+    assert isinstance(_lib.last_error(), str)
+
+
+def test_no_compute_without_gpu_and_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from diffsound_b200 import native
+    with pytest.raises(RuntimeError):
+        native._p(torch.zeros(3))
+    from diffsound_b200.diffelastic.diff_model import DiffSoundObj
+    with pytest.raises(RuntimeError):
+        DiffSoundObj(torch.zeros(4, 3), torch.zeros(1, 4, dtype=torch.long))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "diffsound_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+                assert "/root/reference" not in txt.replace("/root/reference/src", "REFDOC") or f.endswith((".cu", ".cuh")), f
+
+
+def test_tables():
+    from diffsound_b200.diffelastic import gauss, mass_matrix as mmx, shape_func as sf
+    from oracle import modal_oracle as mo
+    for order in (1, 2):
+        pts, w = gauss.generate_gauss_points_weights(order + 2)
+        opts, ow = mo.gauss_rule(order + 2)
+        assert pts.dtype == np.float32 and np.array_equal(pts, opts) and np.array_equal(w, ow)
+        L = torch.from_numpy(pts)
+        assert torch.equal(sf.get_shape_function(L, order), mo.shape_fn(L, order))
+        assert torch.equal(sf.get_shape_function_grad(L, order), mo.shape_fn_grad(L, order))
+        assert torch.equal(mmx.calculate_element_mass_matrix(order, order + 2), mo.element_mass_table(order))
+        npe = sf.NODES_PER_TET[order]
+        full = mmx.get_elememt_mass_matrix(order)
+        assert full.shape == (9 * npe * npe,) and full.dtype == torch.float32
+        ct = mmx.stiffness_contraction_table(order)
+        assert ct.shape == (npe, npe, 4, 4) and ct.dtype == torch.float64
+        # sum over nodes of dN_a/dL_l is the derivative of the partition of unity: sum_a N_a = 1
+        # (exactly 1 for order 1; for order 2 it is 4 sum(L) - 1 + ... = constant) -> rows sum consistently
+        assert torch.allclose(ct, ct.permute(1, 0, 3, 2))
+    assert abs(float(mmx.stiffness_contraction_table(1)[0, 0, 0, 0]) - 1 / 6) <= 1e-7
+
+
+@pytest.mark.parametrize("name", ["cube2", "cube3", "grid16", "bowl"])
+def test_tetmesh_promotion_matches_reference(meshes, name):
+    from diffsound_b200.diffelastic.mesh import TetMesh
+    g = golden(f"modal_{name}_o2")
+    v, t = meshes[name]
+    leaf = torch.tensor(v, requires_grad=True)
+    m2 = TetMesh(leaf, torch.tensor(t)).to_high_order(2)
+    assert m2.order == 2 and m2.tets.shape[1] == 10 and m2.tets.dtype == torch.int64
+    assert _sha(m2.vertices.detach().numpy()) == str(g["pverts_sha"])
+    assert _sha(m2.tets.numpy()) == str(g["ptets_sha"])
+    # autograd link to the caller's vertices survives the renumbering (mesh.py:178)
+    m2.vertices.sum().backward()
+    assert leaf.grad is not None and leaf.grad.shape == leaf.shape
+    m1 = TetMesh(leaf, torch.tensor(t)).to_high_order(1)
+    assert m1.vertices is leaf and m1.order == 1
+    A = m2.transform_matrix
+    assert A.shape == (t.shape[0], 3, 3) and A.dtype == torch.float32
+    with pytest.raises(NotImplementedError):
+        TetMesh(leaf, torch.tensor(t)).to_high_order(3)
+
+
+def test_msh_roundtrip(tmp_path, meshes):
+    from diffsound_b200.diffelastic import mesh as M
+    v, t = meshes["cube2"]
+    p = str(tmp_path / "c.msh")
+    M.write_msh(p, v, t, "tetra")
+    pts, cells = M.read_msh(p)
+    assert np.array_equal(pts.astype(np.float32), v) and np.array_equal(cells["tetra"], t)
+    with pytest.raises(FileNotFoundError):
+        M.TetMesh.from_triangle_mesh(str(tmp_path / "missing.obj"))
+
+
+def test_bench_cube_matches_oracle_cube():
+    import bench
+    from oracle import modal_oracle as mo
+    v, t = bench.kuhn_cube(3)
+    ov, ot = mo.kuhn_cube(3)
+    assert np.array_equal(v, ov.numpy()) and np.array_equal(t, ot.numpy())
+
+
+def test_material_models_cpu_side():
+    from diffsound_b200.diffelastic.diff_model import TrainableLinear, FixedLinear
+    from diffsound_b200.diffelastic.material_model import Material, MatSet
+    fl = FixedLinear(Material(MatSet.Steel))
+    mu, lam = fl.lame()
+    assert abs(mu - 2.0e11 / (2 * 1.29)) < 1 and abs(lam - 2.0e11 * 0.29 / (1.29 * 0.42)) < 1
+    torch.manual_seed(0)
+    tl = TrainableLinear(Material(MatSet.Ceramic))
+    assert tl.youngs_list.shape == (16,) and tl.poisson_list.shape == (16,)
+    assert float(tl.poisson_list[0]) == pytest.approx(0.01) and float(tl.poisson_list[-1]) == pytest.approx(0.499)
+    assert len(list(tl.parameters())) == 2
+    y = tl.youngs()
+    assert y.dtype == torch.float32 and y.device.type == "cpu" and y.requires_grad
+    bl = TrainableLinear(Material(MatSet.Ceramic), baseline=True)
+    assert bl.poisson_list.shape == (1,) and float(bl.poisson()) == pytest.approx(0.19)
+    F = torch.randn(5, 3, 3)
+    P = fl.get_stress(F.double())
+    ref = mu * (F.double() + F.double().transpose(1, 2)) + lam * torch.einsum("bii->b", F.double())[:, None, None] * torch.eye(3).double()
+    assert torch.allclose(P, ref)

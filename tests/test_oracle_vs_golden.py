@@ -1,0 +1,142 @@
+"""CPU tests: the oracle (oracle/modal_oracle.py) pinned against goldens produced by the UNMODIFIED
+reference (oracle/make_goldens.py, run in the build container where /root/reference exists).
+
+The reference ships no tests or golden vectors for this path, so these
+reference-generated files are the pin.  Tolerances: integer artefacts bit-exact; K <= 2e-15-level
+relative to max|K| is not attainable across different summation orders, so K values are compared at
+1e-12 * max|K| and M at 1e-12 relative; eigenvalues 1e-9 (ARPACK vs ARPACK); gradients 1e-6.
+"""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle import modal_oracle as mo
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+CASES = [("cube2", 1), ("cube2", 2), ("cube3", 1), ("cube3", 2), ("grid16", 1), ("grid16", 2), ("bowl", 1)]
+
+
+@pytest.mark.parametrize("name,order", CASES + [("bowl", 2)])
+def test_promotion_and_pattern_bit_exact(meshes, name, order):
+    g = golden(f"modal_{name}_o{order}")
+    v, t = meshes[name]
+    pv, pt = mo.promote(torch.tensor(v), torch.tensor(t), order)
+    assert _sha(pv.numpy()) == str(g["pverts_sha"])
+    assert _sha(pt.numpy().astype(np.int64)) == str(g["ptets_sha"])
+    assert pv.shape[0] == int(g["n_nodes"])
+    crow, col, brow, bcol = mo.pattern(pt, pv.shape[0])
+    assert _sha(crow) == str(g["crow_sha"]) and _sha(col) == str(g["col_sha"])
+    assert col.size == int(g["nnz"]) == 9 * bcol.size
+
+
+@pytest.mark.parametrize("name,order", CASES)
+def test_assembled_values(meshes, name, order):
+    g = golden(f"modal_{name}_o{order}")
+    rho, E, nu = g["material"][:3]
+    v, t = meshes[name]
+    pv, pt = mo.promote(torch.tensor(v), torch.tensor(t), order)
+    K, M = mo.assemble(pv, pt, order, E, nu, rho)
+    s = g["sample_idx"]
+    assert np.abs(K.data[s] - g["K_sample"]).max() <= 1e-12 * float(g["K_absmax"])
+    assert np.allclose(M.data[s], g["M_sample"], rtol=1e-12, atol=0)
+    assert abs(K.data.sum() - float(g["K_sum"])) <= 1e-9 * float(g["K_fro"])
+    assert abs(np.sqrt((K.data ** 2).sum()) - float(g["K_fro"])) <= 1e-12 * float(g["K_fro"])
+    assert abs(M.data.sum() - float(g["M_sum"])) <= 1e-12 * float(g["M_sum"])
+    if "K_values" in g.files:
+        assert np.abs(K.data - g["K_values"]).max() <= 1e-12 * float(g["K_absmax"])
+        assert np.array_equal(M.data == 0, g["M_values"] == 0)
+
+
+@pytest.mark.parametrize("name,order", [("cube2", 1), ("cube2", 2), ("cube3", 1), ("cube3", 2), ("grid16", 1), ("bowl", 1)])
+def test_eigenvalues_and_get_vals(meshes, name, order):
+    g = golden(f"modal_{name}_o{order}")
+    rho, E, nu = g["material"][:3]
+    v, t = meshes[name]
+    pv, pt = mo.promote(torch.tensor(v), torch.tensor(t), order)
+    K, M = mo.assemble(pv, pt, order, E, nu, rho)
+    lam, U, Uf, S = mo.eig_arpack(K, M, int(g["k"]))
+    assert (np.abs(lam - g["eigenvalues"]) / g["eigenvalues"]).max() <= 1e-9
+    assert np.abs(S[:6]).max() <= 1e-6 * lam[0]                       # six rigid modes
+    assert np.abs(U.T @ (M @ U) - np.eye(U.shape[1])).max() <= 1e-10   # M-orthonormal
+    gv = g["get_vals"][:, 0]
+    assert (np.abs(lam.astype(np.float32) - gv) / gv).max() <= 3e-7    # get_vals == lambda in fp32
+
+
+@pytest.mark.parametrize("name,order", [("cube2", 1), ("cube2", 2), ("cube3", 1), ("cube3", 2), ("grid16", 1)])
+def test_shape_gradient(meshes, name, order):
+    g = golden(f"modal_{name}_o{order}")
+    rho, E, nu = g["material"][:3]
+    v, t = meshes[name]
+    pv, pt = mo.promote(torch.tensor(v), torch.tensor(t), order)
+    got = mo.eigval_grad_shape(pv, pt, order, E, nu, rho, g["U_hat"], g["eigenvalues"],
+                               g["upstream"].astype(np.float64)).numpy()
+    ref = g["grad_verts"]
+    if order == 2:
+        key = {tuple(x): i for i, x in enumerate(pv.numpy().tolist())}
+        got = np.stack([got[key[tuple(x)]] for x in v.tolist()])
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) <= 1e-6
+
+
+@pytest.mark.parametrize("name,order", [("cube3", 2), ("grid16", 1), ("bowl", 1)])
+def test_material_path(meshes, name, order):
+    """lambda_i(E, nu) = mu q_mu + lam q_lam reproduces the reference's get_undamped_freqs."""
+    g = golden(f"material_{name}_o{order}")
+    rho = g["material"][0]
+    v, t = meshes[name]
+    pv, pt = mo.promote(torch.tensor(v), torch.tensor(t), order)
+    K, M = mo.assemble(pv, pt, order, float(g["E0"]), float(g["nu0"]), rho)
+    lam, U, _, _ = mo.eig_arpack(K, M, int(g["k"]))
+    assert (np.abs(lam - g["eigenvalues0"]) / g["eigenvalues0"]).max() <= 1e-6
+    qmu, qla = mo.material_quadforms(pv, pt, order, U)
+    for E, nu, ref in ((float(g["E0"]), float(g["nu0"]), g["freqs0"]), (float(g["E1"]), float(g["nu1"]), g["freqs1"])):
+        mu, la = mo.lame(E, nu)
+        f = mo.undamped_freqs(mu * qmu + la * qla)
+        assert (np.abs(f - ref[:, 0]) / ref[:, 0]).max() <= 2e-6
+
+
+def test_oscillator_closed_form():
+    g = golden("oscillator")
+    k, T, sr, F = (int(x) for x in g["trad_meta"])
+    f = g["trad_freq"].reshape(-1).astype(np.float64)
+    force = np.zeros((1, F))
+    force[0, 0] = 1
+    y = mo.traditional_oscillator(f, 6.0, 1e-7, force, T, sr)
+    ref = g["trad_audio_f64"]
+    assert np.linalg.norm(y - ref) / np.linalg.norm(ref) <= 1e-9
+    # and the reference's own fp32 run sits 3e-5 away from its fp64 run
+    assert np.linalg.norm(g["trad_audio_f32"] - ref) / np.linalg.norm(ref) <= 1e-4
+    y2 = mo.traditional_oscillator(f, 1.0, 1e-7, g["trad2_force"], T, sr)
+    assert np.linalg.norm(y2 - g["trad2_audio_f64"]) / np.linalg.norm(g["trad2_audio_f64"]) <= 1e-9
+    d, fd = mo.rayleigh_damping(f, 6.0, 1e-7)
+    assert np.allclose(fd, g["trad_damped_freq_f64"].reshape(-1), rtol=1e-12)
+
+
+def test_first_principles():
+    """KATs derived from first principles."""
+    for order in (1, 2):
+        pts, w = mo.gauss_rule(order + 2)
+        assert abs(w.sum() - 1 / 6) <= 1e-7
+        assert np.abs(pts.sum(1) - 1).max() <= 1e-6
+        Mt = mo.element_mass_table(order)
+        assert abs(float(Mt.sum()) - 1 / 6) <= 1e-6
+    v, t = mo.kuhn_cube(3)
+    for order in (1, 2):
+        pv, pt = mo.promote(v, t, order)
+        K, M = mo.assemble(pv, pt, order, 2e11, 0.29, 7850.0)
+        n = K.shape[0]
+        R = np.zeros((n, 6))
+        p = pv.numpy().astype(np.float64)
+        for c in range(3):
+            R[c::3, c] = 1
+        R[0::3, 3], R[1::3, 3] = -p[:, 1], p[:, 0]
+        R[1::3, 4], R[2::3, 4] = -p[:, 2], p[:, 1]
+        R[2::3, 5], R[0::3, 5] = -p[:, 0], p[:, 2]
+        assert np.abs(K @ R).max() <= 1e-5 * np.abs(K.data).max()      # rigid motions are in the null space
+        assert abs(M.sum() / 3 - 7850.0) <= 1e-6 * 7850.0                # total mass of the unit cube (fp32 rule: 4e-7)
