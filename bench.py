@@ -286,11 +286,11 @@ def main():
         steps_total = stats.get("cheb_steps", None)
         if steps_total:
             per_step_bytes = nnzb * 84 + n_nodes * (4 + 72) + 4 * n * c_avg * 8
-            t_avg = prof["cheb_step"]["ms"] / steps_total * 1e-3
+            t_avg = prof["cheb_step"]["ms"] / (steps_total * args.steps) * 1e-3     # seconds per launch
             roof = {"bound": "hbm", "kernel": "k_cheb_step (block-CSR SpMM fused with the Chebyshev update)",
                     "achieved": per_step_bytes / t_avg / 1e9, "peak": peak, "unit": "GB/s",
                     "frac": per_step_bytes / t_avg / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                    "launches": steps_total, "avg_cols": c_avg, "bytes_per_launch": per_step_bytes,
+                    "launches_per_step": steps_total, "avg_launch_ms": t_avg * 1e3, "avg_cols": c_avg, "bytes_per_launch": per_step_bytes,
                     "share_of_step": prof["cheb_step"]["ms"] / ms}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

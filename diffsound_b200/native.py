@@ -155,7 +155,7 @@ def mass_expand(pattern, Mblk):
 def assemble_mass_coo(vertices, tets, values, rows, cols, element_mm, density, order):
     """Same argument order as the reference's `assemble_mass_matrix` export."""
     lib = _lib.load()
-    vnum = {1: 4, 2: 10, 3: 20}[order]
+    vnum = {1: 4, 2: 10, 3: 20}.get(order, 4)   # an invalid order is rejected by the library
     T = tets.numel() // vnum
     with torch.cuda.device(vertices.device):
         _lib.check(lib.ds_assemble_mass_coo(_p(vertices), _p(tets), T, order, _p(element_mm), float(density),
