@@ -278,21 +278,22 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    dom = max(prof.items(), key=lambda kv: kv[1]["ms"])[0] if prof else None
-    if stats and "cheb_step" in prof:
-        # one Chebyshev step streams K (72 B), M (8 B) and bcol (4 B) per 3x3 block, brow and the 3x3
-        # block-Jacobi inverse per node, reads Z, Zprev, R and writes Znew (4 x n x c x 8 B).
-        c_avg = stats.get("cheb_cols_avg", 48)
-        steps_total = stats.get("cheb_steps", None)
-        if steps_total:
-            per_step_bytes = nnzb * 84 + n_nodes * (4 + 72) + 4 * n * c_avg * 8
-            t_avg = prof["cheb_step"]["ms"] / (steps_total * args.steps) * 1e-3     # seconds per launch
-            roof = {"bound": "hbm", "kernel": "k_cheb_step (block-CSR SpMM fused with the Chebyshev update)",
-                    "achieved": per_step_bytes / t_avg / 1e9, "peak": peak, "unit": "GB/s",
-                    "frac": per_step_bytes / t_avg / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                    "launches_per_step": steps_total, "avg_launch_ms": t_avg * 1e3, "avg_cols": c_avg, "bytes_per_launch": per_step_bytes,
-                    "share_of_step": prof["cheb_step"]["ms"] / ms}
-
+    if stats and "cheb_step" in prof and stats.get("cheb_steps"):
+        # One fine-level FP32 SpMM launch (k_spmm32) streams one 40-byte record per 3x3 block (9 fp32 K
+        # values + bcol), brow (4 B) and the 3x3 block-Jacobi inverse (36 B) per node, reads the gathered
+        # block Z once plus R and Zprev, and writes Znew: 4 x n x c x 4 B (3 for the residual launch of a
+        # V-cycle, which has no Zprev).
+        c_avg = stats["cheb_cols_avg"]
+        steps_total = stats["cheb_steps"]
+        streams = (5 * 4 + 3) / 6.0 if stats.get("two_level") else 4.0
+        per_launch_bytes = nnzb * 40 + n_nodes * (4 + 36) + streams * n * c_avg * 4
+        t_avg = prof["cheb_step"]["ms"] / prof["cheb_step"]["count"] * 1e-3     # seconds per launch
+        roof = {"bound": "hbm", "kernel": "k_spmm32 (FP32 block-CSR SpMM on TMA-staged 40 B records, fused Chebyshev "
+                                          "update; the fine-level smoother of the eigensolver's preconditioner)",
+                "achieved": per_launch_bytes / t_avg / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": per_launch_bytes / t_avg / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                "launches_per_step": steps_total, "avg_launch_ms": t_avg * 1e3, "avg_cols": c_avg,
+                "bytes_per_launch": per_launch_bytes, "share_of_step": prof["cheb_step"]["ms"] / ms}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -301,6 +302,8 @@ def main():
                                    "one independent mesh per GPU",
                        "l2_policy": "inputs larger than L2 (K values alone 553 MB vs 126 MB L2); no flush needed",
                        "eig_tol": DiffSoundObj.eig_tol, "lobpcg_iterations": stats["iterations"] if stats else None,
+                       "preconditioner": ("fp32 two-level p-multigrid (P2 Chebyshev-Jacobi smoother, P1 coarse Chebyshev)"
+                                          if stats and stats.get("two_level") else "fp32 block-Jacobi Chebyshev"),
                        "pattern_rebuilt_each_step": True, "eigensolver_cold_start": True},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps},

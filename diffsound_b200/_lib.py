@@ -23,7 +23,15 @@ dbl = C.c_double
 
 class LobpcgOpts(C.Structure):
     _fields_ = [("nev", C.c_int), ("maxit", C.c_int), ("cheb_degree", C.c_int), ("tol", C.c_double),
-                ("sigma", C.c_double), ("cheb_ratio", C.c_double), ("n_rigid", C.c_int), ("verbose", C.c_int)]
+                ("sigma", C.c_double), ("cheb_ratio", C.c_double), ("n_rigid", C.c_int), ("verbose", C.c_int),
+                ("smooth_steps", C.c_int), ("coarse_degree", C.c_int), ("smooth_ratio", C.c_double),
+                ("coarse_ratio", C.c_double)]
+
+
+class PmgLevel(C.Structure):
+    _fields_ = [("brow", C.c_void_p), ("bcol", C.c_void_p), ("n_nodes", C.c_int64), ("nnzb", C.c_int64),
+                ("Kval", C.c_void_p), ("Mblk", C.c_void_p), ("parents", C.c_void_p), ("rptr", C.c_void_p),
+                ("rlist", C.c_void_p)]
 
 
 # name -> (restype, argtypes); mirrors include/diffsound_sm100.h one to one
@@ -46,8 +54,15 @@ SIGNATURES = {
     "ds_gram_f64": (cint, [f64p, i64, cint, f64p, i64, cint, i64, f64p, i64, f64p, ptr]),
     "ds_block_gemm_f64": (cint, [f64p, i64, cint, f64p, i64, cint, i64, dbl, f64p, i64, ptr]),
     "ds_eigh_generalized_f64": (cint, [f64p, f64p, cint, i64, dbl, f64p, f64p, i64, f64p, ptr, ptr]),
-    "ds_lobpcg": (cint, [ptr, i32p, i32p, i64, f64p, f64p, f64p, cint, C.POINTER(LobpcgOpts), f64p, f64p,
-                         C.POINTER(C.c_int64), ptr]),
+    "ds_lobpcg": (cint, [ptr, i32p, i32p, i64, f64p, f64p, C.POINTER(PmgLevel), f64p, cint, C.POINTER(LobpcgOpts),
+                         f64p, f64p, C.POINTER(C.c_int64), ptr]),
+    "ds_k32_record_bytes": (i64, [i64]),
+    "ds_k32_pack": (cint, [i32p, i32p, i64, i64, f64p, f64p, dbl, ptr, f32p, ptr]),
+    "ds_spmm32": (cint, [cint, i32p, ptr, i64, cint, f32p, f32p, f32p, f32p, f32p, dbl, dbl, ptr]),
+    "ds_pmg_coarse_count": (cint, [ptr, i32p, i64, i64, i32p, C.POINTER(C.c_int64), ptr]),
+    "ds_pmg_coarse_fill": (cint, [ptr, f32p, i32p, i64, i64, i32p, i64, i32p, f32p, i32p, i32p, i32p, ptr]),
+    "ds_pmg_restrict32": (cint, [i32p, i32p, i64, f32p, cint, f32p, ptr]),
+    "ds_pmg_prolong_add32": (cint, [i32p, i64, f32p, cint, f32p, ptr]),
     "ds_corner_incidence": (cint, [ptr, i32p, i64, cint, cint, i64, i32p, i32p, ptr]),
     "ds_eigval_grad_shape": (cint, [f32p, i32p, i64, cint, i64, dbl, dbl, f64p, f64p, f64p, i64, cint, f64p, f64p,
                                     i32p, i32p, f64p, f32p, ptr]),

@@ -18,6 +18,46 @@ int cheb_precond(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, cons
                  double shift, const double* invD, double lmin, double lmax, int degree, const double* R, int64_t ldr,
                  int ncols, double* Z0, double* Z1, int64_t ldz, double** result, cudaStream_t stream);
 
+// precond32.cu -- FP32 preconditioner pieces
+struct ColIdx {
+    short v[128];
+};
+enum { S32_MODE_PLAIN = 0, S32_MODE_RESID = 1, S32_MODE_CHEB = 2 };
+// Out = A X | R - A X | X + ab (X - Zprev) + cc invD (R - A X) on 40-byte block records; ncols in {16,32,48,64}
+int spmm32(int mode, const int32_t* brow, const void* rec, int64_t n_nodes, int ncols, const float* X, const float* R,
+           const float* invD, const float* Zprev, float* Out, float ab, float cc, int prof_cls, cudaStream_t st);
+int pack_k32(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, const double* Kval, const double* Mblk,
+             double shift, void* rec, float* invD, cudaStream_t st);
+int jacobi32(const float* invD, const float* R, int64_t n_nodes, int ncols, float cc, float* Out, cudaStream_t st);
+int restrict32(const int32_t* rptr, const int32_t* rlist, int64_t n_coarse, const float* res, int ncols, float* rc,
+               cudaStream_t st);
+int prolong_add32(const int32_t* par, int64_t n_fine, const float* zc, int ncols, float* z, cudaStream_t st);
+int prolong64(const int32_t* par, int64_t n_fine, const double* xc, int64_t ldc, int w, double* x, int64_t ldx,
+              cudaStream_t st);
+int gather_cols_f32(const double* src, int64_t lds, const ColIdx& idx, int count, int width, int64_t n, float* dst,
+                    cudaStream_t st);
+int widen_f32(const float* src, int width, int64_t n, double* dst, int64_t ldd, cudaStream_t st);
+int colnorm2_f32(const float* V, int w, int64_t n, double* partial, int ctas, cudaStream_t st);
+int fill_random_f32(float* V, int64_t count, uint64_t seed, cudaStream_t st);
+
+// one level of the FP32 preconditioner: records + block-Jacobi inverse + spectral bound of invD A
+struct Level32 {
+    const int32_t* brow = nullptr;
+    int64_t n_nodes = 0, nnzb = 0;
+    unsigned char* rec = nullptr;
+    float* invD = nullptr;
+    double lmax = 0.0;
+    int prof_cls = PROF_CHEB;
+    int64_t launches = 0, cols = 0;          // SpMM launches and the sum of their column counts
+    static size_t bytes(int64_t n_nodes, int64_t nnzb);
+    int setup(Arena& a, const int32_t* brow, const int32_t* bcol, int64_t n_nodes, int64_t nnzb, const double* Kval,
+              const double* Mblk, double shift, cudaStream_t st);
+    // z = p(invD A) invD r, `degree` Chebyshev steps on [lmax/ratio, lmax]; from_zero: z0 = 0, else z0 = *zc.
+    // zc / zp ping-pong; the result is in *zc on return.
+    int cheb(const float* r, int ncols, int degree, double ratio, bool from_zero, float** zc, float** zp,
+             cudaStream_t st);
+};
+
 // dense.cu
 int64_t gram_scratch_elems(int p, int q);
 int gram_f64(const double* A, int64_t lda, int p, const double* B, int64_t ldb, int q, int64_t n, double* G,

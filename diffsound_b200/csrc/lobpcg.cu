@@ -7,9 +7,12 @@
 // is the classical [X, W, P] scheme with soft locking:
 //   R = K X - M X diag(lam);  W = T R (active columns only), M-orthogonalised against X;
 //   Rayleigh-Ritz on span[X, W, P];  X, P updated from the Ritz vectors.
-// T is `cheb_degree` steps of block-Jacobi-scaled Chebyshev iteration on K (+ sigma M),
-// i.e. a fixed SPD polynomial in the SpMM kernel -- the eigen-solve is therefore a
-// stream of SpMM (HBM-bound) + DMMA Gram/GEMM kernels + one single-CTA Jacobi per step.
+// T ~ K^-1 is evaluated in FP32 (csrc/precond32.cu): either `cheb_degree` steps of
+// block-Jacobi-scaled Chebyshev iteration on K (+ sigma M), or -- when the caller supplies the
+// P1 operator of a quadratic mesh (ds_pmg_level) -- a symmetric two-level V-cycle: Chebyshev
+// smoothing on the P2 operator around a Chebyshev solve on the 15x smaller P1 operator.  Either
+// way T is a fixed SPD polynomial in the SpMM kernel, so the eigen-solve is a stream of SpMM
+// (HBM-bound) + DMMA Gram/GEMM kernels + one single-CTA Jacobi per step.
 //
 // Storage: three wide row-major buffers S, KS, MS of n x 3m (columns [X | W | P]) plus a
 // ping-pong copy, so the Ritz update is one tall-skinny GEMM per buffer.
@@ -80,10 +83,6 @@ __global__ void k_colnorm2(const double* __restrict__ V, int64_t ld, int w, int6
     }
 }
 
-struct ColIdx {
-    short v[128];
-};
-
 // dst[:, s] = src[:, idx[s]] for s < count, zero for count <= s < width
 __global__ void k_gather_cols(const double* __restrict__ src, int64_t lds, const __grid_constant__ ColIdx idx,
                               int count, int width, int64_t n, double* __restrict__ dst, int64_t ldd) {
@@ -113,13 +112,17 @@ struct Driver {
     int m;
     ds_lobpcg_opts o;
 
+    const ds_pmg_level* cl = nullptr;   // optional coarse (P1) level
+    Level32 fine, coarse;
+    float *R32, *Za, *Zb, *RC32, *ZCa, *ZCb;
+
     int ld;                      // 3m
     double *S[2], *KS[2], *MS[2];
-    double *R, *Rc, *Z0, *Z1, *invD;
+    double *R;
     double *GK, *GM, *Cm, *theta, *eig_scratch, *gram_partial, *norm_partial, *norms, *lam_d;
     int* info_d;
     int cur = 0;
-    int64_t spmm_count = 0, cheb_launches = 0, cheb_cols = 0;
+    int64_t spmm_count = 0;
     int norm_ctas = 296;
 
     int alloc() {
@@ -128,7 +131,17 @@ struct Driver {
         size_t need = 0;
         auto add = [&](size_t elems) { need += ((elems * 8 + 255) & ~size_t(255)) + 256; };
         for (int i = 0; i < 6; ++i) add(3 * blk);
-        add(blk); add(blk); add(blk); add(blk); add(9 * (size_t)n_nodes);
+        add(blk);
+        const int64_t nnzb = nnzb_of(brow, n_nodes);
+        if (nnzb < 0) return DS_ERR_CUDA;
+        need += Level32::bytes(n_nodes, nnzb);
+        for (int i = 0; i < 3; ++i) add(blk / 2 + 64);
+        int64_t nnzb_c = 0;
+        if (cl) {
+            nnzb_c = cl->nnzb;
+            need += Level32::bytes(cl->n_nodes, nnzb_c);
+            for (int i = 0; i < 3; ++i) add((size_t)3 * cl->n_nodes * m / 2 + 64);
+        }
         add(144 * 144); add(144 * 144); add(144 * 144); add(144); add(2 * 144 * 144);
         add((size_t)gram_scratch_elems(64, 64)); add((size_t)norm_ctas * 2 * 128); add(2 * 128); add(128);
         add(64);
@@ -139,8 +152,13 @@ struct Driver {
             KS[i] = a.take<double>(3 * blk);
             MS[i] = a.take<double>(3 * blk);
         }
-        R = a.take<double>(blk); Rc = a.take<double>(blk); Z0 = a.take<double>(blk); Z1 = a.take<double>(blk);
-        invD = a.take<double>(9 * (size_t)n_nodes);
+        R = a.take<double>(blk);
+        R32 = a.take<float>(blk); Za = a.take<float>(blk); Zb = a.take<float>(blk);
+        RC32 = ZCa = ZCb = nullptr;
+        if (cl) {
+            const size_t cb = (size_t)3 * cl->n_nodes * m;
+            RC32 = a.take<float>(cb); ZCa = a.take<float>(cb); ZCb = a.take<float>(cb);
+        }
         GK = a.take<double>(144 * 144); GM = a.take<double>(144 * 144); Cm = a.take<double>(144 * 144);
         theta = a.take<double>(144); eig_scratch = a.take<double>(2 * 144 * 144);
         gram_partial = a.take<double>((size_t)gram_scratch_elems(64, 64));
@@ -154,8 +172,24 @@ struct Driver {
             DS_CUDA(cudaMemsetAsync(KS[i], 0, 3 * blk * 8, st));
             DS_CUDA(cudaMemsetAsync(MS[i], 0, 3 * blk * 8, st));
         }
-        DS_CUDA(cudaMemsetAsync(Z1, 0, blk * 8, st));
+        // FP32 copies of the operators (records + block-Jacobi inverses)
+        DS_TRY(fine.setup(a, brow, bcol, n_nodes, nnzb, Kval, Mblk, o.sigma > 0.0 ? o.sigma : 0.0, st));
+        fine.prof_cls = PROF_CHEB;
+        if (cl) {
+            DS_TRY(coarse.setup(a, cl->brow, cl->bcol, cl->n_nodes, nnzb_c, cl->Kval, cl->Mblk,
+                                o.sigma > 0.0 ? o.sigma : 0.0, st));
+            coarse.prof_cls = PROF_COARSE;
+        }
         return DS_OK;
+    }
+
+    static int64_t nnzb_of(const int32_t* brow, int64_t n_nodes) {
+        int32_t v = 0;
+        if (cudaMemcpy(&v, brow + n_nodes, sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) {
+            set_error("ds_lobpcg: cannot read brow[n_nodes]");
+            return -1;
+        }
+        return v;
     }
 
     double* Xb(int w) { return S[w]; }
@@ -181,59 +215,78 @@ struct Driver {
         return DS_OK;
     }
 
-    // largest eigenvalue of invD (K + shift M) by power iteration on I + invD A (16 columns)
-    int estimate_lmax(double shift, double* lmax) {
+    // largest eigenvalue of invD A by power iteration on I + invD A (16 fp32 columns)
+    int estimate_lmax(Level32& L, float* a, float* b, float* zero_r) {
         const int w = 16;
-        DS_CUDA(cudaMemsetAsync(R, 0, sizeof(double) * n * w, st));
-        k_fill_random<<<(unsigned)ceil_div(n * w, 256), 256, 0, st>>>(Z0, n * w, 0x1234567ull);
-        DS_LAUNCH_CHECK();
-        double* a = Z0;
-        double* b = Z1;
-        std::vector<double> n0, n1;
-        const int iters = 24;
+        const int64_t nl = 3 * L.n_nodes;
+        DS_CUDA(cudaMemsetAsync(zero_r, 0, sizeof(float) * nl * w, st));
+        DS_TRY(fill_random_f32(a, nl * w, 0x1234567ull, st));
+        std::vector<double> n0(w), n1(w);
+        auto norms_of = [&](const float* v, std::vector<double>& out) -> int {
+            DS_TRY(colnorm2_f32(v, w, nl, norm_partial, norm_ctas, st));
+            k_colsum_reduce<<<1, 128, 0, st>>>(norm_partial, norm_ctas, w, norms);
+            DS_LAUNCH_CHECK();
+            DS_CUDA(cudaMemcpyAsync(out.data(), norms, w * sizeof(double), cudaMemcpyDeviceToHost, st));
+            DS_CUDA(cudaStreamSynchronize(st));
+            return DS_OK;
+        };
+        const int iters = 20;
         for (int it = 0; it < iters; ++it) {
-            if (it == iters - 1) DS_TRY(colnorms(a, w, w, n0));
-            // b <- a + 0*(a - b) + (-1) invD (0 - A a) = (I + invD A) a   (R = 0, ab = 0, cc = -1)
-            DS_TRY(cheb_step_raw(shift, a, b, w, 0.0, -1.0));
+            if (it == iters - 1) DS_TRY(norms_of(a, n0));
+            // b = a + 0 (a - a) + (-1) invD (0 - A a) = (I + invD A) a
+            DS_TRY(spmm32(S32_MODE_CHEB, L.brow, L.rec, L.n_nodes, w, a, zero_r, L.invD, a, b, 0.f, -1.f, L.prof_cls, st));
             std::swap(a, b);
             spmm_count++;
         }
-        DS_TRY(colnorms(a, w, w, n1));
+        DS_TRY(norms_of(a, n1));
         double best = 0.0;
         for (int c = 0; c < w; ++c) best = std::max(best, std::sqrt(n1[c] / n0[c]));
-        *lmax = best - 1.0;
+        L.lmax = 1.1 * (best - 1.0);
         return DS_OK;
     }
 
-    int cheb_step_raw(double shift, const double* z, double* zprev_new, int w, double ab, double cc);
+    // W32 = T R32 (w columns): Chebyshev polynomial (one level) or the two-level V-cycle
+    int apply_precond(int w, float** out) {
+        float* zc = Za;
+        float* zp = Zb;
+        if (!cl) {
+            DS_TRY(fine.cheb(R32, w, o.cheb_degree, o.cheb_ratio > 1.0 ? o.cheb_ratio : 30.0, true, &zc, &zp, st));
+            *out = zc;
+            return DS_OK;
+        }
+        const int nu = o.smooth_steps > 0 ? o.smooth_steps : 3;
+        const double sr = o.smooth_ratio > 1.0 ? o.smooth_ratio : 8.0;
+        DS_TRY(fine.cheb(R32, w, nu, sr, true, &zc, &zp, st));                               // pre-smooth from zero
+        DS_TRY(spmm32(S32_MODE_RESID, fine.brow, fine.rec, n_nodes, w, zc, R32, nullptr, nullptr, zp, 0.f, 0.f,
+                      PROF_CHEB, st));                                                       // zp = r - A z
+        fine.launches++; fine.cols += w;
+        DS_TRY(restrict32(cl->rptr, cl->rlist, cl->n_nodes, zp, w, RC32, st));
+        float* cc = ZCa;
+        float* cp = ZCb;
+        DS_TRY(coarse.cheb(RC32, w, o.coarse_degree, o.coarse_ratio > 1.0 ? o.coarse_ratio : 30.0, true, &cc, &cp, st));
+        DS_TRY(prolong_add32(cl->parents, n_nodes, cc, w, zc, st));
+        DS_TRY(fine.cheb(R32, w, nu, sr, false, &zc, &zp, st));                              // post-smooth
+        *out = zc;
+        return DS_OK;
+    }
 
     int run(double* X, double* lambda_out, double* resid_out, int64_t* stats);
 };
 
 }  // namespace ds
 
-// k_cheb_step lives in spmm.cu; expose one raw step through a tiny internal hook
 namespace ds {
-int cheb_single_step(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, const double* Kval, const double* Mblk,
-                     double shift, const double* invD, const double* R, int64_t ldr, int ncols, const double* Z,
-                     double* Zprev_new, int64_t ldz, double ab, double cc, cudaStream_t stream);
-
-int Driver::cheb_step_raw(double shift, const double* z, double* zprev_new, int w, double ab, double cc) {
-    return cheb_single_step(brow, bcol, n_nodes, Kval, Mblk, shift, invD, R, w, w, z, zprev_new, w, ab, cc, st);
-}
 
 int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats) {
     const int nev = o.nev;
     int nr = o.n_rigid < 0 ? 0 : o.n_rigid;
     DS_TRY(alloc());
-    const double shift = o.sigma > 0.0 ? o.sigma : 0.0;
-    DS_TRY(block_jacobi(brow, bcol, n_nodes, Kval, Mblk, shift, invD, st));
-    double lmax = 0.0;
-    DS_TRY(estimate_lmax(shift, &lmax));
-    lmax *= 1.1;
-    const double lmin = lmax / (o.cheb_ratio > 1.0 ? o.cheb_ratio : 30.0);
-    if (o.verbose) fprintf(stderr, "[ds_lobpcg] n=%lld m=%d nev=%d lmax(invD A)=%.4f cheb=[%.4g,%.4g] deg=%d\n",
-                           (long long)n, m, nev, lmax / 1.1, lmin, lmax, o.cheb_degree);
+    DS_TRY(estimate_lmax(fine, Za, Zb, R32));
+    if (cl) DS_TRY(estimate_lmax(coarse, ZCa, ZCb, RC32));
+    if (o.verbose)
+        fprintf(stderr, "[ds_lobpcg] n=%lld m=%d nev=%d lmax(invD K)=%.4f %s deg=%d coarse: n=%lld lmax=%.4f deg=%d nu=%d\n",
+                (long long)n, m, nev, fine.lmax / 1.1, cl ? "two-level" : "chebyshev", o.cheb_degree,
+                (long long)(cl ? 3 * cl->n_nodes : 0), coarse.lmax / 1.1, o.coarse_degree, o.smooth_steps);
 
     // ---- initial Rayleigh-Ritz on X
     cur = 0;
@@ -334,17 +387,10 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
         ColIdx ci;
         for (int s = 0; s < 128; ++s) ci.v[s] = (short)(s < na ? act[s] : 0);
         // ---- W = T(R[:, act])
-        { ProfScope prof(PROF_COPY, st);
-        k_gather_cols<<<(unsigned)ceil_div(n * wpad, 256), 256, 0, st>>>(R, m, ci, na, wpad, n, Rc, wpad);
-        DS_LAUNCH_CHECK(); }
-        double* Zres = nullptr;
-        DS_TRY(cheb_precond(brow, bcol, n_nodes, Kval, Mblk, shift, invD, lmin, lmax, o.cheb_degree, Rc, wpad, wpad, Z0,
-                            Z1, wpad, &Zres, st));
-        spmm_count += o.cheb_degree - 1;
-        cheb_launches += o.cheb_degree;
-        cheb_cols += (int64_t)o.cheb_degree * wpad;
-        { ProfScope prof(PROF_COPY, st);
-        DS_CUDA(cudaMemcpy2DAsync(Wb(cur), ld * 8, Zres, wpad * 8, wpad * 8, n, cudaMemcpyDeviceToDevice, st)); }
+        DS_TRY(gather_cols_f32(R, m, ci, na, wpad, n, R32, st));
+        float* Zres = nullptr;
+        DS_TRY(apply_precond(wpad, &Zres));
+        DS_TRY(widen_f32(Zres, wpad, n, Wb(cur), ld, st));
         // ---- W <- W - X (MX^T W)
         DS_TRY(gram_f64(MS[cur], ld, m, Wb(cur), ld, wpad, n, GK, 144, gram_partial, st));
         DS_TRY(block_gemm_f64(Xb(cur), ld, m, GK, 144, wpad, n, -1.0, 1.0, Wb(cur), ld, st));
@@ -401,11 +447,12 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
     DS_CUDA(cudaStreamSynchronize(st));
     stats[0] = it;
     stats[1] = nconv;
-    stats[2] = spmm_count;
     stats[3] = status;
-    stats[4] = cheb_launches;
-    stats[5] = cheb_cols;
-    stats[6] = stats[7] = 0;
+    stats[2] = spmm_count + fine.launches + coarse.launches;
+    stats[4] = fine.launches;
+    stats[5] = fine.cols;
+    stats[6] = coarse.launches;
+    stats[7] = coarse.cols;
     return DS_OK;
 }
 
@@ -414,8 +461,9 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
 using namespace ds;
 
 extern "C" int ds_lobpcg(ds_workspace* ws, const int32_t* brow, const int32_t* bcol, int64_t n_nodes,
-                         const double* Kval, const double* Mblk, double* X, int m, const ds_lobpcg_opts* opts,
-                         double* lambda_out, double* resid_out, int64_t* stats_host, void* stream) {
+                         const double* Kval, const double* Mblk, const ds_pmg_level* coarse, double* X, int m,
+                         const ds_lobpcg_opts* opts, double* lambda_out, double* resid_out, int64_t* stats_host,
+                         void* stream) {
     DS_REQUIRE(ws && brow && bcol && Kval && Mblk && X && opts && lambda_out && resid_out && stats_host,
                "ds_lobpcg: null argument");
     DS_REQUIRE(m >= 16 && m % 16 == 0 && m <= 48, "ds_lobpcg: block size m=%d must be 16, 32 or 48", m);
@@ -424,7 +472,14 @@ extern "C" int ds_lobpcg(ds_workspace* ws, const int32_t* brow, const int32_t* b
                (long long)(3 * n_nodes), 3 * m);
     DS_REQUIRE(opts->cheb_degree >= 1 && opts->maxit >= 1 && opts->tol > 0, "ds_lobpcg: bad options");
     DS_REQUIRE(opts->n_rigid >= -1 && opts->n_rigid <= opts->nev, "ds_lobpcg: bad n_rigid");
+    if (coarse) {
+        DS_REQUIRE(coarse->brow && coarse->bcol && coarse->Kval && coarse->parents && coarse->rptr && coarse->rlist &&
+                       coarse->n_nodes > 0 && coarse->nnzb > 0,
+                   "ds_lobpcg: incomplete coarse level");
+        DS_REQUIRE(opts->coarse_degree >= 1, "ds_lobpcg: coarse_degree must be >= 1 with a coarse level");
+    }
     Driver d;
+    d.cl = coarse;
     d.ws = ws;
     d.st = (cudaStream_t)stream;
     d.brow = brow; d.bcol = bcol;

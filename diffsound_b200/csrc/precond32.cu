@@ -1,0 +1,648 @@
+// FP32 preconditioner kernels of the eigensolver: block-CSR SpMM on 40-byte block records
+// streamed through shared memory by the TMA unit, fused with the Chebyshev / residual epilogue.
+//
+// Reference behaviour replaced: none one-to-one -- the reference factorises K - sigma M on the CPU
+// (SciPy SuperLU inside eigsh, /root/reference/src/diffelastic/diff_model.py:356-358) and its own
+// LOBPCG takes an optional dense/callable preconditioner `iK` (src/lobpcg/_lobpcg.py:453,475).
+// Here the preconditioner T ~ K^-1 is a fixed polynomial / V-cycle in the SpMM below, evaluated in
+// FP32 (LOBPCG only needs an approximate SPD operator; the eigenpairs themselves stay FP64).
+//
+// Layout: one record per 3x3 block, 10 x 4 bytes = {k00 k01 k02 k10 k11 k12 k20 k21 k22 | bcol},
+// in block-CSR order, so the records of consecutive node rows are ONE contiguous byte range:
+// a tile of S32_ROWS node rows is fetched by a single cp.async.bulk (1-D TMA) into a 2-stage
+// shared-memory ring while the previous tile is being multiplied.  Dense blocks are row-major
+// fp32 (n x c), c in {16, 32, 48, 64}; the 3 rows of a node are contiguous (3c floats), so a
+// gathered neighbour is one 192..768-byte run.
+//
+// Mapping: a warp owns one node row at a time (rows of the tile are handed out through a
+// shared-memory ticket, so long and short rows balance); LPR lanes cover the c columns
+// (CPT contiguous columns each, 64/128-bit loads), the 32/LPR lane groups walk alternate
+// blocks of the row and are combined by a butterfly at the end.  Lane groups 0..2 then apply the
+// epilogue for component 0..2 of the node.
+#include "common.cuh"
+#include "../../include/diffsound_sm100.h"
+#include "kernels.cuh"
+#include "ptx.cuh"
+#include <utility>
+
+namespace ds {
+
+constexpr int S32_ROWS = 8;                  // node rows per tile
+constexpr int S32_CAP = 384;                 // block records staged per tile (rest read from global)
+constexpr int S32_THREADS = 128;
+constexpr int S32_REC_BYTES = 40;
+constexpr int S32_STAGE_BYTES = (S32_CAP + 2) * S32_REC_BYTES;   // 15440: multiple of 16
+static_assert(S32_STAGE_BYTES % 16 == 0, "stage must keep 16-byte alignment");
+constexpr int S32_SMEM = 2 * S32_STAGE_BYTES + 64;
+
+enum { S32_PLAIN = S32_MODE_PLAIN, S32_RESID = S32_MODE_RESID, S32_CHEB = S32_MODE_CHEB };
+
+template <int VEC> struct VecT;
+template <> struct VecT<2> { using type = float2; };
+template <> struct VecT<4> { using type = float4; };
+
+template <int VEC>
+__device__ __forceinline__ void ld_vec(const float* p, float* out) {
+    if constexpr (VEC == 4) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(p));
+        out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+    } else {
+        float2 v = __ldg(reinterpret_cast<const float2*>(p));
+        out[0] = v.x; out[1] = v.y;
+    }
+}
+// plain (coherent) load: for buffers the same kernel also writes (Zprev may alias Out)
+template <int VEC>
+__device__ __forceinline__ void ld_vec_plain(const float* p, float* out) {
+    if constexpr (VEC == 4) {
+        float4 v = *reinterpret_cast<const float4*>(p);
+        out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+    } else {
+        float2 v = *reinterpret_cast<const float2*>(p);
+        out[0] = v.x; out[1] = v.y;
+    }
+}
+template <int VEC>
+__device__ __forceinline__ void st_vec(float* p, const float* v) {
+    if constexpr (VEC == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    else *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+}
+
+// acc[c][t] += K[c][d] * X[3j+d][cols of this lane] for one block record
+template <int C, int CPT, int VEC>
+__device__ __forceinline__ void block_fma(const uint2* __restrict__ r, const float* __restrict__ Xl,
+                                          float (&acc)[3][CPT]) {
+    constexpr int NV = CPT / VEC;
+    const uint2 a0 = r[0], a1 = r[1], a2 = r[2], a3 = r[3], a4 = r[4];
+    const float* xr = Xl + (int64_t)(int)a4.y * (3 * C);
+    float x[3][CPT];
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int q = 0; q < NV; ++q) ld_vec<VEC>(xr + d * C + q * VEC, &x[d][q * VEC]);
+    const float k00 = __uint_as_float(a0.x), k01 = __uint_as_float(a0.y), k02 = __uint_as_float(a1.x);
+    const float k10 = __uint_as_float(a1.y), k11 = __uint_as_float(a2.x), k12 = __uint_as_float(a2.y);
+    const float k20 = __uint_as_float(a3.x), k21 = __uint_as_float(a3.y), k22 = __uint_as_float(a4.x);
+#pragma unroll
+    for (int t = 0; t < CPT; ++t) {
+        acc[0][t] = fmaf(k00, x[0][t], fmaf(k01, x[1][t], fmaf(k02, x[2][t], acc[0][t])));
+        acc[1][t] = fmaf(k10, x[0][t], fmaf(k11, x[1][t], fmaf(k12, x[2][t], acc[1][t])));
+        acc[2][t] = fmaf(k20, x[0][t], fmaf(k21, x[1][t], fmaf(k22, x[2][t], acc[2][t])));
+    }
+}
+
+// two independent blocks with all loads issued before the first FMA (memory-level parallelism)
+template <int C, int CPT, int VEC>
+__device__ __forceinline__ void block_fma2(const uint2* __restrict__ ra, const uint2* __restrict__ rb,
+                                           const float* __restrict__ Xl, float (&acc)[3][CPT]) {
+    constexpr int NV = CPT / VEC;
+    const uint2 a0 = ra[0], a1 = ra[1], a2 = ra[2], a3 = ra[3], a4 = ra[4];
+    const uint2 b0 = rb[0], b1 = rb[1], b2 = rb[2], b3 = rb[3], b4 = rb[4];
+    const float* xa = Xl + (int64_t)(int)a4.y * (3 * C);
+    const float* xb = Xl + (int64_t)(int)b4.y * (3 * C);
+    float x[3][CPT], y[3][CPT];
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            ld_vec<VEC>(xa + d * C + q * VEC, &x[d][q * VEC]);
+            ld_vec<VEC>(xb + d * C + q * VEC, &y[d][q * VEC]);
+        }
+    {
+        const float k00 = __uint_as_float(a0.x), k01 = __uint_as_float(a0.y), k02 = __uint_as_float(a1.x);
+        const float k10 = __uint_as_float(a1.y), k11 = __uint_as_float(a2.x), k12 = __uint_as_float(a2.y);
+        const float k20 = __uint_as_float(a3.x), k21 = __uint_as_float(a3.y), k22 = __uint_as_float(a4.x);
+#pragma unroll
+        for (int t = 0; t < CPT; ++t) {
+            acc[0][t] = fmaf(k00, x[0][t], fmaf(k01, x[1][t], fmaf(k02, x[2][t], acc[0][t])));
+            acc[1][t] = fmaf(k10, x[0][t], fmaf(k11, x[1][t], fmaf(k12, x[2][t], acc[1][t])));
+            acc[2][t] = fmaf(k20, x[0][t], fmaf(k21, x[1][t], fmaf(k22, x[2][t], acc[2][t])));
+        }
+    }
+    {
+        const float k00 = __uint_as_float(b0.x), k01 = __uint_as_float(b0.y), k02 = __uint_as_float(b1.x);
+        const float k10 = __uint_as_float(b1.y), k11 = __uint_as_float(b2.x), k12 = __uint_as_float(b2.y);
+        const float k20 = __uint_as_float(b3.x), k21 = __uint_as_float(b3.y), k22 = __uint_as_float(b4.x);
+#pragma unroll
+        for (int t = 0; t < CPT; ++t) {
+            acc[0][t] = fmaf(k00, y[0][t], fmaf(k01, y[1][t], fmaf(k02, y[2][t], acc[0][t])));
+            acc[1][t] = fmaf(k10, y[0][t], fmaf(k11, y[1][t], fmaf(k12, y[2][t], acc[1][t])));
+            acc[2][t] = fmaf(k20, y[0][t], fmaf(k21, y[1][t], fmaf(k22, y[2][t], acc[2][t])));
+        }
+    }
+}
+
+// MODE PLAIN:  Out = A X
+//      RESID:  Out = R - A X
+//      CHEB:   Out = X + ab (X - Zprev) + cc invD (R - A X)      (Zprev may alias Out)
+template <int LPR, int CPT, int MODE>
+__global__ void __launch_bounds__(S32_THREADS)
+k_spmm32(const int32_t* __restrict__ brow, const uint2* __restrict__ rec, int64_t n_nodes,
+         const float* __restrict__ X, const float* __restrict__ R, const float* __restrict__ invD,
+         const float* Zprev, float* Out, float ab, float cc) {
+    constexpr int C = LPR * CPT;
+    constexpr int NG = 32 / LPR;
+    constexpr int VEC = (CPT % 4 == 0) ? 4 : 2;
+    constexpr int NV = CPT / VEC;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * S32_STAGE_BYTES);
+    int* ticket = reinterpret_cast<int*>(full + 2);        // [2]
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int g = lane / LPR, l = lane % LPR;
+    const int64_t n_tiles = (n_nodes + S32_ROWS - 1) / S32_ROWS;
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        ticket[0] = 0;
+        ticket[1] = 0;
+        fence_barrier_init();
+    }
+    __syncthreads();
+    uint32_t phase = 0;     // bit s = parity to wait for on stage s
+
+    auto issue = [&](int s, int64_t lo, int64_t hi) {      // one thread; hi > lo
+        const int64_t al = lo & ~int64_t(1);                // 80-byte pairs keep the source 16-byte aligned
+        const uint32_t bytes = (uint32_t)(((hi - al) * S32_REC_BYTES + 15) & ~int64_t(15));
+        mbar_expect_tx(&full[s], bytes);
+        tma_load_1d(smem + s * S32_STAGE_BYTES, reinterpret_cast<const unsigned char*>(rec) + al * S32_REC_BYTES,
+                    bytes, &full[s]);
+    };
+    auto tile_range = [&](int64_t tile, int64_t& r0, int64_t& r1, int64_t& b0, int64_t& b1) {
+        r0 = tile * S32_ROWS;
+        r1 = min(r0 + (int64_t)S32_ROWS, n_nodes);
+        b0 = brow[r0];
+        b1 = brow[r1];
+    };
+
+    int64_t tile = blockIdx.x;
+    if (tid == 0 && tile < n_tiles) {
+        int64_t r0, r1, b0, b1;
+        tile_range(tile, r0, r1, b0, b1);
+        if (b1 > b0) issue(0, b0, min(b1, b0 + (int64_t)S32_CAP));
+    }
+    const float* Xl = X + l * CPT;
+    for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int s = it & 1;
+        int64_t r0, r1, tb0, tb1;
+        tile_range(tile, r0, r1, tb0, tb1);
+        if (tid == 0) {
+            ticket[s ^ 1] = 0;
+            const int64_t nt = tile + gridDim.x;
+            if (nt < n_tiles) {
+                int64_t nr0, nr1, nb0, nb1;
+                tile_range(nt, nr0, nr1, nb0, nb1);
+                if (nb1 > nb0) issue(s ^ 1, nb0, min(nb1, nb0 + (int64_t)S32_CAP));
+            }
+        }
+        const int64_t staged_hi = min(tb1, tb0 + (int64_t)S32_CAP);
+        if (tb1 > tb0) {
+            mbar_wait(&full[s], (phase >> s) & 1u);
+            phase ^= 1u << s;
+        }
+        // record p of the tile lives at stage + (p - (tb0 & ~1)) * 40
+        const unsigned char* stage = smem + s * S32_STAGE_BYTES;
+        const int64_t sb = tb0 & ~int64_t(1);
+        const unsigned char* gbase = reinterpret_cast<const unsigned char*>(rec);
+        for (;;) {
+            int rr = 0;
+            if (lane == 0) rr = atomicAdd(&ticket[s], 1);
+            rr = __shfl_sync(0xffffffffu, rr, 0);
+            const int64_t row = r0 + rr;
+            if (row >= r1) break;
+            const int64_t rb0 = brow[row], rb1 = brow[row + 1];
+            float acc[3][CPT];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int t = 0; t < CPT; ++t) acc[c][t] = 0.f;
+            const int64_t se = min(rb1, staged_hi);          // blocks [rb0, se) are in shared memory
+            int64_t p = rb0 + g;
+            for (; p + NG < se; p += 2 * NG)
+                block_fma2<C, CPT, VEC>(reinterpret_cast<const uint2*>(stage + (p - sb) * S32_REC_BYTES),
+                                        reinterpret_cast<const uint2*>(stage + (p + NG - sb) * S32_REC_BYTES), Xl, acc);
+            if (p < se) {
+                block_fma<C, CPT, VEC>(reinterpret_cast<const uint2*>(stage + (p - sb) * S32_REC_BYTES), Xl, acc);
+                p += NG;
+            }
+            for (; p < rb1; p += NG)                         // overflow of an oversized tile: straight from global
+                block_fma<C, CPT, VEC>(reinterpret_cast<const uint2*>(gbase + p * S32_REC_BYTES), Xl, acc);
+#pragma unroll
+            for (int off = LPR; off < 32; off <<= 1)
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int t = 0; t < CPT; ++t) acc[c][t] += __shfl_xor_sync(0xffffffffu, acc[c][t], off);
+            if (g < 3) {
+                const int64_t o = (3 * row + g) * C + l * CPT;
+                float a[CPT];
+#pragma unroll
+                for (int t = 0; t < CPT; ++t) a[t] = g == 0 ? acc[0][t] : (g == 1 ? acc[1][t] : acc[2][t]);
+                float v[CPT];
+                if (MODE == S32_PLAIN) {
+#pragma unroll
+                    for (int t = 0; t < CPT; ++t) v[t] = a[t];
+                } else if (MODE == S32_RESID) {
+                    float rv[CPT];
+#pragma unroll
+                    for (int q = 0; q < NV; ++q) ld_vec<VEC>(R + o + q * VEC, &rv[q * VEC]);
+#pragma unroll
+                    for (int t = 0; t < CPT; ++t) v[t] = rv[t] - a[t];
+                } else {
+                    const float d0 = __ldg(invD + 9 * row + 3 * g), d1 = __ldg(invD + 9 * row + 3 * g + 1),
+                                d2 = __ldg(invD + 9 * row + 3 * g + 2);
+                    float r0v[CPT], r1v[CPT], r2v[CPT], z[CPT], zp[CPT];
+                    const int64_t ob = 3 * row * C + l * CPT;
+#pragma unroll
+                    for (int q = 0; q < NV; ++q) {
+                        ld_vec<VEC>(R + ob + q * VEC, &r0v[q * VEC]);
+                        ld_vec<VEC>(R + ob + C + q * VEC, &r1v[q * VEC]);
+                        ld_vec<VEC>(R + ob + 2 * C + q * VEC, &r2v[q * VEC]);
+                        ld_vec<VEC>(X + o + q * VEC, &z[q * VEC]);
+                        ld_vec_plain<VEC>(Zprev + o + q * VEC, &zp[q * VEC]);
+                    }
+#pragma unroll
+                    for (int t = 0; t < CPT; ++t) {
+                        const float dr = d0 * (r0v[t] - acc[0][t]) + d1 * (r1v[t] - acc[1][t]) + d2 * (r2v[t] - acc[2][t]);
+                        v[t] = z[t] + ab * (z[t] - zp[t]) + cc * dr;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < NV; ++q) st_vec<VEC>(Out + o + q * VEC, &v[q * VEC]);
+            }
+        }
+        __syncthreads();     // every warp is done with stage s (and ticket[s]) before it is refilled
+    }
+}
+
+// records + block-Jacobi inverse from the FP64 matrix: one warp per node row
+__global__ void __launch_bounds__(256)
+k_pack_k32(const int32_t* __restrict__ brow, const int32_t* __restrict__ bcol, int64_t n_nodes,
+           const double* __restrict__ Kval, const double* __restrict__ Mblk, double shift,
+           uint32_t* __restrict__ rec, float* __restrict__ invD) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (row >= n_nodes) return;
+    const int64_t b0 = brow[row];
+    const int deg = (int)(brow[row + 1] - b0);
+    const double* kb = Kval + 9 * b0;
+    const int64_t rs = 3 * (int64_t)deg;
+    for (int p = lane; p < deg; p += 32) {
+        const int32_t j = bcol[b0 + p];
+        double k[9];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) k[3 * c + d] = kb[c * rs + 3 * p + d];
+        if (Mblk != nullptr && shift != 0.0) {
+            const double m = shift * Mblk[b0 + p];
+            k[0] += m; k[4] += m; k[8] += m;
+        }
+        uint32_t* o = rec + (b0 + p) * 10;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) o[q] = __float_as_uint((float)k[q]);
+        o[9] = (uint32_t)j;
+        if (j == row) {
+            const double c00 = k[4] * k[8] - k[5] * k[7];
+            const double c01 = k[5] * k[6] - k[3] * k[8];
+            const double c02 = k[3] * k[7] - k[4] * k[6];
+            const double id = 1.0 / (k[0] * c00 + k[1] * c01 + k[2] * c02);
+            float* iv = invD + 9 * row;
+            iv[0] = (float)(c00 * id);
+            iv[1] = (float)((k[2] * k[7] - k[1] * k[8]) * id);
+            iv[2] = (float)((k[1] * k[5] - k[2] * k[4]) * id);
+            iv[3] = (float)(c01 * id);
+            iv[4] = (float)((k[0] * k[8] - k[2] * k[6]) * id);
+            iv[5] = (float)((k[2] * k[3] - k[0] * k[5]) * id);
+            iv[6] = (float)(c02 * id);
+            iv[7] = (float)((k[1] * k[6] - k[0] * k[7]) * id);
+            iv[8] = (float)((k[0] * k[4] - k[1] * k[3]) * id);
+        }
+    }
+}
+
+// Out = cc * invD R   (first Chebyshev step from a zero initial guess); one thread per (node, 4 columns)
+__global__ void k_jacobi32(const float* __restrict__ invD, const float* __restrict__ R, int64_t n_nodes, int c4,
+                           float cc, float* __restrict__ Out) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_nodes * c4) return;
+    const int64_t row = t / c4;
+    const int q = (int)(t - row * c4);
+    const int C = 4 * c4;
+    const float4 r0 = __ldg(reinterpret_cast<const float4*>(R + 3 * row * C) + q);
+    const float4 r1 = __ldg(reinterpret_cast<const float4*>(R + (3 * row + 1) * C) + q);
+    const float4 r2 = __ldg(reinterpret_cast<const float4*>(R + (3 * row + 2) * C) + q);
+    const float* d = invD + 9 * row;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float d0 = cc * d[3 * c], d1 = cc * d[3 * c + 1], d2 = cc * d[3 * c + 2];
+        float4 v;
+        v.x = d0 * r0.x + d1 * r1.x + d2 * r2.x;
+        v.y = d0 * r0.y + d1 * r1.y + d2 * r2.y;
+        v.z = d0 * r0.z + d1 * r1.z + d2 * r2.z;
+        v.w = d0 * r0.w + d1 * r1.w + d2 * r2.w;
+        reinterpret_cast<float4*>(Out + (3 * row + c) * C)[q] = v;
+    }
+}
+
+// dst32[:, s] = (float) src64[:, idx[s]] for s < count, 0 for count <= s < width
+__global__ void k_gather_cols_f32(const double* __restrict__ src, int64_t lds, const __grid_constant__ ColIdx idx,
+                                  int count, int width, int64_t n, float* __restrict__ dst) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n * width) return;
+    const int64_t row = t / width;
+    const int s = (int)(t - row * width);
+    dst[t] = s < count ? (float)src[row * lds + idx.v[s]] : 0.f;
+}
+
+// dst64[:, :width] (ld) = (double) src32 (n x width)
+__global__ void k_widen_f32(const float* __restrict__ src, int width, int64_t n, double* __restrict__ dst, int64_t ldd) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n * width) return;
+    const int64_t row = t / width;
+    const int s = (int)(t - row * width);
+    dst[row * ldd + s] = (double)src[t];
+}
+
+// per-column sum of squares of an fp32 block (n x w), fp64 accumulation; partial[cta][w]
+__global__ void k_colnorm2_f32(const float* __restrict__ V, int w, int64_t n, double* __restrict__ partial) {
+    extern __shared__ double sh[];
+    const int rpp = blockDim.x / w;
+    const int c = threadIdx.x % w, rr = threadIdx.x / w;
+    double s = 0.0;
+    if (rr < rpp) {
+        for (int64_t row = (int64_t)blockIdx.x * rpp + rr; row < n; row += (int64_t)gridDim.x * rpp) {
+            const double v = (double)V[row * w + c];
+            s = fma(v, v, s);
+        }
+        sh[rr * w + c] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < w) {
+        double t = 0.0;
+        for (int r2 = 0; r2 < rpp; ++r2) t += sh[r2 * w + threadIdx.x];
+        partial[(size_t)blockIdx.x * w + threadIdx.x] = t;
+    }
+}
+
+// ---- two-level transfer operators (nodes; 3 components x c columns per node) -------------------
+// rc[I] = 0.5 * sum_{t in rptr[I]..rptr[I+1]} res[rlist[t]]      (P^T, gather form, fixed order)
+__global__ void k_restrict32(const int32_t* __restrict__ rptr, const int32_t* __restrict__ rlist, int64_t n_coarse,
+                             const float* __restrict__ res, int c4x3, float* __restrict__ rc) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_coarse * c4x3) return;
+    const int64_t I = t / c4x3;
+    const int q = (int)(t - I * c4x3);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int e = rptr[I + 1];
+    for (int u = rptr[I]; u < e; ++u) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(res) + (int64_t)rlist[u] * c4x3 + q);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    s.x *= 0.5f; s.y *= 0.5f; s.z *= 0.5f; s.w *= 0.5f;
+    reinterpret_cast<float4*>(rc)[t] = s;
+}
+
+// z[i] += 0.5 * (zc[par[2i]] + zc[par[2i+1]])                  (P)
+__global__ void k_prolong_add32(const int32_t* __restrict__ par, int64_t n_fine, const float* __restrict__ zc, int c4x3,
+                                float* __restrict__ z) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_fine * c4x3) return;
+    const int64_t i = t / c4x3;
+    const int q = (int)(t - i * c4x3);
+    const int2 pp = __ldg(reinterpret_cast<const int2*>(par) + i);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(zc) + (int64_t)pp.x * c4x3 + q);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(zc) + (int64_t)pp.y * c4x3 + q);
+    float4 v = reinterpret_cast<float4*>(z)[t];
+    v.x += 0.5f * (a.x + b.x); v.y += 0.5f * (a.y + b.y); v.z += 0.5f * (a.z + b.z); v.w += 0.5f * (a.w + b.w);
+    reinterpret_cast<float4*>(z)[t] = v;
+}
+
+// fp64 variant used to prolong a coarse eigenvector block into the fine start block
+__global__ void k_prolong64(const int32_t* __restrict__ par, int64_t n_fine, const double* __restrict__ xc, int64_t ldc,
+                            int w, double* __restrict__ x, int64_t ldx) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_fine * 3 * w) return;
+    const int64_t i = t / (3 * w);
+    const int r = (int)(t - i * 3 * w);
+    const int c = r / w, s = r - c * w;
+    const int2 pp = __ldg(reinterpret_cast<const int2*>(par) + i);
+    x[(3 * i + c) * ldx + s] = 0.5 * (xc[(3 * (int64_t)pp.x + c) * ldc + s] + xc[(3 * (int64_t)pp.y + c) * ldc + s]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int s32_grid(int64_t n_nodes) {
+    static int ctas_per_sm = 0, sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_spmm32<8, 6, S32_CHEB>, S32_THREADS, S32_SMEM);
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    }
+    const int64_t tiles = ceil_div(n_nodes, S32_ROWS);
+    const int64_t g = (int64_t)sms * ctas_per_sm;
+    return (int)(tiles < g ? tiles : g);
+}
+
+template <int LPR, int CPT>
+static int launch_spmm32(int mode, const int32_t* brow, const void* rec, int64_t n_nodes, const float* X, const float* R,
+                         const float* invD, const float* Zprev, float* Out, float ab, float cc, cudaStream_t st) {
+    const int grid = s32_grid(n_nodes);
+    auto go = [&](auto kern) -> int {
+        kern<<<grid, S32_THREADS, S32_SMEM, st>>>(brow, reinterpret_cast<const uint2*>(rec), n_nodes, X, R, invD, Zprev,
+                                                  Out, ab, cc);
+        DS_LAUNCH_CHECK();
+        return DS_OK;
+    };
+    switch (mode) {
+        case S32_PLAIN: return go(k_spmm32<LPR, CPT, S32_PLAIN>);
+        case S32_RESID: return go(k_spmm32<LPR, CPT, S32_RESID>);
+        default: return go(k_spmm32<LPR, CPT, S32_CHEB>);
+    }
+}
+
+int spmm32(int mode, const int32_t* brow, const void* rec, int64_t n_nodes, int ncols, const float* X, const float* R,
+           const float* invD, const float* Zprev, float* Out, float ab, float cc, int prof_cls, cudaStream_t st) {
+    DS_REQUIRE(brow && rec && X && Out, "spmm32: null argument");
+    DS_REQUIRE(X != Out, "spmm32: the gathered block must not alias the output");
+    DS_REQUIRE(mode == S32_PLAIN || R, "spmm32: this mode needs R");
+    DS_REQUIRE(mode != S32_CHEB || (invD && Zprev), "spmm32: Chebyshev mode needs invD and Zprev");
+    ProfScope prof(prof_cls, st);
+    switch (ncols) {
+        case 16: return launch_spmm32<4, 4>(mode, brow, rec, n_nodes, X, R, invD, Zprev, Out, ab, cc, st);
+        case 32: return launch_spmm32<8, 4>(mode, brow, rec, n_nodes, X, R, invD, Zprev, Out, ab, cc, st);
+        case 48: return launch_spmm32<8, 6>(mode, brow, rec, n_nodes, X, R, invD, Zprev, Out, ab, cc, st);
+        case 64: return launch_spmm32<8, 8>(mode, brow, rec, n_nodes, X, R, invD, Zprev, Out, ab, cc, st);
+        default: set_error("spmm32: ncols=%d must be 16, 32, 48 or 64", ncols); return DS_ERR_ARG;
+    }
+}
+
+int pack_k32(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, const double* Kval, const double* Mblk,
+             double shift, void* rec, float* invD, cudaStream_t st) {
+    DS_REQUIRE(brow && bcol && Kval && rec && invD, "pack_k32: null argument");
+    DS_REQUIRE(((uintptr_t)rec & 15) == 0, "pack_k32: records must be 16-byte aligned");
+    ProfScope prof(PROF_COPY, st);
+    k_pack_k32<<<(unsigned)ceil_div(n_nodes * 32, 256), 256, 0, st>>>(brow, bcol, n_nodes, Kval, Mblk, shift,
+                                                                      reinterpret_cast<uint32_t*>(rec), invD);
+    DS_LAUNCH_CHECK();
+    return DS_OK;
+}
+
+int jacobi32(const float* invD, const float* R, int64_t n_nodes, int ncols, float cc, float* Out, cudaStream_t st) {
+    ProfScope prof(PROF_CHEB, st);
+    const int c4 = ncols / 4;
+    k_jacobi32<<<(unsigned)ceil_div(n_nodes * c4, 256), 256, 0, st>>>(invD, R, n_nodes, c4, cc, Out);
+    DS_LAUNCH_CHECK();
+    return DS_OK;
+}
+
+int restrict32(const int32_t* rptr, const int32_t* rlist, int64_t n_coarse, const float* res, int ncols, float* rc,
+               cudaStream_t st) {
+    ProfScope prof(PROF_TRANSFER, st);
+    const int q = 3 * ncols / 4;
+    k_restrict32<<<(unsigned)ceil_div(n_coarse * q, 256), 256, 0, st>>>(rptr, rlist, n_coarse, res, q, rc);
+    DS_LAUNCH_CHECK();
+    return DS_OK;
+}
+
+int prolong_add32(const int32_t* par, int64_t n_fine, const float* zc, int ncols, float* z, cudaStream_t st) {
+    ProfScope prof(PROF_TRANSFER, st);
+    const int q = 3 * ncols / 4;
+    k_prolong_add32<<<(unsigned)ceil_div(n_fine * q, 256), 256, 0, st>>>(par, n_fine, zc, q, z);
+    DS_LAUNCH_CHECK();
+    return DS_OK;
+}
+
+int prolong64(const int32_t* par, int64_t n_fine, const double* xc, int64_t ldc, int w, double* x, int64_t ldx,
+              cudaStream_t st) {
+    ProfScope prof(PROF_TRANSFER, st);
+    k_prolong64<<<(unsigned)ceil_div(n_fine * 3 * w, 256), 256, 0, st>>>(par, n_fine, xc, ldc, w, x, ldx);
+    DS_LAUNCH_CHECK();
+    return DS_OK;
+}
+
+int gather_cols_f32(const double* src, int64_t lds, const ColIdx& idx, int count, int width, int64_t n, float* dst,
+                    cudaStream_t st) {
+    ProfScope prof(PROF_COPY, st);
+    k_gather_cols_f32<<<(unsigned)ceil_div(n * width, 256), 256, 0, st>>>(src, lds, idx, count, width, n, dst);
+    DS_LAUNCH_CHECK();
+    return DS_OK;
+}
+
+int widen_f32(const float* src, int width, int64_t n, double* dst, int64_t ldd, cudaStream_t st) {
+    ProfScope prof(PROF_COPY, st);
+    k_widen_f32<<<(unsigned)ceil_div(n * width, 256), 256, 0, st>>>(src, width, n, dst, ldd);
+    DS_LAUNCH_CHECK();
+    return DS_OK;
+}
+
+__global__ void k_fill_random_f32(float* __restrict__ V, int64_t count, uint64_t seed) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(t + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    V[t] = (float)((double)(z >> 11) * (2.0 / 9007199254740992.0) - 1.0);
+}
+
+int fill_random_f32(float* V, int64_t count, uint64_t seed, cudaStream_t st) {
+    k_fill_random_f32<<<(unsigned)ceil_div(count, 256), 256, 0, st>>>(V, count, seed);
+    DS_LAUNCH_CHECK();
+    return DS_OK;
+}
+
+int colnorm2_f32(const float* V, int w, int64_t n, double* partial, int ctas, cudaStream_t st) {
+    const int threads = (1024 / w) * w;
+    const size_t sm = (size_t)(threads / w) * w * sizeof(double);
+    k_colnorm2_f32<<<ctas, threads, sm, st>>>(V, w, n, partial);
+    DS_LAUNCH_CHECK();
+    return DS_OK;
+}
+
+// ---- Level32 -----------------------------------------------------------------------------------
+size_t Level32::bytes(int64_t n_nodes, int64_t nnzb) {
+    auto al = [](size_t b) { return ((b + 255) & ~size_t(255)) + 256; };
+    return al((size_t)nnzb * S32_REC_BYTES + 64) + al((size_t)n_nodes * 9 * sizeof(float));
+}
+
+int Level32::setup(Arena& a, const int32_t* brow_, const int32_t* bcol, int64_t n_nodes_, int64_t nnzb_,
+                   const double* Kval, const double* Mblk, double shift, cudaStream_t st) {
+    brow = brow_;
+    n_nodes = n_nodes_;
+    nnzb = nnzb_;
+    rec = a.take<unsigned char>((size_t)nnzb * S32_REC_BYTES + 64);
+    invD = a.take<float>((size_t)n_nodes * 9);
+    DS_REQUIRE(rec && invD, "Level32: workspace arena exhausted");
+    DS_CUDA(cudaMemsetAsync(rec + (size_t)nnzb * S32_REC_BYTES, 0, 64, st));    // TMA reads up to 8 bytes past the end
+    return pack_k32(brow, bcol, n_nodes, Kval, Mblk, shift, rec, invD, st);
+}
+
+// z = p(invD A) invD r by `degree` Chebyshev steps on [lmax/ratio, lmax].
+//   from_zero: z0 = 0 (first step is a pure Jacobi scaling); else z0 = contents of *zc.
+// zc / zp: ping-pong buffers; on return *zc holds the result.
+int Level32::cheb(const float* r, int ncols, int degree, double ratio, bool from_zero, float** zc, float** zp,
+                  cudaStream_t st) {
+    const double lmin = lmax / ratio;
+    const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sig = theta / delta;
+    double rho = 1.0 / sig;
+    int k = 0;
+    if (from_zero) {
+        DS_TRY(jacobi32(invD, r, n_nodes, ncols, (float)(1.0 / theta), *zc, st));
+    } else {
+        DS_TRY(spmm32(S32_CHEB, brow, rec, n_nodes, ncols, *zc, r, invD, *zc, *zp, 0.f, (float)(1.0 / theta), prof_cls,
+                      st));
+        std::swap(*zc, *zp);
+        ++launches;
+        cols += ncols;
+    }
+    for (k = 1; k < degree; ++k) {
+        const double rho_new = 1.0 / (2.0 * sig - rho);
+        const float ab = (float)(rho_new * rho);
+        const float cc = (float)(2.0 * rho_new / delta);
+        // z_{k+1} = z_k + ab (z_k - z_{k-1}) + cc invD (r - A z_k); for k == 1 from zero, z_0 = 0
+        if (k == 1 && from_zero) DS_CUDA(cudaMemsetAsync(*zp, 0, sizeof(float) * 3 * (size_t)n_nodes * ncols, st));
+        DS_TRY(spmm32(S32_CHEB, brow, rec, n_nodes, ncols, *zc, r, invD, *zp, *zp, ab, cc, prof_cls, st));
+        std::swap(*zc, *zp);
+        rho = rho_new;
+        ++launches;
+        cols += ncols;
+    }
+    return DS_OK;
+}
+
+}  // namespace ds
+
+using namespace ds;
+
+extern "C" int64_t ds_k32_record_bytes(int64_t nnzb) { return nnzb * S32_REC_BYTES + 64; }
+
+extern "C" int ds_k32_pack(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, int64_t nnzb, const double* Kval,
+                           const double* Mblk, double shift, void* rec, float* invD, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    DS_REQUIRE(rec, "ds_k32_pack: null argument");
+    DS_CUDA(cudaMemsetAsync(reinterpret_cast<unsigned char*>(rec) + nnzb * S32_REC_BYTES, 0, 64, st));
+    return pack_k32(brow, bcol, n_nodes, Kval, Mblk, shift, rec, invD, st);
+}
+
+extern "C" int ds_spmm32(int mode, const int32_t* brow, const void* rec, int64_t n_nodes, int ncols, const float* X,
+                         const float* R, const float* invD, const float* Zprev, float* Out, double ab, double cc,
+                         void* stream) {
+    DS_REQUIRE(mode >= 0 && mode <= 2, "ds_spmm32: mode must be 0 (A X), 1 (R - A X) or 2 (Chebyshev step)");
+    return spmm32(mode, brow, rec, n_nodes, ncols, X, R, invD, Zprev, Out, (float)ab, (float)cc, PROF_CHEB,
+                  (cudaStream_t)stream);
+}
+
+extern "C" int ds_pmg_restrict32(const int32_t* rptr, const int32_t* rlist, int64_t n_coarse, const float* res,
+                                 int ncols, float* rc, void* stream) {
+    DS_REQUIRE(rptr && rlist && res && rc && ncols % 4 == 0, "ds_pmg_restrict32: bad argument");
+    return restrict32(rptr, rlist, n_coarse, res, ncols, rc, (cudaStream_t)stream);
+}
+
+extern "C" int ds_pmg_prolong_add32(const int32_t* parents, int64_t n_fine, const float* zc, int ncols, float* z,
+                                    void* stream) {
+    DS_REQUIRE(parents && zc && z && ncols % 4 == 0, "ds_pmg_prolong_add32: bad argument");
+    return prolong_add32(parents, n_fine, zc, ncols, z, (cudaStream_t)stream);
+}

@@ -66,7 +66,8 @@ static void drain() {
 }
 
 static const char* kNames[PROF_NCLASS] = {"pattern", "geometry", "assemble", "spmm", "cheb_step", "gram", "block_gemm",
-                                          "eigh", "residual", "copy", "grad_shape", "quadforms", "synth", "other"};
+                                          "eigh", "residual", "copy", "grad_shape", "quadforms", "synth", "other",
+                                          "coarse_step", "transfer"};
 
 }  // namespace ds
 

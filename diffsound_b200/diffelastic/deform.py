@@ -60,6 +60,24 @@ class Deform:
         return self._incidence
 
     @property
+    def coarse(self):
+        """P1 level of a quadratic mesh (two-level eigensolver preconditioner); None for linear tets."""
+        if self.tetmesh.order != 2:
+            return None
+        if not hasattr(self, "_coarse"):
+            self._coarse = native.CoarseLevel(self.verts_f32(), self.tets_i32)
+            self._coarse.ctab = _mm.stiffness_contraction_table(1).to(self.device)
+            self._coarse.mtabs = {}
+        return self._coarse
+
+    def coarse_mtab(self, density):
+        key = float(density)
+        cache = self.coarse.mtabs
+        if key not in cache:
+            cache[key] = _mm.mass_density_table(1, key).to(self.device)
+        return cache[key]
+
+    @property
     def ctab(self):
         if not hasattr(self, "_ctab"):
             self._ctab = _mm.stiffness_contraction_table(self.tetmesh.order).to(self.device)

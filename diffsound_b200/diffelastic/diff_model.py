@@ -154,6 +154,7 @@ class DiffSoundObj:
     # relative residual ||K u - lam M u|| / (lam ||M u||).  Eigenvalue error ~ tol^2, eigenvector (and
     # therefore d(lambda)/d(theta)) error ~ tol * lam / gap: 1e-5 keeps the gradient inside 1e-5.
     eig_tol = 1e-5
+    two_level = True        # quadratic meshes: p-multigrid preconditioner (P1 coarse level) in the eigensolver
     eig_maxit = 400
 
     def __init__(self, vertices=None, tets=None, mode_num=16, mat=MatSet.Ceramic, order=1, mat_model=FixedLinear,
@@ -311,8 +312,17 @@ class DiffSoundObj:
             raise ValueError(f"mesh too small for {k} modes (n={pat.n})")
         X = self._start_block(m)
         deg = int(min(40, max(8, round(pat.n ** (1.0 / 3.0) / 3.0))))
+        kw = {}
+        coarse = self.deform.coarse if self.two_level else None
+        if coarse is not None and 3 * coarse.n_nodes >= 3 * m:
+            # two-level p-multigrid preconditioner: P1 operator of the same mesh, same material
+            mu, la = self._lame_used
+            coarse.assemble(self._verts32, mu, la, coarse.ctab, self.deform.coarse_mtab(self._density_used))
+            cdeg = int(min(64, max(6, round((3 * coarse.n_nodes) ** (1.0 / 3.0) / 1.2))))
+            kw = dict(coarse=coarse, smooth_steps=3, smooth_ratio=8.0, coarse_degree=cdeg,
+                      coarse_ratio=0.4 * cdeg * cdeg)
         lam, res, stats = native.lobpcg(pat, self._Kval, self._Mblk, X, nev=need, tol=self.eig_tol, maxit=self.eig_maxit,
-                                        cheb_degree=deg, cheb_ratio=0.4 * deg * deg, n_rigid=6)
+                                        cheb_degree=deg, cheb_ratio=0.4 * deg * deg, n_rigid=6, **kw)
         if stats["status"] != 0:
             raise RuntimeError(f"eigensolver did not converge: {stats}, max residual {float(res[:need].max()):.3e}")
         self.eig_stats = stats

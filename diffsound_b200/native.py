@@ -242,10 +242,100 @@ def eigh_generalized(GK, GM, sigma):
     return theta, Cm, info
 
 
+class CoarseLevel:
+    """P1 level of a quadratic mesh for the two-level preconditioner (csrc/pmg.cu): corner numbering,
+    coarse tets / vertices, prolongation parents and the gather lists of its transpose, plus the
+    block pattern of the P1 operator.  Topology only; values come from `assemble_km(order=1)`."""
+
+    def __init__(self, verts_f32, tets_i32):
+        lib = _lib.load()
+        assert tets_i32.dtype == torch.int32 and tets_i32.shape[1] == 10 and tets_i32.is_contiguous()
+        dev = tets_i32.device
+        T = tets_i32.shape[0]
+        n_nodes = verts_f32.shape[0]
+        i32 = dict(dtype=torch.int32, device=dev)
+        ws = workspace(dev)
+        self.cid = torch.empty(n_nodes, **i32)
+        nc = C.c_int64(0)
+        with torch.cuda.device(dev):
+            _lib.check(lib.ds_pmg_coarse_count(ws.handle, _p(tets_i32), T, n_nodes, _p(self.cid), C.byref(nc), _stream()),
+                       "ds_pmg_coarse_count")
+            self.n_nodes = int(nc.value)
+            self.tets = torch.empty(T, 4, **i32)
+            self.verts = torch.empty(self.n_nodes, 3, dtype=torch.float32, device=dev)
+            self.parents = torch.empty(2 * n_nodes, **i32)
+            self.rptr = torch.empty(self.n_nodes + 1, **i32)
+            self.rlist = torch.empty(2 * n_nodes, **i32)
+            _lib.check(lib.ds_pmg_coarse_fill(ws.handle, _p(verts_f32), _p(tets_i32), T, n_nodes, _p(self.cid),
+                                              self.n_nodes, _p(self.tets), _p(self.verts), _p(self.parents),
+                                              _p(self.rptr), _p(self.rlist), _stream()), "ds_pmg_coarse_fill")
+        self.n_fine_nodes = n_nodes
+        self.pattern = Pattern(self.tets, self.n_nodes)
+        self.corner_nodes = torch.nonzero(self.cid >= 0).squeeze(1)     # fine id of coarse node c, ascending
+        self.Kval = self.Mblk = self.geom = None
+
+    def assemble(self, verts_f32, mu, lam, ctab1, mtab1):
+        """P1 stiffness (and mass) on the corner nodes at the current vertex positions."""
+        self.verts = verts_f32[self.corner_nodes].contiguous()
+        if self.geom is None:
+            self.geom = torch.empty(self.tets.shape[0] * 14, dtype=torch.float64, device=self.tets.device)
+        self.Kval, self.Mblk = assemble_km(self.verts, self.tets, 1, self.pattern, mu, lam, ctab1, mtab1,
+                                           Kval=self.Kval, Mblk=self.Mblk, geom=self.geom)
+
+    def struct(self):
+        assert self.Kval is not None, "CoarseLevel: assemble the P1 operator first"
+        return _lib.PmgLevel(brow=self.pattern.brow.data_ptr(), bcol=self.pattern.bcol.data_ptr(),
+                             n_nodes=self.n_nodes, nnzb=self.pattern.nnzb, Kval=self.Kval.data_ptr(),
+                             Mblk=self.Mblk.data_ptr() if self.Mblk is not None else None,
+                             parents=self.parents.data_ptr(), rptr=self.rptr.data_ptr(), rlist=self.rlist.data_ptr())
+
+
+def k32_pack(pattern, Kval, Mblk=None, shift=0.0):
+    """FP32 block records + block-Jacobi inverses of K + shift M (ds_k32_pack)."""
+    lib = _lib.load()
+    dev = Kval.device
+    rec = torch.empty((lib.ds_k32_record_bytes(pattern.nnzb) + 15) // 16 * 4, dtype=torch.int32, device=dev)
+    invD = torch.empty(pattern.n_nodes * 9, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ds_k32_pack(_p(pattern.brow), _p(pattern.bcol), pattern.n_nodes, pattern.nnzb, _p(Kval),
+                                   _p(Mblk), float(shift), _p(rec), _p(invD), _stream()), "ds_k32_pack")
+    return rec, invD
+
+
+def spmm32(pattern, rec, X, mode=0, R=None, invD=None, Zprev=None, ab=0.0, cc=0.0, out=None):
+    """mode 0: A X; 1: R - A X; 2: X + ab (X - Zprev) + cc invD (R - A X).  fp32 (n, ncols) contiguous."""
+    lib = _lib.load()
+    assert X.dtype == torch.float32 and X.is_contiguous()
+    if out is None:
+        out = torch.empty_like(X)
+    with torch.cuda.device(X.device):
+        _lib.check(lib.ds_spmm32(int(mode), _p(pattern.brow), _p(rec), pattern.n_nodes, X.shape[1], _p(X), _p(R),
+                                 _p(invD), _p(Zprev), _p(out), float(ab), float(cc), _stream()), "ds_spmm32")
+    return out
+
+
+def pmg_restrict32(coarse, res):
+    lib = _lib.load()
+    rc = torch.empty(3 * coarse.n_nodes, res.shape[1], dtype=torch.float32, device=res.device)
+    with torch.cuda.device(res.device):
+        _lib.check(lib.ds_pmg_restrict32(_p(coarse.rptr), _p(coarse.rlist), coarse.n_nodes, _p(res), res.shape[1],
+                                         _p(rc), _stream()), "ds_pmg_restrict32")
+    return rc
+
+
+def pmg_prolong_add32(coarse, zc, z):
+    lib = _lib.load()
+    with torch.cuda.device(z.device):
+        _lib.check(lib.ds_pmg_prolong_add32(_p(coarse.parents), coarse.n_fine_nodes, _p(zc), z.shape[1], _p(z),
+                                            _stream()), "ds_pmg_prolong_add32")
+    return z
+
+
 def lobpcg(pattern, Kval, Mblk, X, nev, tol=1e-4, maxit=200, cheb_degree=8, sigma=0.0, cheb_ratio=30.0, n_rigid=6,
-           verbose=0):
+           verbose=0, coarse=None, smooth_steps=3, smooth_ratio=8.0, coarse_degree=20, coarse_ratio=160.0):
     """Lowest `nev` pairs of K u = lam M u from the start block X (n, m) fp64 (overwritten with the
-    M-orthonormal Ritz vectors).  Returns (lam (m,), resid (m,), stats dict)."""
+    M-orthonormal Ritz vectors).  `coarse`: a CoarseLevel with assembled Kval -> two-level
+    preconditioner.  Returns (lam (m,), resid (m,), stats dict)."""
     lib = _lib.load()
     assert X.dtype == torch.float64 and X.is_contiguous()
     n, m = X.shape
@@ -253,14 +343,20 @@ def lobpcg(pattern, Kval, Mblk, X, nev, tol=1e-4, maxit=200, cheb_degree=8, sigm
     lam = torch.empty(m, dtype=torch.float64, device=dev)
     res = torch.empty(m, dtype=torch.float64, device=dev)
     opts = _lib.LobpcgOpts(nev=int(nev), maxit=int(maxit), cheb_degree=int(cheb_degree), tol=float(tol),
-                           sigma=float(sigma), cheb_ratio=float(cheb_ratio), n_rigid=int(n_rigid), verbose=int(verbose))
+                           sigma=float(sigma), cheb_ratio=float(cheb_ratio), n_rigid=int(n_rigid), verbose=int(verbose),
+                           smooth_steps=int(smooth_steps), coarse_degree=int(coarse_degree),
+                           smooth_ratio=float(smooth_ratio), coarse_ratio=float(coarse_ratio))
     stats = (C.c_int64 * 8)()
     ws = workspace(dev)
+    lvl = coarse.struct() if coarse is not None else None
     with torch.cuda.device(dev):
         _lib.check(lib.ds_lobpcg(ws.handle, _p(pattern.brow), _p(pattern.bcol), pattern.n_nodes, _p(Kval), _p(Mblk),
-                                 _p(X), m, C.byref(opts), _p(lam), _p(res), stats, _stream()), "ds_lobpcg")
+                                 C.byref(lvl) if lvl is not None else None, _p(X), m, C.byref(opts), _p(lam), _p(res),
+                                 stats, _stream()), "ds_lobpcg")
     return lam, res, dict(iterations=int(stats[0]), converged=int(stats[1]), spmm=int(stats[2]), status=int(stats[3]),
-                          cheb_steps=int(stats[4]), cheb_cols_avg=(stats[5] / stats[4] if stats[4] else 0.0))
+                          cheb_steps=int(stats[4]), cheb_cols_avg=(stats[5] / stats[4] if stats[4] else 0.0),
+                          coarse_steps=int(stats[6]), coarse_cols_avg=(stats[7] / stats[6] if stats[6] else 0.0),
+                          two_level=coarse is not None)
 
 
 def corner_incidence(tets_i32, order, n_nodes):

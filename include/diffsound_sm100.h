@@ -125,8 +125,12 @@ int ds_eigh_generalized_f64(const double* GK, const double* GM, int N, int64_t l
  * X: fp64 [n x m] row-major start block on entry (m >= nev, multiple of 16),
  * M-orthonormal Ritz vectors on exit; lambda_out [m]; resid_out [m] relative
  * residuals; stats_host (host int64[8]) = {iterations, converged, spmm_count, status,
- * chebyshev kernel launches, sum over those launches of the column count, 0, 0}.
- * Preconditioner: `cheb_degree` steps of block-Jacobi Chebyshev on K + sigma*M.
+ * fine-level FP32 SpMM launches, sum over those launches of the column count,
+ * coarse-level launches, sum of their column counts}.
+ * Preconditioner (FP32, see ds_spmm32): `cheb_degree` steps of block-Jacobi Chebyshev on
+ * K + sigma*M, or, when `coarse` is given (quadratic meshes), a two-level p-multigrid V-cycle:
+ * `smooth_steps` Chebyshev-Jacobi steps on [lmax/smooth_ratio, lmax] before and after a
+ * `coarse_degree`-step Chebyshev solve on the P1 operator.
  * Synchronises the stream. */
 typedef struct ds_lobpcg_opts {
     int nev;            /* number of pairs that must converge (lowest nev) */
@@ -137,11 +141,59 @@ typedef struct ds_lobpcg_opts {
     double cheb_ratio;  /* lmax / lmin of the Chebyshev interval */
     int n_rigid;        /* leading columns that hold (near-)null-space vectors; -1: detect */
     int verbose;
+    int smooth_steps;   /* two-level only: Chebyshev-Jacobi steps per smoothing leg (default 3) */
+    int coarse_degree;  /* two-level only: Chebyshev steps of the coarse solve */
+    double smooth_ratio;/* lmax / lmin of the smoother interval (default 8) */
+    double coarse_ratio;/* lmax / lmin of the coarse Chebyshev interval */
 } ds_lobpcg_opts;
+/* Coarse level of the two-level preconditioner: the P1 operator on the corner nodes of a quadratic
+ * mesh (pattern + values from ds_pattern_* / ds_assemble_km at order 1 on ds_pmg_coarse_fill's
+ * output) and the transfer tables.  All device pointers. */
+typedef struct ds_pmg_level {
+    const int32_t* brow;      /* [n_nodes+1] */
+    const int32_t* bcol;      /* [nnzb] */
+    int64_t n_nodes;          /* coarse (corner) nodes */
+    int64_t nnzb;
+    const double* Kval;       /* [9*nnzb] */
+    const double* Mblk;       /* [nnzb] or NULL (only used with sigma > 0) */
+    const int32_t* parents;   /* [2*n_fine_nodes]: fine node i = 0.5 (coarse parents[2i] + parents[2i+1]) */
+    const int32_t* rptr;      /* [n_nodes+1]  transpose (gather) lists of the prolongation */
+    const int32_t* rlist;     /* [2*n_fine_nodes] */
+} ds_pmg_level;
 int ds_lobpcg(ds_workspace* ws, const int32_t* brow, const int32_t* bcol, int64_t n_nodes,
-              const double* Kval, const double* Mblk, double* X, int m,
-              const ds_lobpcg_opts* opts, double* lambda_out, double* resid_out,
+              const double* Kval, const double* Mblk, const ds_pmg_level* coarse /* may be NULL */,
+              double* X, int m, const ds_lobpcg_opts* opts, double* lambda_out, double* resid_out,
               int64_t* stats_host, void* stream);
+
+/* ---- FP32 preconditioner pieces (exported for tests and for callers that build their own cycle) ---
+ * No reference counterpart: the reference factorises K - sigma M with SuperLU on the CPU
+ * (diff_model.py:356-358).  rec: ds_k32_record_bytes(nnzb) bytes, 16-byte aligned, one 40-byte
+ * record {k00..k22 (fp32), bcol} per block of K + shift*M; invD: fp32 [9*n_nodes] inverses of the
+ * diagonal blocks.  ds_spmm32 modes: 0: Out = A X; 1: Out = R - A X; 2 (one Chebyshev step):
+ * Out = X + ab (X - Zprev) + cc invD (R - A X), Zprev may alias Out, X must not.  Dense blocks are
+ * fp32 row-major [3*n_nodes x ncols] with ld = ncols in {16, 32, 48, 64}. */
+int64_t ds_k32_record_bytes(int64_t nnzb);
+int ds_k32_pack(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, int64_t nnzb,
+                const double* Kval, const double* Mblk, double shift, void* rec, float* invD,
+                void* stream);
+int ds_spmm32(int mode, const int32_t* brow, const void* rec, int64_t n_nodes, int ncols,
+              const float* X, const float* R, const float* invD, const float* Zprev, float* Out,
+              double ab, double cc, void* stream);
+/* Quadratic -> linear coarsening (integer work).  tets: int32 [T*10] in the reference's local
+ * order (mesh.py:139-154: corners at 0,2,4,9).  cid[n_nodes]: coarse id of each corner node
+ * (ascending fine id) or -1; ds_pmg_coarse_count synchronises and returns n_coarse.
+ * ds_pmg_coarse_fill writes ctets [T*4], cverts fp32 [n_coarse*3], parents [2*n_nodes] (8-byte
+ * aligned), rptr [n_coarse+1], rlist [2*n_nodes]. */
+int ds_pmg_coarse_count(ds_workspace* ws, const int32_t* tets, int64_t T, int64_t n_nodes,
+                        int32_t* cid, int64_t* n_coarse_host, void* stream);
+int ds_pmg_coarse_fill(ds_workspace* ws, const float* verts, const int32_t* tets, int64_t T,
+                       int64_t n_nodes, const int32_t* cid, int64_t n_coarse, int32_t* ctets,
+                       float* cverts, int32_t* parents, int32_t* rptr, int32_t* rlist, void* stream);
+/* rc = P^T res, z += P zc on fp32 blocks [3*nodes x ncols] (ncols multiple of 4) */
+int ds_pmg_restrict32(const int32_t* rptr, const int32_t* rlist, int64_t n_coarse, const float* res,
+                      int ncols, float* rc, void* stream);
+int ds_pmg_prolong_add32(const int32_t* parents, int64_t n_fine, const float* zc, int ncols,
+                         float* z, void* stream);
 
 /* ---- eigenvalue derivative --------------------------------------------------
  * Shape: grad_verts += d/dx sum_i g_i (u_i^T K u_i - lam_i u_i^T M u_i); replaces
