@@ -52,6 +52,8 @@ SIGNATURES = {
     "ds_spmm_k_and_m": (cint, [i32p, i32p, i64, f64p, f64p, f64p, i64, cint, f64p, i64, f64p, i64, ptr]),
     "ds_gram_scratch_elems": (i64, [cint, cint]),
     "ds_gram_f64": (cint, [f64p, i64, cint, f64p, i64, cint, i64, f64p, i64, f64p, ptr]),
+    "ds_gram_sym2_scratch_elems": (i64, []),
+    "ds_gram_sym2_f64": (cint, [f64p, f64p, f64p, i64, i64, C.POINTER(C.c_int), cint, f64p, f64p, i64, f64p, ptr]),
     "ds_block_gemm_f64": (cint, [f64p, i64, cint, f64p, i64, cint, i64, dbl, f64p, i64, ptr]),
     "ds_eigh_generalized_f64": (cint, [f64p, f64p, cint, i64, dbl, f64p, f64p, i64, f64p, ptr, ptr]),
     "ds_lobpcg": (cint, [ptr, i32p, i32p, i64, f64p, f64p, C.POINTER(PmgLevel), f64p, cint, C.POINTER(LobpcgOpts),

@@ -62,6 +62,10 @@ struct Level32 {
 int64_t gram_scratch_elems(int p, int q);
 int gram_f64(const double* A, int64_t lda, int p, const double* B, int64_t ldb, int q, int64_t n, double* G,
              int64_t ldg, double* partial, cudaStream_t stream);
+// gram_sym.cu: GK = S^T KS, GM = S^T MS (upper-triangle 8x8 tiles over the active tile columns), one pass
+int64_t gram_sym2_scratch_elems(int num_sms);
+int gram_sym2(const double* S, const double* KS, const double* MS, int64_t ld, int64_t n, const int* tiles, int ntiles,
+              double* GK, double* GM, int64_t ldg, double* partial, int num_sms, cudaStream_t stream);
 // Y = beta Y + alpha A C
 int block_gemm_f64(const double* A, int64_t lda, int p, const double* C, int64_t ldc, int q, int64_t n, double alpha,
                    double beta, double* Y, int64_t ldy, cudaStream_t stream);

@@ -119,7 +119,7 @@ struct Driver {
     int ld;                      // 3m
     double *S[2], *KS[2], *MS[2];
     double *R;
-    double *GK, *GM, *Cm, *theta, *eig_scratch, *gram_partial, *norm_partial, *norms, *lam_d;
+    double *GK, *GM, *Cm, *theta, *eig_scratch, *gram_partial, *gram_partial2, *norm_partial, *norms, *lam_d;
     int* info_d;
     int cur = 0;
     int64_t spmm_count = 0;
@@ -144,6 +144,7 @@ struct Driver {
         }
         add(144 * 144); add(144 * 144); add(144 * 144); add(144); add(2 * 144 * 144);
         add((size_t)gram_scratch_elems(64, 64)); add((size_t)norm_ctas * 2 * 128); add(2 * 128); add(128);
+        add((size_t)gram_sym2_scratch_elems(ws->num_sms));
         add(64);
         DS_TRY(ws->arena.reserve(need, st));
         Arena& a = ws->arena;
@@ -162,6 +163,7 @@ struct Driver {
         GK = a.take<double>(144 * 144); GM = a.take<double>(144 * 144); Cm = a.take<double>(144 * 144);
         theta = a.take<double>(144); eig_scratch = a.take<double>(2 * 144 * 144);
         gram_partial = a.take<double>((size_t)gram_scratch_elems(64, 64));
+        gram_partial2 = a.take<double>((size_t)gram_sym2_scratch_elems(ws->num_sms));
         norm_partial = a.take<double>((size_t)norm_ctas * 2 * 128);
         norms = a.take<double>(2 * 128);
         lam_d = a.take<double>(128);
@@ -295,29 +297,14 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
     spmm_count += 2;
     std::vector<int> idx(144);
     auto rr = [&](int w, int nx, int nw, int np, const std::vector<int>& slots) -> int {
-        // Gram blocks (upper triangle of the 3x3 block structure), widths padded to 8
+        // both Gram matrices in one pass over [X | W | P]: upper-triangle 8x8 tiles over the used columns
         DS_CUDA(cudaMemsetAsync(GK, 0, sizeof(double) * 144 * 144, st));
         DS_CUDA(cudaMemsetAsync(GM, 0, sizeof(double) * 144 * 144, st));
-        const double* Sx = S[w]; const double* Sw = S[w] + m; const double* Sp = S[w] + 2 * m;
-        const double* Kx = KS[w]; const double* Kw = KS[w] + m; const double* Kp = KS[w] + 2 * m;
-        const double* Mx = MS[w]; const double* Mw = MS[w] + m; const double* Mp = MS[w] + 2 * m;
-        int pw = (nw + 7) & ~7, pp = (np + 7) & ~7;
-        DS_TRY(gram_block(Sx, m, Kx, m, GK, 0, 0));
-        DS_TRY(gram_block(Sx, m, Mx, m, GM, 0, 0));
-        if (nw) {
-            DS_TRY(gram_block(Sx, m, Kw, pw, GK, 0, m));
-            DS_TRY(gram_block(Sx, m, Mw, pw, GM, 0, m));
-            DS_TRY(gram_block(Sw, pw, Kw, pw, GK, m, m));
-            DS_TRY(gram_block(Sw, pw, Mw, pw, GM, m, m));
-        }
-        if (np) {
-            DS_TRY(gram_block(Sx, m, Kp, pp, GK, 0, 2 * m));
-            DS_TRY(gram_block(Sx, m, Mp, pp, GM, 0, 2 * m));
-            DS_TRY(gram_block(Sw, pw, Kp, pp, GK, m, 2 * m));
-            DS_TRY(gram_block(Sw, pw, Mp, pp, GM, m, 2 * m));
-            DS_TRY(gram_block(Sp, pp, Kp, pp, GK, 2 * m, 2 * m));
-            DS_TRY(gram_block(Sp, pp, Mp, pp, GM, 2 * m, 2 * m));
-        }
+        int tiles[18], nt = 0;
+        for (int t = 0; t < m / 8; ++t) tiles[nt++] = t;
+        for (int t = 0; t < (nw + 7) / 8; ++t) tiles[nt++] = m / 8 + t;
+        for (int t = 0; t < (np + 7) / 8; ++t) tiles[nt++] = 2 * m / 8 + t;
+        DS_TRY(gram_sym2(S[w], KS[w], MS[w], ld, n, tiles, nt, GK, GM, 144, gram_partial2, ws->num_sms, st));
         DS_CUDA(cudaMemsetAsync(Cm, 0, sizeof(double) * 144 * 144, st));
         int N = (int)slots.size();
         (void)nx;

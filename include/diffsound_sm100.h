@@ -106,6 +106,14 @@ int ds_spmm_k_and_m(const int32_t* brow, const int32_t* bcol, int64_t n_nodes,
 int64_t ds_gram_scratch_elems(int p, int q);
 int ds_gram_f64(const double* A, int64_t lda, int p, const double* B, int64_t ldb, int q,
                 int64_t n, double* G, int64_t ldg, double* partial, void* stream);
+/* Fused Rayleigh-Ritz Gram pair in one pass over S, KS, MS (n x ld row-major, ld multiple of 8,
+ * <= 144): GK = S^T KS, GM = S^T MS restricted to the 8-column tiles listed in tiles_host
+ * (ascending, host int[ntiles]); only tiles with row-tile <= column-tile (upper triangle) of the
+ * ldg-strided outputs are written.  partial: fp64 [ds_gram_sym2_scratch_elems()]. */
+int64_t ds_gram_sym2_scratch_elems(void);
+int ds_gram_sym2_f64(const double* S, const double* KS, const double* MS, int64_t ld, int64_t n,
+                     const int* tiles_host, int ntiles, double* GK, double* GM, int64_t ldg,
+                     double* partial, void* stream);
 /* Y (n x q) = beta*Y + A (n x p) C (p x q, row-major ldc) */
 int ds_block_gemm_f64(const double* A, int64_t lda, int p, const double* C, int64_t ldc, int q,
                       int64_t n, double beta, double* Y, int64_t ldy, void* stream);

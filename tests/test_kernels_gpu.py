@@ -151,7 +151,7 @@ def test_block_gemm_dmma(n, p, q):
     assert float((Y - ref).abs().max()) <= 1e-12 * float(ref.abs().max()) * np.sqrt(p)
 
 
-@pytest.mark.parametrize("N", [6, 48, 96, 114, 144])
+@pytest.mark.parametrize("N", [6, 7, 33, 48, 95, 96, 114, 131, 143, 144])
 def test_eigh_generalized_jacobi(N):
     from diffsound_b200 import native
     rng = np.random.default_rng(N)
@@ -202,3 +202,35 @@ def test_legacy_mass_coo_matches_reference_layout(meshes):
         assert np.allclose(values.cpu().numpy().reshape(T, msz, msz), Me, rtol=1e-6, atol=0)
         assert np.array_equal(rows.cpu().numpy().reshape(T, msz, msz), np.broadcast_to(d[:, :, None], (T, msz, msz)))
         assert np.array_equal(cols.cpu().numpy().reshape(T, msz, msz), np.broadcast_to(d[:, None, :], (T, msz, msz)))
+
+
+@pytest.mark.parametrize("ld,tiles", [(144, list(range(18))), (144, [0, 1, 2, 3, 4, 5, 6, 7, 8, 12, 13]), (96, list(range(12))),
+                                      (48, list(range(6)))])
+def test_gram_sym2_matches_fp64(ld, tiles):
+    """Fused GK = S^T KS, GM = S^T MS (upper-triangle tiles over the active tile columns) against
+    torch fp64 matmul: <= 1e-12 of the largest entry; inactive tiles stay untouched."""
+    import ctypes as C
+    from diffsound_b200 import _lib, native
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    n = 50_003                     # not a multiple of the 16-row chunk
+    g = torch.Generator(device=dev).manual_seed(3)
+    S, KS, MS = (torch.randn(n, ld, dtype=torch.float64, device=dev, generator=g) for _ in range(3))
+    GK = torch.full((144, 144), -7.0, dtype=torch.float64, device=dev)
+    GM = torch.full((144, 144), -7.0, dtype=torch.float64, device=dev)
+    part = torch.empty(lib.ds_gram_sym2_scratch_elems(), dtype=torch.float64, device=dev)
+    arr = (C.c_int * len(tiles))(*tiles)
+    _lib.check(lib.ds_gram_sym2_f64(native._p(S), native._p(KS), native._p(MS), ld, n, arr, len(tiles), native._p(GK),
+                                    native._p(GM), 144, native._p(part), native._stream()), "ds_gram_sym2_f64")
+    rk, rm = (S.T @ KS).cpu().numpy(), (S.T @ MS).cpu().numpy()
+    gk, gm = GK.cpu().numpy(), GM.cpu().numpy()
+    act = np.zeros(18, dtype=bool)
+    act[tiles] = True
+    for ti in range(18):
+        for tj in range(18):
+            blk = (slice(8 * ti, 8 * ti + 8), slice(8 * tj, 8 * tj + 8))
+            if act[ti] and act[tj] and ti <= tj:
+                assert np.abs(gk[blk] - rk[blk]).max() <= 1e-12 * np.abs(rk).max()
+                assert np.abs(gm[blk] - rm[blk]).max() <= 1e-12 * np.abs(rm).max()
+            else:
+                assert (gk[blk] == -7.0).all() and (gm[blk] == -7.0).all()
