@@ -25,7 +25,7 @@ class LobpcgOpts(C.Structure):
     _fields_ = [("nev", C.c_int), ("maxit", C.c_int), ("cheb_degree", C.c_int), ("tol", C.c_double),
                 ("sigma", C.c_double), ("cheb_ratio", C.c_double), ("n_rigid", C.c_int), ("verbose", C.c_int),
                 ("smooth_steps", C.c_int), ("coarse_degree", C.c_int), ("smooth_ratio", C.c_double),
-                ("coarse_ratio", C.c_double)]
+                ("coarse_ratio", C.c_double), ("nested", C.c_int), ("nested_tol", C.c_double)]
 
 
 class PmgLevel(C.Structure):
@@ -55,6 +55,7 @@ SIGNATURES = {
     "ds_gram_sym2_scratch_elems": (i64, []),
     "ds_gram_sym2_f64": (cint, [f64p, f64p, f64p, i64, i64, C.POINTER(C.c_int), cint, f64p, f64p, i64, f64p, ptr]),
     "ds_block_gemm_f64": (cint, [f64p, i64, cint, f64p, i64, cint, i64, dbl, f64p, i64, ptr]),
+    "ds_eigh_scratch_elems": (i64, [cint]),
     "ds_eigh_generalized_f64": (cint, [f64p, f64p, cint, i64, dbl, f64p, f64p, i64, f64p, ptr, ptr]),
     "ds_lobpcg": (cint, [ptr, i32p, i32p, i64, f64p, f64p, C.POINTER(PmgLevel), f64p, cint, C.POINTER(LobpcgOpts),
                          f64p, f64p, C.POINTER(C.c_int64), ptr]),

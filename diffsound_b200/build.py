@@ -61,7 +61,8 @@ def build(verbose=False, force=False):
                 raise RuntimeError(f"nvcc failed for {s}")
             with open(os.path.join(OBJ, os.path.basename(s)[:-3] + ".ptxas.txt"), "w") as f:
                 f.write(r.stderr)
-    if jobs or not os.path.exists(LIB):
+    stale = not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs)
+    if jobs or stale:
         cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

@@ -102,4 +102,5 @@ struct ds_workspace {
     int64_t n_pairs = 0;
     int64_t nnzb = 0;
     int num_sms = 0;
+    ds_workspace* child = nullptr;   // arena of the nested coarse eigen-solve (created on first use)
 };

@@ -1,0 +1,432 @@
+// Generalised symmetric eigenproblem GK c = theta GM c of the Rayleigh-Ritz step, N <= 144, FP64.
+//
+// Reference behaviour replaced: torch.linalg.cholesky / torch.linalg.eigh on the projected problem
+// (/root/reference/src/lobpcg/_lobpcg.py:507-525, _linalg_utils.py:87-96).
+//
+// Method (implicit Cholesky / one-sided Jacobi, high relative accuracy for the small eigenvalues):
+//   D = diag(GM)^-1/2;  L L^T = D GM D;  R R^T = D (GK + sigma GM) D;  Y = L^-1 R;
+//   one-sided Jacobi orthogonalises the ROWS of Y:  Q^T Y,  |row_j|^2 = theta_j + sigma;
+//   c_j = D R^-T row_j.
+// Three kernels:
+//   k_eigh_prepare (one CTA)      gather/scale, both Cholesky factorisations, Y -> global scratch
+//   k_eigh_jacobi  (cluster of 8) the Jacobi sweeps.  One WARP per pair of rows, rows in registers
+//                                 (5 elements per lane); pairs follow the odd-even transposition
+//                                 ordering on a line of positions, so per step exactly one row per warp
+//                                 moves to the neighbouring warp -- through a mailbox in the RECEIVER's
+//                                 shared memory, written with st.shared::cluster (DSMEM) when the
+//                                 neighbour sits in another CTA of the cluster, and one
+//                                 barrier.cluster per step.  One SM's FP64 pipe and shared-memory
+//                                 bandwidth were the limit of the single-CTA version (4.3 ms at N = 144).
+//   k_eigh_finish  (one CTA)      eigenvalues, ascending rank, back substitution, C.
+#include "common.cuh"
+#include "../../include/diffsound_sm100.h"
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace ds {
+
+constexpr int EIG_MAXN = 144;
+constexpr int EIG_THREADS = 1024;                 // prepare / finish
+constexpr int JC_CL = 8;                          // CTAs per cluster
+constexpr int JC_GPC = EIG_MAXN / 2 / JC_CL;      // 9 row pairs (warps) per CTA
+constexpr int JC_THREADS = JC_GPC * 32;           // 288
+constexpr int JC_E = 5;                           // row elements per lane: 5 * 32 = 160 >= 144
+constexpr int JC_LD = 32 * JC_E;                  // row pitch of Y in global scratch
+constexpr int JC_SLOT = JC_LD + 8;                // mailbox slot: elements + |row|^2 at [JC_LD]
+static_assert(JC_GPC * JC_CL * 2 == EIG_MAXN, "line positions must tile the cluster");
+
+// scratch layout (doubles): L [N*N] | R^T [N*N] | Y [(N+1) * JC_LD] | scale [N] | sigma, fail [8]
+__host__ __device__ inline size_t eig_off_Rt(int N) { return (size_t)N * N; }
+__host__ __device__ inline size_t eig_off_Y(int N) { return 2 * (size_t)N * N; }
+__host__ __device__ inline size_t eig_off_scale(int N) { return eig_off_Y(N) + (size_t)(N + 1) * JC_LD; }
+__host__ __device__ inline size_t eig_off_meta(int N) { return eig_off_scale(N) + N; }
+int64_t eigh_scratch_elems(int N) { return (int64_t)eig_off_meta(N) + 8; }
+
+// in-place Cholesky (lower) of the N x N matrix in shared memory (row stride ld).
+// returns 0 or failing column + 1 (same value in every thread).
+__device__ int chol_lower(double* S, int N, int ld, int* s_flag) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int tpr = nt / N > 0 ? nt / N : 1;            // threads per row of the trailing update
+    for (int k = 0; k < N; ++k) {
+        if (tid == 0) {
+            double d = S[k * ld + k];
+            if (!(d > 0.0)) *s_flag = k + 1;
+            else S[k * ld + k] = sqrt(d);
+        }
+        __syncthreads();
+        if (*s_flag) return *s_flag;
+        const double rdk = 1.0 / S[k * ld + k];
+        for (int i = k + 1 + tid; i < N; i += nt) S[i * ld + k] *= rdk;
+        __syncthreads();
+        for (int i = k + 1 + tid / tpr; i < N; i += nt / tpr) {
+            const double lik = S[i * ld + k];
+            for (int j = k + 1 + tid % tpr; j <= i; j += tpr) S[i * ld + j] -= lik * S[j * ld + k];
+        }
+        __syncthreads();
+    }
+    return 0;
+}
+
+struct EigIdx {
+    short v[EIG_MAXN];
+};
+
+// upper-triangle read through the slot map: entry (i, j) of the compact problem
+__device__ __forceinline__ double g_up(const double* __restrict__ G, int64_t ldg, const EigIdx& ix, int i, int j) {
+    int a = ix.v[i], b = ix.v[j];
+    return a <= b ? G[(int64_t)a * ldg + b] : G[(int64_t)b * ldg + a];
+}
+
+__global__ void __launch_bounds__(EIG_THREADS)
+k_eigh_prepare(const double* __restrict__ GK, const double* __restrict__ GM, int N, int64_t ldg,
+               const __grid_constant__ EigIdx ix, double sigma_in, double* __restrict__ scratch,
+               int* __restrict__ info) {
+    extern __shared__ __align__(16) double S[];  // [N][ld]
+    const int ld = N + 2;
+    double* s_scale = S + (size_t)N * ld;        // [N]
+    int* s_flag = reinterpret_cast<int*>(s_scale + N);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    double* Lg = scratch;                        // L, row-major [N][N]
+    double* Rt = scratch + eig_off_Rt(N);        // R^T, row-major: Rt[k][i] = R[i][k]
+    double* Yg = scratch + eig_off_Y(N);
+    double* meta = scratch + eig_off_meta(N);
+    if (tid == 0) { s_flag[0] = 0; meta[1] = 1.0; }      // meta[1] = fail until the factorisations succeed
+    for (int i = tid; i < N; i += nt) {
+        double d = g_up(GM, ldg, ix, i, i);
+        s_scale[i] = d > 0.0 ? rsqrt(d) : 1.0;
+    }
+    __syncthreads();
+    // sigma < 0: automatic shift = |sigma| * mean diagonal of the scaled GK
+    double sigma = sigma_in;
+    if (sigma_in < 0.0) {
+        double tr = 0.0;
+        for (int i = 0; i < N; ++i) tr += fabs(g_up(GK, ldg, ix, i, i)) * s_scale[i] * s_scale[i];
+        sigma = -sigma_in * tr / N;
+    }
+    // ---- L = chol(D GM D)
+    for (int t = tid; t < N * N; t += nt) {
+        int i = t / N, j = t % N;
+        double v = (j <= i) ? g_up(GM, ldg, ix, i, j) : 0.0;
+        S[i * ld + j] = v * s_scale[i] * s_scale[j];
+    }
+    __syncthreads();
+    int bad = chol_lower(S, N, ld, s_flag);
+    if (bad) { if (tid == 0) { info[0] = bad; info[1] = 0; } return; }
+    for (int t = tid; t < N * N; t += nt) {
+        int i = t / N, j = t % N;
+        Lg[t] = (j <= i) ? S[i * ld + j] : 0.0;
+    }
+    __syncthreads();
+    // ---- R = chol(D (GK + sigma GM) D)
+    for (int t = tid; t < N * N; t += nt) {
+        int i = t / N, j = t % N;
+        double v = 0.0;
+        if (j <= i) v = g_up(GK, ldg, ix, i, j) + sigma * g_up(GM, ldg, ix, i, j);
+        S[i * ld + j] = v * s_scale[i] * s_scale[j];
+    }
+    __syncthreads();
+    bad = chol_lower(S, N, ld, s_flag);
+    if (bad) { if (tid == 0) { info[0] = 1000 + bad; info[1] = 0; } return; }
+    for (int t = tid; t < N * N; t += nt) {
+        int i = t / N, k = t % N;   // Rt[k][i] = R[i][k]
+        Rt[(size_t)k * N + i] = (k <= i) ? S[i * ld + k] : 0.0;
+    }
+    for (int t = tid; t < N * N; t += nt) {
+        int i = t / N, j = t % N;
+        if (j > i) S[i * ld + j] = 0.0;
+    }
+    __threadfence_block();
+    __syncthreads();
+    // ---- Y = L^-1 R  (forward substitution, one thread per column j; Y lower triangular)
+    if (tid < N) {
+        int j = tid;
+        for (int i = j; i < N; ++i) {
+            double v = S[i * ld + j];
+            const double* Li = Lg + (size_t)i * N;
+            for (int k = j; k < i; ++k) v -= Li[k] * S[k * ld + j];
+            S[i * ld + j] = v / Li[i];
+        }
+    }
+    __syncthreads();
+    // ---- rows of Y (zero padded to JC_LD, plus one zero row when N is odd) -> global
+    const int Np = (N + 1) & ~1;
+    for (int t = tid; t < Np * JC_LD; t += nt) {
+        int p = t / JC_LD, e = t - p * JC_LD;
+        Yg[t] = (p < N && e < N) ? S[p * ld + e] : 0.0;
+    }
+    for (int i = tid; i < N; i += nt) scratch[eig_off_scale(N) + i] = s_scale[i];
+    if (tid == 0) { meta[0] = sigma; meta[1] = 0.0; }
+}
+
+// ---- cluster primitives ----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// address of `p` (a shared-memory pointer of this CTA's layout) inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(const void* p, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f64(uint32_t addr, double v) {
+    asm volatile("st.shared::cluster.f64 [%0], %1;\n" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;\n" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_cluster_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared::cluster.u32 %0, [%1];\n" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+__global__ void __cluster_dims__(JC_CL, 1, 1) __launch_bounds__(JC_THREADS)
+k_eigh_jacobi(int N, double* __restrict__ scratch, int* __restrict__ info) {
+    __shared__ __align__(16) double slotO[JC_GPC][JC_SLOT];   // odd steps: position 2g+2 arriving at group g
+    __shared__ __align__(16) double slotE[JC_GPC][JC_SLOT];   // even steps: position 2g arriving at group g
+    __shared__ __align__(16) double park[JC_SLOT];            // position 0 rests here during odd steps
+    __shared__ uint32_t s_again;                              // used in CTA 0 of the cluster
+    double* Yg = scratch + eig_off_Y(N);
+    if (scratch[eig_off_meta(N) + 1] != 0.0) return;          // factorisation failed (every CTA sees the same flag)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int g = (int)rank * JC_GPC + warp;                  // this warp's pair of line positions: 2g, 2g+1
+    const int Np = (N + 1) & ~1, G = Np / 2;
+    const bool active = g < G;
+    const double tol2 = 1.44e-32 * (double)N;                 // (1.2e-16 sqrt(N))^2
+
+    double ra[JC_E], rb[JC_E];                                // even configuration: ra = position 2g, rb = 2g+1
+    double na = 0.0, nb = 0.0;
+#pragma unroll
+    for (int i = 0; i < JC_E; ++i) {
+        ra[i] = active ? Yg[(size_t)(2 * g) * JC_LD + lane + 32 * i] : 0.0;
+        rb[i] = active ? Yg[(size_t)(2 * g + 1) * JC_LD + lane + 32 * i] : 0.0;
+    }
+    // receivers of this warp's outgoing rows
+    const uint32_t dstO = g >= 1 ? map_to_cta(&slotO[(g - 1) % JC_GPC][0], (uint32_t)((g - 1) / JC_GPC)) : 0u;
+    const uint32_t dstE = g + 1 < G ? map_to_cta(&slotE[(g + 1) % JC_GPC][0], (uint32_t)((g + 1) / JC_GPC)) : 0u;
+    const uint32_t again_addr = map_to_cta(&s_again, 0u);
+
+    // rotate x (|x|^2 = nx) against y; returns 1 if a rotation was applied (all lanes of the warp call it)
+    auto rotate = [&](bool enable, double (&x)[JC_E], double& nx, double (&y)[JC_E], double& ny) -> int {
+        double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < JC_E; ++i) {
+            if (i & 1) g1 = fma(x[i], y[i], g1);
+            else g0 = fma(x[i], y[i], g0);
+        }
+        const double ga = warp_sum(g0 + g1);
+        if (!(enable && ga * ga > tol2 * nx * ny)) return 0;
+        // tan(theta) = 2 ga / (d + sign(d) sqrt(d^2 + 4 ga^2)),  d = ny - nx
+        const double d = ny - nx;
+        const double h = sqrt(fma(d, d, 4.0 * ga * ga));
+        const double t = 2.0 * ga / (d + (d >= 0.0 ? h : -h));
+        const double c = rsqrt(fma(t, t, 1.0)), sn = c * t;
+#pragma unroll
+        for (int i = 0; i < JC_E; ++i) {
+            const double xv = x[i], yv = y[i];
+            x[i] = fma(c, xv, -sn * yv);
+            y[i] = fma(sn, xv, c * yv);
+        }
+        nx -= t * ga;
+        ny += t * ga;
+        return 1;
+    };
+    auto send = [&](uint32_t dst, const double (&x)[JC_E], double nx) {
+#pragma unroll
+        for (int i = 0; i < JC_E; ++i) st_cluster_f64(dst + (uint32_t)(lane + 32 * i) * 8u, x[i]);
+        if (lane == 0) st_cluster_f64(dst + (uint32_t)JC_LD * 8u, nx);
+    };
+    auto recv = [&](const double* src, double (&x)[JC_E], double& nx) {
+#pragma unroll
+        for (int i = 0; i < JC_E; ++i) x[i] = src[lane + 32 * i];
+        nx = src[JC_LD];
+    };
+
+    int sweep = 0;
+    for (; sweep < 24; ++sweep) {
+        if (rank == 0 && tid == 0) s_again = 0u;
+        {   // refresh the norms (they are updated by -+ t*gamma inside a sweep)
+            double qa = 0.0, qb = 0.0;
+#pragma unroll
+            for (int i = 0; i < JC_E; ++i) { qa = fma(ra[i], ra[i], qa); qb = fma(rb[i], rb[i], qb); }
+            na = warp_sum(qa);
+            nb = warp_sum(qb);
+        }
+        cluster_sync_all();
+        int rotated = 0;
+        for (int step = 0; step < Np; step += 2) {
+            // even step: positions (2g, 2g+1) = (ra, rb); afterwards the rows trade places:
+            // position 2g is in rb, position 2g+1 in ra
+            rotated |= rotate(active, ra, na, rb, nb);
+            // odd step: position 2g (rb) goes to the left neighbour; position 2g+2 arrives in rb
+            if (active) {
+                if (g == 0) {
+#pragma unroll
+                    for (int i = 0; i < JC_E; ++i) park[lane + 32 * i] = rb[i];
+                    if (lane == 0) park[JC_LD] = nb;
+                } else {
+                    send(dstO, rb, nb);
+                }
+            }
+            cluster_sync_all();
+            if (active) {
+                if (g < G - 1) {
+                    recv(&slotO[warp][0], rb, nb);
+                } else {                                       // beyond the end of the line: a zero row
+#pragma unroll
+                    for (int i = 0; i < JC_E; ++i) rb[i] = 0.0;
+                    nb = 0.0;
+                }
+            }
+            rotated |= rotate(active && g < G - 1, ra, na, rb, nb);           // positions (2g+1, 2g+2)
+            // trade places: position 2g+1 is now in rb, position 2g+2 in ra -- except for the last group,
+            // which keeps its row at position 2g+1
+            if (active && g == G - 1) {
+#pragma unroll
+                for (int i = 0; i < JC_E; ++i) { const double tv = ra[i]; ra[i] = rb[i]; rb[i] = tv; }
+                const double tv = na; na = nb; nb = tv;
+            }
+            // next even step: position 2g+2 (ra) goes to the right neighbour; position 2g arrives in ra
+            if (active && g + 1 < G) send(dstE, ra, na);
+            cluster_sync_all();
+            if (active) {
+                if (g == 0) recv(park, ra, na);
+                else recv(&slotE[warp][0], ra, na);
+            }
+        }
+        if (__any_sync(0xffffffffu, rotated) && lane == 0) st_cluster_u32(again_addr, 1u);
+        cluster_sync_all();
+        const uint32_t again = ld_cluster_u32(again_addr);
+        cluster_sync_all();                                    // everybody has read the flag before it is reset
+        if (!again) break;
+    }
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < JC_E; ++i) {
+            Yg[(size_t)(2 * g) * JC_LD + lane + 32 * i] = ra[i];
+            Yg[(size_t)(2 * g + 1) * JC_LD + lane + 32 * i] = rb[i];
+        }
+    }
+    if (rank == 0 && tid == 0) info[1] = sweep + 1;
+    cluster_sync_all();                                        // no CTA leaves while DSMEM traffic may be pending
+}
+
+__global__ void __launch_bounds__(EIG_THREADS)
+k_eigh_finish(int N, const __grid_constant__ EigIdx ix, double* __restrict__ theta, double* __restrict__ C, int64_t ldc,
+              const double* __restrict__ scratch, int* __restrict__ info) {
+    extern __shared__ __align__(16) double S[];  // [N][ld]
+    const int ld = N + 2;
+    double* s_scale = S + (size_t)N * ld;        // [N]
+    double* s_theta = s_scale + N;               // [N + 2]
+    int* s_rank = reinterpret_cast<int*>(s_theta + N + 2);   // [N]
+    int* s_flag = s_rank + N;                    // [2]
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const double* Rt = scratch + eig_off_Rt(N);
+    const double* Yg = scratch + eig_off_Y(N);
+    const double* meta = scratch + eig_off_meta(N);
+    if (meta[1] != 0.0) return;                  // info was set by k_eigh_prepare
+    const double sigma = meta[0];
+    const int Np = (N + 1) & ~1;
+    // norms of all line positions; an odd N leaves exactly one zero row somewhere on the line
+    for (int p = tid / 32; p < Np; p += nt / 32) {
+        double v = 0.0;
+        for (int e = tid & 31; e < N; e += 32) { double a = Yg[(size_t)p * JC_LD + e]; v = fma(a, a, v); }
+        v = warp_sum(v);
+        if ((tid & 31) == 0) s_theta[p] = v;
+    }
+    for (int i = tid; i < N; i += nt) s_scale[i] = scratch[eig_off_scale(N) + i];
+    __syncthreads();
+    if (tid == 0) {
+        int ph = Np;
+        if (Np > N)
+            for (int p = 0; p < Np; ++p)
+                if (s_theta[p] == 0.0) { ph = p; break; }
+        s_flag[0] = ph;
+    }
+    __syncthreads();
+    const int ph = s_flag[0];
+    for (int t = tid; t < N * N; t += nt) {
+        int j = t / N, e = t - j * N;
+        S[(size_t)j * ld + e] = Yg[(size_t)(j + (j >= ph ? 1 : 0)) * JC_LD + e];
+    }
+    __syncthreads();
+    // ---- eigenvalues and ascending rank
+    for (int j = tid / 32; j < N; j += nt / 32) {
+        double v = 0.0;
+        for (int e = tid & 31; e < N; e += 32) { double a = S[(size_t)j * ld + e]; v = fma(a, a, v); }
+        v = warp_sum(v);
+        if ((tid & 31) == 0) s_theta[j] = v - sigma;
+    }
+    __syncthreads();
+    for (int j = tid; j < N; j += nt) {
+        double tj = s_theta[j];
+        int rk = 0;
+        for (int i = 0; i < N; ++i) {
+            double ti = s_theta[i];
+            rk += (ti < tj) || (ti == tj && i < j);
+        }
+        s_rank[j] = rk;
+        theta[rk] = tj;
+    }
+    __syncthreads();
+    // ---- c_j^T = y_j R^-1 (back substitution, thread per vector), scaled, placed in column rank_j
+    if (tid < N) {
+        int j = tid;
+        double* y = S + (size_t)j * ld;
+        for (int k = N - 1; k >= 0; --k) {
+            double v = y[k];
+            const double* Rk = Rt + (size_t)k * N;   // Rk[i] = R[i][k]
+            for (int i = k + 1; i < N; ++i) v -= y[i] * Rk[i];
+            y[k] = v / Rk[k];
+        }
+    }
+    __syncthreads();
+    for (int t = tid; t < N * N; t += nt) {
+        int k = t / N, j = t % N;
+        C[(int64_t)ix.v[k] * ldc + s_rank[j]] = S[(size_t)j * ld + k] * s_scale[k];
+    }
+    if (tid == 0) info[0] = 0;
+}
+
+int eigh_generalized_f64(const double* GK, const double* GM, int N, int64_t ldg, const int* idx_host, double sigma,
+                         double* theta, double* C, int64_t ldc, double* scratch, int* info, cudaStream_t stream) {
+    DS_REQUIRE(N >= 2 && N <= EIG_MAXN, "eigh_generalized: N=%d must be in [2,%d]", N, EIG_MAXN);
+    DS_REQUIRE(GK && GM && theta && C && scratch && info, "eigh_generalized: null argument");
+    ProfScope prof(PROF_EIGH, stream);
+    EigIdx ix;
+    for (int i = 0; i < EIG_MAXN; ++i) ix.v[i] = (short)(i < N ? (idx_host ? idx_host[i] : i) : 0);
+    const size_t smem = ((size_t)N * (N + 2) + 2 * N + 2) * sizeof(double) + (N + 4) * sizeof(int);
+    static bool attr = false;
+    if (!attr) {
+        const int mx = (int)(((size_t)EIG_MAXN * (EIG_MAXN + 2) + 2 * EIG_MAXN + 2) * sizeof(double) + (EIG_MAXN + 4) * sizeof(int));
+        DS_CUDA(cudaFuncSetAttribute(k_eigh_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        DS_CUDA(cudaFuncSetAttribute(k_eigh_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        attr = true;
+    }
+    k_eigh_prepare<<<1, EIG_THREADS, smem, stream>>>(GK, GM, N, ldg, ix, sigma, scratch, info);
+    DS_LAUNCH_CHECK();
+    k_eigh_jacobi<<<JC_CL, JC_THREADS, 0, stream>>>(N, scratch, info);
+    DS_LAUNCH_CHECK();
+    k_eigh_finish<<<1, EIG_THREADS, smem, stream>>>(N, ix, theta, C, ldc, scratch, info);
+    DS_LAUNCH_CHECK();
+    return DS_OK;
+}
+
+}  // namespace ds
+
+using namespace ds;
+
+extern "C" int64_t ds_eigh_scratch_elems(int N) { return eigh_scratch_elems(N); }
+
+extern "C" int ds_eigh_generalized_f64(const double* GK, const double* GM, int N, int64_t ldg, double sigma,
+                                       double* theta, double* C, int64_t ldc, double* scratch, int* info,
+                                       void* stream) {
+    return eigh_generalized_f64(GK, GM, N, ldg, nullptr, sigma, theta, C, ldc, scratch, info, (cudaStream_t)stream);
+}

@@ -20,8 +20,8 @@
 
 namespace ds {
 
-constexpr int GS_ROWS = 16;
-constexpr int GS_STAGES = 3;
+constexpr int GS_ROWS = 8;
+constexpr int GS_STAGES = 6;
 constexpr int GS_THREADS = 512;
 constexpr int GS_WARPS = GS_THREADS / 32;
 constexpr int GS_SEG = 148;               // doubles per segment (144 used); 148 * 8 B keeps 16-byte alignment
@@ -116,7 +116,9 @@ k_gram_sym2(const double* __restrict__ S, const double* __restrict__ KS, const d
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
-        if (warp == 0 && it + GS_STAGES < mine) issue(it + GS_STAGES);
+        // refill the stage of the PREVIOUS chunk: by now every warp has normally released it, so the
+        // issuing warp (a consumer itself) does not stall the pipeline waiting for the slowest one
+        if (warp == 0 && it >= 1 && it - 1 + GS_STAGES < mine) issue(it - 1 + GS_STAGES);
     }
     // partial[cta][entry][matrix][64]; lane holds C[row = lane>>2][col = 2*(lane&3) + {0,1}]
     double* out = partial + (size_t)blockIdx.x * GS_MAX_ENTRIES * 128;

@@ -34,6 +34,8 @@ int restrict32(const int32_t* rptr, const int32_t* rlist, int64_t n_coarse, cons
 int prolong_add32(const int32_t* par, int64_t n_fine, const float* zc, int ncols, float* z, cudaStream_t st);
 int prolong64(const int32_t* par, int64_t n_fine, const double* xc, int64_t ldc, int w, double* x, int64_t ldx,
               cudaStream_t st);
+int inject64(const int32_t* rptr, const int32_t* rlist, int64_t n_coarse, const double* x, int64_t ldx, int w,
+             double* xc, int64_t ldc, cudaStream_t st);
 int gather_cols_f32(const double* src, int64_t lds, const ColIdx& idx, int count, int width, int64_t n, float* dst,
                     cudaStream_t st);
 int widen_f32(const float* src, int width, int64_t n, double* dst, int64_t ldd, cudaStream_t st);
@@ -72,6 +74,7 @@ int block_gemm_f64(const double* A, int64_t lda, int p, const double* C, int64_t
 // idx_host (may be NULL = identity): slot of compact index i inside the ldg x ldg Gram storage;
 // only the upper triangle of the storage is read; rows of C are written at the mapped slots.
 // sigma < 0 selects an automatic shift |sigma| * mean(diag(scaled GK)).
+int64_t eigh_scratch_elems(int N);
 int eigh_generalized_f64(const double* GK, const double* GM, int N, int64_t ldg, const int* idx_host, double sigma,
                          double* theta, double* C, int64_t ldc, double* scratch, int* info, cudaStream_t stream);
 

@@ -115,6 +115,8 @@ struct Driver {
     const ds_pmg_level* cl = nullptr;   // optional coarse (P1) level
     Level32 fine, coarse;
     float *R32, *Za, *Zb, *RC32, *ZCa, *ZCb;
+    double *Xc = nullptr, *lamc = nullptr, *resc = nullptr;    // nested coarse eigen-solve
+    int64_t nested_iters = 0, nested_status = 0;
 
     int ld;                      // 3m
     double *S[2], *KS[2], *MS[2];
@@ -141,8 +143,9 @@ struct Driver {
             nnzb_c = cl->nnzb;
             need += Level32::bytes(cl->n_nodes, nnzb_c);
             for (int i = 0; i < 3; ++i) add((size_t)3 * cl->n_nodes * m / 2 + 64);
+            if (o.nested && cl->Mblk) { add((size_t)3 * cl->n_nodes * m); add(128); add(128); }
         }
-        add(144 * 144); add(144 * 144); add(144 * 144); add(144); add(2 * 144 * 144);
+        add(144 * 144); add(144 * 144); add(144 * 144); add(144); add((size_t)eigh_scratch_elems(144));
         add((size_t)gram_scratch_elems(64, 64)); add((size_t)norm_ctas * 2 * 128); add(2 * 128); add(128);
         add((size_t)gram_sym2_scratch_elems(ws->num_sms));
         add(64);
@@ -159,9 +162,12 @@ struct Driver {
         if (cl) {
             const size_t cb = (size_t)3 * cl->n_nodes * m;
             RC32 = a.take<float>(cb); ZCa = a.take<float>(cb); ZCb = a.take<float>(cb);
+            if (o.nested && cl->Mblk) {
+                Xc = a.take<double>(cb); lamc = a.take<double>(128); resc = a.take<double>(128);
+            }
         }
         GK = a.take<double>(144 * 144); GM = a.take<double>(144 * 144); Cm = a.take<double>(144 * 144);
-        theta = a.take<double>(144); eig_scratch = a.take<double>(2 * 144 * 144);
+        theta = a.take<double>(144); eig_scratch = a.take<double>((size_t)eigh_scratch_elems(144));
         gram_partial = a.take<double>((size_t)gram_scratch_elems(64, 64));
         gram_partial2 = a.take<double>((size_t)gram_sym2_scratch_elems(ws->num_sms));
         norm_partial = a.take<double>((size_t)norm_ctas * 2 * 128);
@@ -273,6 +279,38 @@ struct Driver {
     }
 
     int run(double* X, double* lambda_out, double* resid_out, int64_t* stats);
+
+    // Nested iteration: lowest pairs of the P1 problem (same driver, one-level Chebyshev preconditioner,
+    // loose tolerance), prolonged into the P2 start block.  The coarse start block is the injection of X
+    // (its first columns are the analytic rigid-body modes, which P reproduces exactly).
+    int nested_start(double* X) {
+        if (!ws->child) {
+            ws->child = new ds_workspace();
+            ws->child->num_sms = ws->num_sms;
+        }
+        DS_TRY(inject64(cl->rptr, cl->rlist, cl->n_nodes, X, m, m, Xc, m, st));
+        Driver dc;
+        dc.ws = ws->child;
+        dc.st = st;
+        dc.brow = cl->brow; dc.bcol = cl->bcol;
+        dc.n_nodes = cl->n_nodes; dc.n = 3 * cl->n_nodes;
+        dc.Kval = cl->Kval; dc.Mblk = cl->Mblk;
+        dc.m = m;
+        dc.o = o;
+        dc.o.nested = 0;
+        dc.o.tol = o.nested_tol > 0.0 ? o.nested_tol : 1e-2;
+        dc.o.maxit = 40;
+        const int deg = (int)std::min(40.0, std::max(8.0, std::round(std::cbrt((double)dc.n) / 3.0)));
+        dc.o.cheb_degree = deg;
+        dc.o.cheb_ratio = 0.4 * deg * deg;
+        int64_t cstats[12] = {0};
+        DS_TRY(dc.run(Xc, lamc, resc, cstats));
+        nested_iters = cstats[0];
+        nested_status = cstats[3];
+        spmm_count += cstats[2];
+        DS_TRY(prolong64(cl->parents, n_nodes, Xc, m, m, X, m, st));
+        return DS_OK;
+    }
 };
 
 }  // namespace ds
@@ -283,6 +321,7 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
     const int nev = o.nev;
     int nr = o.n_rigid < 0 ? 0 : o.n_rigid;
     DS_TRY(alloc());
+    if (Xc) DS_TRY(nested_start(X));
     DS_TRY(estimate_lmax(fine, Za, Zb, R32));
     if (cl) DS_TRY(estimate_lmax(coarse, ZCa, ZCb, RC32));
     if (o.verbose)
@@ -440,6 +479,9 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
     stats[5] = fine.cols;
     stats[6] = coarse.launches;
     stats[7] = coarse.cols;
+    stats[8] = nested_iters;
+    stats[9] = nested_status;
+    stats[10] = stats[11] = 0;
     return DS_OK;
 }
 

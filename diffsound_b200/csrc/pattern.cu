@@ -134,12 +134,15 @@ extern "C" int ds_workspace_create(ds_workspace** ws) {
 
 extern "C" int ds_workspace_destroy(ds_workspace* ws) {
     if (!ws) return DS_OK;
+    if (ws->child) ds_workspace_destroy(ws->child);
     ws->arena.release();
     delete ws;
     return DS_OK;
 }
 
-extern "C" int64_t ds_workspace_bytes(const ds_workspace* ws) { return ws ? (int64_t)ws->arena.cap : 0; }
+extern "C" int64_t ds_workspace_bytes(const ds_workspace* ws) {
+    return ws ? (int64_t)ws->arena.cap + (ws->child ? (int64_t)ws->child->arena.cap : 0) : 0;
+}
 
 extern "C" int ds_pattern_count(ds_workspace* ws, const int32_t* tets, int64_t T, int npe,
                                 int64_t n_nodes, int64_t* nnzb_host, void* stream_) {

@@ -429,6 +429,29 @@ __global__ void k_prolong64(const int32_t* __restrict__ par, int64_t n_fine, con
     x[(3 * i + c) * ldx + s] = 0.5 * (xc[(3 * (int64_t)pp.x + c) * ldc + s] + xc[(3 * (int64_t)pp.y + c) * ldc + s]);
 }
 
+// xc[3I + c][:] = x[3 f(I) + c][:], f(I) = the fine (corner) node of coarse node I: the one entry that
+// appears twice in I's gather list (a corner is its own parent twice)
+__global__ void k_inject64(const int32_t* __restrict__ rptr, const int32_t* __restrict__ rlist, int64_t n_coarse,
+                           const double* __restrict__ x, int64_t ldx, int w, double* __restrict__ xc, int64_t ldc) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_coarse * 3 * w) return;
+    const int64_t I = t / (3 * w);
+    const int r = (int)(t - I * 3 * w);
+    const int c = r / w, s = r - c * w;
+    int64_t f = -1;
+    for (int u = rptr[I]; u + 1 < rptr[I + 1]; ++u)
+        if (rlist[u] == rlist[u + 1]) { f = rlist[u]; break; }
+    xc[(3 * I + c) * ldc + s] = f >= 0 ? x[(3 * f + c) * ldx + s] : 0.0;
+}
+
+int inject64(const int32_t* rptr, const int32_t* rlist, int64_t n_coarse, const double* x, int64_t ldx, int w,
+             double* xc, int64_t ldc, cudaStream_t st) {
+    ProfScope prof(PROF_TRANSFER, st);
+    k_inject64<<<(unsigned)ceil_div(n_coarse * 3 * w, 256), 256, 0, st>>>(rptr, rlist, n_coarse, x, ldx, w, xc, ldc);
+    DS_LAUNCH_CHECK();
+    return DS_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------

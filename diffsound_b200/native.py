@@ -234,7 +234,7 @@ def eigh_generalized(GK, GM, sigma):
     assert ldg == ldg2
     theta = torch.empty(N, dtype=torch.float64, device=dev)
     Cm = torch.empty(N, N, dtype=torch.float64, device=dev)
-    scratch = torch.empty(2 * N * N, dtype=torch.float64, device=dev)
+    scratch = torch.empty(lib.ds_eigh_scratch_elems(N), dtype=torch.float64, device=dev)
     info = torch.zeros(2, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         _lib.check(lib.ds_eigh_generalized_f64(kp, mp, N, ldg, float(sigma), _p(theta), _p(Cm), N, _p(scratch),
@@ -332,7 +332,8 @@ def pmg_prolong_add32(coarse, zc, z):
 
 
 def lobpcg(pattern, Kval, Mblk, X, nev, tol=1e-4, maxit=200, cheb_degree=8, sigma=0.0, cheb_ratio=30.0, n_rigid=6,
-           verbose=0, coarse=None, smooth_steps=3, smooth_ratio=8.0, coarse_degree=20, coarse_ratio=160.0):
+           verbose=0, coarse=None, smooth_steps=3, smooth_ratio=8.0, coarse_degree=20, coarse_ratio=160.0, nested=True,
+           nested_tol=1e-2):
     """Lowest `nev` pairs of K u = lam M u from the start block X (n, m) fp64 (overwritten with the
     M-orthonormal Ritz vectors).  `coarse`: a CoarseLevel with assembled Kval -> two-level
     preconditioner.  Returns (lam (m,), resid (m,), stats dict)."""
@@ -345,8 +346,9 @@ def lobpcg(pattern, Kval, Mblk, X, nev, tol=1e-4, maxit=200, cheb_degree=8, sigm
     opts = _lib.LobpcgOpts(nev=int(nev), maxit=int(maxit), cheb_degree=int(cheb_degree), tol=float(tol),
                            sigma=float(sigma), cheb_ratio=float(cheb_ratio), n_rigid=int(n_rigid), verbose=int(verbose),
                            smooth_steps=int(smooth_steps), coarse_degree=int(coarse_degree),
-                           smooth_ratio=float(smooth_ratio), coarse_ratio=float(coarse_ratio))
-    stats = (C.c_int64 * 8)()
+                           smooth_ratio=float(smooth_ratio), coarse_ratio=float(coarse_ratio),
+                           nested=int(bool(nested) and coarse is not None), nested_tol=float(nested_tol))
+    stats = (C.c_int64 * 12)()
     ws = workspace(dev)
     lvl = coarse.struct() if coarse is not None else None
     with torch.cuda.device(dev):
@@ -356,7 +358,7 @@ def lobpcg(pattern, Kval, Mblk, X, nev, tol=1e-4, maxit=200, cheb_degree=8, sigm
     return lam, res, dict(iterations=int(stats[0]), converged=int(stats[1]), spmm=int(stats[2]), status=int(stats[3]),
                           cheb_steps=int(stats[4]), cheb_cols_avg=(stats[5] / stats[4] if stats[4] else 0.0),
                           coarse_steps=int(stats[6]), coarse_cols_avg=(stats[7] / stats[6] if stats[6] else 0.0),
-                          two_level=coarse is not None)
+                          two_level=coarse is not None, nested_iterations=int(stats[8]), nested_status=int(stats[9]))
 
 
 def corner_incidence(tets_i32, order, n_nodes):

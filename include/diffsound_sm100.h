@@ -117,11 +117,13 @@ int ds_gram_sym2_f64(const double* S, const double* KS, const double* MS, int64_
 /* Y (n x q) = beta*Y + A (n x p) C (p x q, row-major ldc) */
 int ds_block_gemm_f64(const double* A, int64_t lda, int p, const double* C, int64_t ldc, int q,
                       int64_t n, double beta, double* Y, int64_t ldy, void* stream);
-/* Generalised symmetric eigenproblem GK c = theta GM c, N <= 144, one CTA:
- * Cholesky of GM and of GK + sigma*GM, one-sided Jacobi in shared memory.
+/* Generalised symmetric eigenproblem GK c = theta GM c, N <= 144: Cholesky of GM and of
+ * GK + sigma*GM (one CTA), one-sided Jacobi on a thread-block cluster of 8 CTAs (rows in registers,
+ * row exchange through distributed shared memory), back substitution (one CTA).
  * theta ascending [N], C [N x N] row-major (columns = GM-orthonormal vectors).
- * scratch: fp64 [2*N*N].  info (device int[2]): {0 ok | failing pivot index+1 (+1000 when
- * the failure is in GK + sigma*GM), sweeps used}. */
+ * scratch: fp64 [ds_eigh_scratch_elems(N)].  info (device int[2]): {0 ok | failing pivot index+1
+ * (+1000 when the failure is in GK + sigma*GM), sweeps used}. */
+int64_t ds_eigh_scratch_elems(int N);
 int ds_eigh_generalized_f64(const double* GK, const double* GM, int N, int64_t ldg, double sigma,
                             double* theta, double* C, int64_t ldc, double* scratch, int* info,
                             void* stream);
@@ -132,9 +134,10 @@ int ds_eigh_generalized_f64(const double* GK, const double* GM, int N, int64_t l
  * behind the lobpcg / lobpcg_func API mirror (src/lobpcg/_lobpcg.py:8-212).
  * X: fp64 [n x m] row-major start block on entry (m >= nev, multiple of 16),
  * M-orthonormal Ritz vectors on exit; lambda_out [m]; resid_out [m] relative
- * residuals; stats_host (host int64[8]) = {iterations, converged, spmm_count, status,
+ * residuals; stats_host (host int64[12]) = {iterations, converged, spmm_count, status,
  * fine-level FP32 SpMM launches, sum over those launches of the column count,
- * coarse-level launches, sum of their column counts}.
+ * coarse-level launches, sum of their column counts, iterations of the nested coarse eigen-solve,
+ * its status, 0, 0}.
  * Preconditioner (FP32, see ds_spmm32): `cheb_degree` steps of block-Jacobi Chebyshev on
  * K + sigma*M, or, when `coarse` is given (quadratic meshes), a two-level p-multigrid V-cycle:
  * `smooth_steps` Chebyshev-Jacobi steps on [lmax/smooth_ratio, lmax] before and after a
@@ -153,6 +156,9 @@ typedef struct ds_lobpcg_opts {
     int coarse_degree;  /* two-level only: Chebyshev steps of the coarse solve */
     double smooth_ratio;/* lmax / lmin of the smoother interval (default 8) */
     double coarse_ratio;/* lmax / lmin of the coarse Chebyshev interval */
+    int nested;         /* two-level only (needs coarse->Mblk): solve the P1 eigenproblem first and start
+                           the P2 iteration from its prolonged Ritz vectors (nested iteration) */
+    double nested_tol;  /* residual tolerance of that coarse solve (default 1e-2) */
 } ds_lobpcg_opts;
 /* Coarse level of the two-level preconditioner: the P1 operator on the corner nodes of a quadratic
  * mesh (pattern + values from ds_pattern_* / ds_assemble_km at order 1 on ds_pmg_coarse_fill's

@@ -184,7 +184,7 @@ def main():
     K, M = mo.assemble(pv, pt, 2, STEEL[1], STEEL[2], STEEL[0])
     n = K.shape[0]
     print(f"N={N} n={n} nnz={K.nnz} assemble {time.time() - t0:.1f}s")
-    m, nev = 48, 38
+    m, nev = int(os.environ.get("PROTO_M", "48")), 38
     rng = np.random.default_rng(0)
     X0 = rng.standard_normal((n, m))
     p = pv.numpy().astype(np.float64); p = p - p.mean(0)

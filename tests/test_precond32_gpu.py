@@ -171,8 +171,9 @@ def test_galerkin_coarse_operator_is_p1_stiffness(meshes):
     assert np.abs(G - Kc.toarray()).max() <= 1e-5 * np.abs(G).max()
 
 
-@pytest.mark.parametrize("mesh,two_level", [("grid16", True), ("grid16", False), ("bowl", True)])
-def test_eigensolver_two_level_matches_arpack(meshes, mesh, two_level):
+@pytest.mark.parametrize("mesh,two_level,nested", [("grid16", True, True), ("grid16", True, False), ("grid16", False, False),
+                                                   ("bowl", True, True)])
+def test_eigensolver_two_level_matches_arpack(meshes, mesh, two_level, nested):
     """LOBPCG with the FP32 two-level (or one-level Chebyshev) preconditioner reproduces the ARPACK
     spectrum of the oracle's matrices to 1e-6 relative (north-star tolerance) on quadratic meshes."""
     from diffsound_b200.diffelastic.diff_model import DiffSoundObj
@@ -181,8 +182,10 @@ def test_eigensolver_two_level_matches_arpack(meshes, mesh, two_level):
     k = 16
     obj = DiffSoundObj(torch.as_tensor(v).to(DEV), torch.as_tensor(t).to(DEV), mode_num=k, order=2, mat=MatSet.Steel)
     obj.two_level = two_level
+    obj.nested_start = nested
     obj.eigen_decomposition()
     assert obj.eig_stats["two_level"] == two_level
+    assert (obj.eig_stats["nested_iterations"] > 0) == nested
     pv, pt = mo.promote(torch.as_tensor(v), torch.as_tensor(t), 2)
     rho, E, nu = MatSet.Steel[:3]
     K, M = mo.assemble(pv, pt, 2, E, nu, rho)
