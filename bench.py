@@ -284,8 +284,9 @@ def main():
         # block Z once plus R and Zprev, and writes Znew: 4 x n x c x 4 B (3 for the residual launch of a
         # V-cycle, which has no Zprev).
         c_avg = stats["cheb_cols_avg"]
-        steps_total = stats["cheb_steps"]
-        streams = (5 * 4 + 3) / 6.0 if stats.get("two_level") else 4.0
+        steps_total = stats["cheb_steps"]          # V-cycle smoothing + residual launches + the 20 power-iteration launches
+        n_resid = stats["iterations"] if stats.get("two_level") else 0
+        streams = 4.0 - n_resid / steps_total
         per_launch_bytes = nnzb * 40 + n_nodes * (4 + 36) + streams * n * c_avg * 4
         t_avg = prof["cheb_step"]["ms"] / prof["cheb_step"]["count"] * 1e-3     # seconds per launch
         roof = {"bound": "hbm", "kernel": "k_spmm32 (FP32 block-CSR SpMM on TMA-staged 40 B records, fused Chebyshev "
@@ -302,6 +303,7 @@ def main():
                                    "one independent mesh per GPU",
                        "l2_policy": "inputs larger than L2 (K values alone 553 MB vs 126 MB L2); no flush needed",
                        "eig_tol": DiffSoundObj.eig_tol, "lobpcg_iterations": stats["iterations"] if stats else None,
+                       "nested_p1_iterations": stats.get("nested_iterations") if stats else None,
                        "preconditioner": ("fp32 two-level p-multigrid (P2 Chebyshev-Jacobi smoother, P1 coarse Chebyshev)"
                                           if stats and stats.get("two_level") else "fp32 block-Jacobi Chebyshev"),
                        "pattern_rebuilt_each_step": True, "eigensolver_cold_start": True},

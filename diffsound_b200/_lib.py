@@ -25,7 +25,8 @@ class LobpcgOpts(C.Structure):
     _fields_ = [("nev", C.c_int), ("maxit", C.c_int), ("cheb_degree", C.c_int), ("tol", C.c_double),
                 ("sigma", C.c_double), ("cheb_ratio", C.c_double), ("n_rigid", C.c_int), ("verbose", C.c_int),
                 ("smooth_steps", C.c_int), ("coarse_degree", C.c_int), ("smooth_ratio", C.c_double),
-                ("coarse_ratio", C.c_double), ("nested", C.c_int), ("nested_tol", C.c_double)]
+                ("coarse_ratio", C.c_double), ("nested", C.c_int), ("nested_tol", C.c_double),
+                ("nested_degree", C.c_int)]
 
 
 class PmgLevel(C.Structure):

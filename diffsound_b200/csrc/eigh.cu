@@ -35,7 +35,7 @@ constexpr int JC_LD = 32 * JC_E;                  // row pitch of Y in global sc
 constexpr int JC_SLOT = JC_LD + 8;                // mailbox slot: elements + |row|^2 at [JC_LD]
 static_assert(JC_GPC * JC_CL * 2 == EIG_MAXN, "line positions must tile the cluster");
 
-// scratch layout (doubles): L [N*N] | R^T [N*N] | Y [(N+1) * JC_LD] | scale [N] | sigma, fail [8]
+// scratch layout (doubles): L^T [N*N] | R [N*N] | Y [(N+1) * JC_LD] | scale [N] | sigma, fail [8]
 __host__ __device__ inline size_t eig_off_Rt(int N) { return (size_t)N * N; }
 __host__ __device__ inline size_t eig_off_Y(int N) { return 2 * (size_t)N * N; }
 __host__ __device__ inline size_t eig_off_scale(int N) { return eig_off_Y(N) + (size_t)(N + 1) * JC_LD; }
@@ -86,8 +86,8 @@ k_eigh_prepare(const double* __restrict__ GK, const double* __restrict__ GM, int
     double* s_scale = S + (size_t)N * ld;        // [N]
     int* s_flag = reinterpret_cast<int*>(s_scale + N);
     const int tid = threadIdx.x, nt = blockDim.x;
-    double* Lg = scratch;                        // L, row-major [N][N]
-    double* Rt = scratch + eig_off_Rt(N);        // R^T, row-major: Rt[k][i] = R[i][k]
+    double* Lt = scratch;                        // L^T, row-major: Lt[k][i] = L[i][k]
+    double* Rg = scratch + eig_off_Rt(N);        // R, row-major [N][N]
     double* Yg = scratch + eig_off_Y(N);
     double* meta = scratch + eig_off_meta(N);
     if (tid == 0) { s_flag[0] = 0; meta[1] = 1.0; }      // meta[1] = fail until the factorisations succeed
@@ -113,8 +113,8 @@ k_eigh_prepare(const double* __restrict__ GK, const double* __restrict__ GM, int
     int bad = chol_lower(S, N, ld, s_flag);
     if (bad) { if (tid == 0) { info[0] = bad; info[1] = 0; } return; }
     for (int t = tid; t < N * N; t += nt) {
-        int i = t / N, j = t % N;
-        Lg[t] = (j <= i) ? S[i * ld + j] : 0.0;
+        int k = t / N, i = t % N;   // Lt[k][i] = L[i][k]
+        Lt[t] = (k <= i) ? S[i * ld + k] : 0.0;
     }
     __syncthreads();
     // ---- R = chol(D (GK + sigma GM) D)
@@ -128,26 +128,26 @@ k_eigh_prepare(const double* __restrict__ GK, const double* __restrict__ GM, int
     bad = chol_lower(S, N, ld, s_flag);
     if (bad) { if (tid == 0) { info[0] = 1000 + bad; info[1] = 0; } return; }
     for (int t = tid; t < N * N; t += nt) {
-        int i = t / N, k = t % N;   // Rt[k][i] = R[i][k]
-        Rt[(size_t)k * N + i] = (k <= i) ? S[i * ld + k] : 0.0;
-    }
-    for (int t = tid; t < N * N; t += nt) {
         int i = t / N, j = t % N;
+        Rg[t] = (j <= i) ? S[i * ld + j] : 0.0;
         if (j > i) S[i * ld + j] = 0.0;
     }
     __threadfence_block();
     __syncthreads();
-    // ---- Y = L^-1 R  (forward substitution, one thread per column j; Y lower triangular)
-    if (tid < N) {
-        int j = tid;
-        for (int i = j; i < N; ++i) {
-            double v = S[i * ld + j];
-            const double* Li = Lg + (size_t)i * N;
-            for (int k = j; k < i; ++k) v -= Li[k] * S[k * ld + j];
-            S[i * ld + j] = v / Li[i];
+    // ---- Y = L^-1 R in place (Y lower triangular), right-looking: once row i is final it is
+    //      eliminated from all later rows by the whole CTA (column i of L = row i of Lt, contiguous)
+    for (int i = 0; i < N; ++i) {
+        const double* Lcol = Lt + (size_t)i * N;     // Lcol[i'] = L[i'][i]
+        const double rd = 1.0 / Lcol[i];
+        for (int j = tid; j <= i; j += nt) S[i * ld + j] *= rd;
+        __syncthreads();
+        const int w = i + 1, cnt = (N - i - 1) * w;
+        for (int t = tid; t < cnt; t += nt) {
+            const int ii = i + 1 + t / w, j = t % w;
+            S[ii * ld + j] -= Lcol[ii] * S[i * ld + j];
         }
+        __syncthreads();
     }
-    __syncthreads();
     // ---- rows of Y (zero padded to JC_LD, plus one zero row when N is odd) -> global
     const int Np = (N + 1) & ~1;
     for (int t = tid; t < Np * JC_LD; t += nt) {
@@ -328,7 +328,7 @@ k_eigh_finish(int N, const __grid_constant__ EigIdx ix, double* __restrict__ the
     int* s_rank = reinterpret_cast<int*>(s_theta + N + 2);   // [N]
     int* s_flag = s_rank + N;                    // [2]
     const int tid = threadIdx.x, nt = blockDim.x;
-    const double* Rt = scratch + eig_off_Rt(N);
+    const double* Rg = scratch + eig_off_Rt(N);  // R, row-major (lower triangular)
     const double* Yg = scratch + eig_off_Y(N);
     const double* meta = scratch + eig_off_meta(N);
     if (meta[1] != 0.0) return;                  // info was set by k_eigh_prepare
@@ -376,18 +376,21 @@ k_eigh_finish(int N, const __grid_constant__ EigIdx ix, double* __restrict__ the
         theta[rk] = tj;
     }
     __syncthreads();
-    // ---- c_j^T = y_j R^-1 (back substitution, thread per vector), scaled, placed in column rank_j
-    if (tid < N) {
-        int j = tid;
-        double* y = S + (size_t)j * ld;
-        for (int k = N - 1; k >= 0; --k) {
-            double v = y[k];
-            const double* Rk = Rt + (size_t)k * N;   // Rk[i] = R[i][k]
-            for (int i = k + 1; i < N; ++i) v -= y[i] * Rk[i];
-            y[k] = v / Rk[k];
+    // ---- c_j^T = y_j R^-1 for all rows j at once (x R = y, R lower triangular), right-looking:
+    //      column k of every x is final after the division, then it is eliminated from columns k' < k
+    //      with row k of R (contiguous); scaled and placed in column rank_j below
+    for (int k = N - 1; k >= 0; --k) {
+        const double* Rk = Rg + (size_t)k * N;       // Rk[k'] = R[k][k'], k' <= k
+        const double rd = 1.0 / Rk[k];
+        for (int j = tid; j < N; j += nt) S[(size_t)j * ld + k] *= rd;
+        __syncthreads();
+        const int cnt = N * k;
+        for (int t = tid; t < cnt; t += nt) {
+            const int j = t / k, kp = t - j * k;
+            S[(size_t)j * ld + kp] -= S[(size_t)j * ld + k] * Rk[kp];
         }
+        __syncthreads();
     }
-    __syncthreads();
     for (int t = tid; t < N * N; t += nt) {
         int k = t / N, j = t % N;
         C[(int64_t)ix.v[k] * ldc + s_rank[j]] = S[(size_t)j * ld + k] * s_scale[k];

@@ -113,6 +113,7 @@ struct Driver {
     ds_lobpcg_opts o;
 
     const ds_pmg_level* cl = nullptr;   // optional coarse (P1) level
+    int fine_prof_cls = PROF_CHEB;      // timing class of this driver's own level (the nested coarse solve reports as coarse)
     Level32 fine, coarse;
     float *R32, *Za, *Zb, *RC32, *ZCa, *ZCb;
     double *Xc = nullptr, *lamc = nullptr, *resc = nullptr;    // nested coarse eigen-solve
@@ -182,7 +183,7 @@ struct Driver {
         }
         // FP32 copies of the operators (records + block-Jacobi inverses)
         DS_TRY(fine.setup(a, brow, bcol, n_nodes, nnzb, Kval, Mblk, o.sigma > 0.0 ? o.sigma : 0.0, st));
-        fine.prof_cls = PROF_CHEB;
+        fine.prof_cls = fine_prof_cls;
         if (cl) {
             DS_TRY(coarse.setup(a, cl->brow, cl->bcol, cl->n_nodes, nnzb_c, cl->Kval, cl->Mblk,
                                 o.sigma > 0.0 ? o.sigma : 0.0, st));
@@ -244,7 +245,8 @@ struct Driver {
             // b = a + 0 (a - a) + (-1) invD (0 - A a) = (I + invD A) a
             DS_TRY(spmm32(S32_MODE_CHEB, L.brow, L.rec, L.n_nodes, w, a, zero_r, L.invD, a, b, 0.f, -1.f, L.prof_cls, st));
             std::swap(a, b);
-            spmm_count++;
+            L.launches++;
+            L.cols += w;
         }
         DS_TRY(norms_of(a, n1));
         double best = 0.0;
@@ -296,11 +298,14 @@ struct Driver {
         dc.n_nodes = cl->n_nodes; dc.n = 3 * cl->n_nodes;
         dc.Kval = cl->Kval; dc.Mblk = cl->Mblk;
         dc.m = m;
+        dc.fine_prof_cls = PROF_COARSE;
         dc.o = o;
         dc.o.nested = 0;
-        dc.o.tol = o.nested_tol > 0.0 ? o.nested_tol : 1e-2;
+        dc.o.tol = o.nested_tol > 0.0 ? o.nested_tol : 3e-2;
         dc.o.maxit = 40;
-        const int deg = (int)std::min(40.0, std::max(8.0, std::round(std::cbrt((double)dc.n) / 3.0)));
+        const int deg = o.nested_degree > 0
+                            ? o.nested_degree
+                            : (int)std::min(48.0, std::max(8.0, std::round(std::cbrt((double)dc.n) / 1.5)));
         dc.o.cheb_degree = deg;
         dc.o.cheb_ratio = 0.4 * deg * deg;
         int64_t cstats[12] = {0};
@@ -308,6 +313,8 @@ struct Driver {
         nested_iters = cstats[0];
         nested_status = cstats[3];
         spmm_count += cstats[2];
+        coarse.launches += cstats[4];           // the nested solve's SpMMs are coarse-level work
+        coarse.cols += cstats[5];
         DS_TRY(prolong64(cl->parents, n_nodes, Xc, m, m, X, m, st));
         return DS_OK;
     }

@@ -68,18 +68,39 @@ __device__ __forceinline__ void st_vec(float* p, const float* v) {
     else *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
 }
 
+// Column ownership of lane l (of LPR) inside a C = LPR * CPT wide row: 128-bit chunk [4l, 4l+4) and, for
+// CPT = 6 / 8, a second 64- / 128-bit chunk behind the first 4*LPR columns -- so that the LPR lanes of a
+// group always touch CONTIGUOUS bytes (a lane owning CPT contiguous columns makes every load
+// instruction of the group hit all sectors of the row: 3x sector over-fetch measured at c = 48).
+template <int LPR, int CPT>
+__device__ __forceinline__ void ld_row(const float* row, int l, float* out) {
+    ld_vec<4>(row + 4 * l, out);
+    if constexpr (CPT == 6) ld_vec<2>(row + 4 * LPR + 2 * l, out + 4);
+    if constexpr (CPT == 8) ld_vec<4>(row + 4 * LPR + 4 * l, out + 4);
+}
+template <int LPR, int CPT>
+__device__ __forceinline__ void ld_row_plain(const float* row, int l, float* out) {
+    ld_vec_plain<4>(row + 4 * l, out);
+    if constexpr (CPT == 6) ld_vec_plain<2>(row + 4 * LPR + 2 * l, out + 4);
+    if constexpr (CPT == 8) ld_vec_plain<4>(row + 4 * LPR + 4 * l, out + 4);
+}
+template <int LPR, int CPT>
+__device__ __forceinline__ void st_row(float* row, int l, const float* v) {
+    st_vec<4>(row + 4 * l, v);
+    if constexpr (CPT == 6) st_vec<2>(row + 4 * LPR + 2 * l, v + 4);
+    if constexpr (CPT == 8) st_vec<4>(row + 4 * LPR + 4 * l, v + 4);
+}
+
 // acc[c][t] += K[c][d] * X[3j+d][cols of this lane] for one block record
-template <int C, int CPT, int VEC>
-__device__ __forceinline__ void block_fma(const uint2* __restrict__ r, const float* __restrict__ Xl,
+template <int LPR, int CPT>
+__device__ __forceinline__ void block_fma(const uint2* __restrict__ r, const float* __restrict__ X, int l,
                                           float (&acc)[3][CPT]) {
-    constexpr int NV = CPT / VEC;
+    constexpr int C = LPR * CPT;
     const uint2 a0 = r[0], a1 = r[1], a2 = r[2], a3 = r[3], a4 = r[4];
-    const float* xr = Xl + (int64_t)(int)a4.y * (3 * C);
+    const float* xr = X + (int64_t)(int)a4.y * (3 * C);
     float x[3][CPT];
 #pragma unroll
-    for (int d = 0; d < 3; ++d)
-#pragma unroll
-        for (int q = 0; q < NV; ++q) ld_vec<VEC>(xr + d * C + q * VEC, &x[d][q * VEC]);
+    for (int d = 0; d < 3; ++d) ld_row<LPR, CPT>(xr + d * C, l, x[d]);
     const float k00 = __uint_as_float(a0.x), k01 = __uint_as_float(a0.y), k02 = __uint_as_float(a1.x);
     const float k10 = __uint_as_float(a1.y), k11 = __uint_as_float(a2.x), k12 = __uint_as_float(a2.y);
     const float k20 = __uint_as_float(a3.x), k21 = __uint_as_float(a3.y), k22 = __uint_as_float(a4.x);
@@ -92,22 +113,20 @@ __device__ __forceinline__ void block_fma(const uint2* __restrict__ r, const flo
 }
 
 // two independent blocks with all loads issued before the first FMA (memory-level parallelism)
-template <int C, int CPT, int VEC>
+template <int LPR, int CPT>
 __device__ __forceinline__ void block_fma2(const uint2* __restrict__ ra, const uint2* __restrict__ rb,
-                                           const float* __restrict__ Xl, float (&acc)[3][CPT]) {
-    constexpr int NV = CPT / VEC;
+                                           const float* __restrict__ X, int l, float (&acc)[3][CPT]) {
+    constexpr int C = LPR * CPT;
     const uint2 a0 = ra[0], a1 = ra[1], a2 = ra[2], a3 = ra[3], a4 = ra[4];
     const uint2 b0 = rb[0], b1 = rb[1], b2 = rb[2], b3 = rb[3], b4 = rb[4];
-    const float* xa = Xl + (int64_t)(int)a4.y * (3 * C);
-    const float* xb = Xl + (int64_t)(int)b4.y * (3 * C);
+    const float* xa = X + (int64_t)(int)a4.y * (3 * C);
+    const float* xb = X + (int64_t)(int)b4.y * (3 * C);
     float x[3][CPT], y[3][CPT];
 #pragma unroll
-    for (int d = 0; d < 3; ++d)
-#pragma unroll
-        for (int q = 0; q < NV; ++q) {
-            ld_vec<VEC>(xa + d * C + q * VEC, &x[d][q * VEC]);
-            ld_vec<VEC>(xb + d * C + q * VEC, &y[d][q * VEC]);
-        }
+    for (int d = 0; d < 3; ++d) {
+        ld_row<LPR, CPT>(xa + d * C, l, x[d]);
+        ld_row<LPR, CPT>(xb + d * C, l, y[d]);
+    }
     {
         const float k00 = __uint_as_float(a0.x), k01 = __uint_as_float(a0.y), k02 = __uint_as_float(a1.x);
         const float k10 = __uint_as_float(a1.y), k11 = __uint_as_float(a2.x), k12 = __uint_as_float(a2.y);
@@ -142,8 +161,6 @@ k_spmm32(const int32_t* __restrict__ brow, const uint2* __restrict__ rec, int64_
          const float* Zprev, float* Out, float ab, float cc) {
     constexpr int C = LPR * CPT;
     constexpr int NG = 32 / LPR;
-    constexpr int VEC = (CPT % 4 == 0) ? 4 : 2;
-    constexpr int NV = CPT / VEC;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * S32_STAGE_BYTES);
     int* ticket = reinterpret_cast<int*>(full + 2);        // [2]
@@ -180,7 +197,6 @@ k_spmm32(const int32_t* __restrict__ brow, const uint2* __restrict__ rec, int64_
         tile_range(tile, r0, r1, b0, b1);
         if (b1 > b0) issue(0, b0, min(b1, b0 + (int64_t)S32_CAP));
     }
-    const float* Xl = X + l * CPT;
     for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
         const int s = it & 1;
         int64_t r0, r1, tb0, tb1;
@@ -218,14 +234,14 @@ k_spmm32(const int32_t* __restrict__ brow, const uint2* __restrict__ rec, int64_
             const int64_t se = min(rb1, staged_hi);          // blocks [rb0, se) are in shared memory
             int64_t p = rb0 + g;
             for (; p + NG < se; p += 2 * NG)
-                block_fma2<C, CPT, VEC>(reinterpret_cast<const uint2*>(stage + (p - sb) * S32_REC_BYTES),
-                                        reinterpret_cast<const uint2*>(stage + (p + NG - sb) * S32_REC_BYTES), Xl, acc);
+                block_fma2<LPR, CPT>(reinterpret_cast<const uint2*>(stage + (p - sb) * S32_REC_BYTES),
+                                     reinterpret_cast<const uint2*>(stage + (p + NG - sb) * S32_REC_BYTES), X, l, acc);
             if (p < se) {
-                block_fma<C, CPT, VEC>(reinterpret_cast<const uint2*>(stage + (p - sb) * S32_REC_BYTES), Xl, acc);
+                block_fma<LPR, CPT>(reinterpret_cast<const uint2*>(stage + (p - sb) * S32_REC_BYTES), X, l, acc);
                 p += NG;
             }
             for (; p < rb1; p += NG)                         // overflow of an oversized tile: straight from global
-                block_fma<C, CPT, VEC>(reinterpret_cast<const uint2*>(gbase + p * S32_REC_BYTES), Xl, acc);
+                block_fma<LPR, CPT>(reinterpret_cast<const uint2*>(gbase + p * S32_REC_BYTES), X, l, acc);
 #pragma unroll
             for (int off = LPR; off < 32; off <<= 1)
 #pragma unroll
@@ -233,7 +249,7 @@ k_spmm32(const int32_t* __restrict__ brow, const uint2* __restrict__ rec, int64_
 #pragma unroll
                     for (int t = 0; t < CPT; ++t) acc[c][t] += __shfl_xor_sync(0xffffffffu, acc[c][t], off);
             if (g < 3) {
-                const int64_t o = (3 * row + g) * C + l * CPT;
+                const int64_t o = (3 * row + g) * C;          // output row of this lane group
                 float a[CPT];
 #pragma unroll
                 for (int t = 0; t < CPT; ++t) a[t] = g == 0 ? acc[0][t] : (g == 1 ? acc[1][t] : acc[2][t]);
@@ -243,31 +259,26 @@ k_spmm32(const int32_t* __restrict__ brow, const uint2* __restrict__ rec, int64_
                     for (int t = 0; t < CPT; ++t) v[t] = a[t];
                 } else if (MODE == S32_RESID) {
                     float rv[CPT];
-#pragma unroll
-                    for (int q = 0; q < NV; ++q) ld_vec<VEC>(R + o + q * VEC, &rv[q * VEC]);
+                    ld_row<LPR, CPT>(R + o, l, rv);
 #pragma unroll
                     for (int t = 0; t < CPT; ++t) v[t] = rv[t] - a[t];
                 } else {
                     const float d0 = __ldg(invD + 9 * row + 3 * g), d1 = __ldg(invD + 9 * row + 3 * g + 1),
                                 d2 = __ldg(invD + 9 * row + 3 * g + 2);
                     float r0v[CPT], r1v[CPT], r2v[CPT], z[CPT], zp[CPT];
-                    const int64_t ob = 3 * row * C + l * CPT;
-#pragma unroll
-                    for (int q = 0; q < NV; ++q) {
-                        ld_vec<VEC>(R + ob + q * VEC, &r0v[q * VEC]);
-                        ld_vec<VEC>(R + ob + C + q * VEC, &r1v[q * VEC]);
-                        ld_vec<VEC>(R + ob + 2 * C + q * VEC, &r2v[q * VEC]);
-                        ld_vec<VEC>(X + o + q * VEC, &z[q * VEC]);
-                        ld_vec_plain<VEC>(Zprev + o + q * VEC, &zp[q * VEC]);
-                    }
+                    const int64_t ob = 3 * row * C;
+                    ld_row<LPR, CPT>(R + ob, l, r0v);
+                    ld_row<LPR, CPT>(R + ob + C, l, r1v);
+                    ld_row<LPR, CPT>(R + ob + 2 * C, l, r2v);
+                    ld_row<LPR, CPT>(X + o, l, z);
+                    ld_row_plain<LPR, CPT>(Zprev + o, l, zp);
 #pragma unroll
                     for (int t = 0; t < CPT; ++t) {
                         const float dr = d0 * (r0v[t] - acc[0][t]) + d1 * (r1v[t] - acc[1][t]) + d2 * (r2v[t] - acc[2][t]);
                         v[t] = z[t] + ab * (z[t] - zp[t]) + cc * dr;
                     }
                 }
-#pragma unroll
-                for (int q = 0; q < NV; ++q) st_vec<VEC>(Out + o + q * VEC, &v[q * VEC]);
+                st_row<LPR, CPT>(Out + o, l, v);
             }
         }
         __syncthreads();     // every warp is done with stage s (and ticket[s]) before it is refilled

@@ -156,6 +156,8 @@ class DiffSoundObj:
     eig_tol = 1e-5
     two_level = True        # quadratic meshes: p-multigrid preconditioner (P1 coarse level) in the eigensolver
     nested_start = True     # ... and a P1 eigen-solve for the start block (skipped on a warm start)
+    nested_tol = 3e-2
+    nested_degree = 0       # 0: automatic
     eig_maxit = 400
 
     def __init__(self, vertices=None, tets=None, mode_num=16, mat=MatSet.Ceramic, order=1, mat_model=FixedLinear,
@@ -321,7 +323,8 @@ class DiffSoundObj:
             coarse.assemble(self._verts32, mu, la, coarse.ctab, self.deform.coarse_mtab(self._density_used))
             cdeg = int(min(64, max(6, round((3 * coarse.n_nodes) ** (1.0 / 3.0) / 1.2))))
             kw = dict(coarse=coarse, smooth_steps=3, smooth_ratio=8.0, coarse_degree=cdeg,
-                      coarse_ratio=0.4 * cdeg * cdeg, nested=self.nested_start and self._X is not X)
+                      coarse_ratio=0.4 * cdeg * cdeg, nested=self.nested_start and self._X is not X,
+                      nested_tol=self.nested_tol, nested_degree=self.nested_degree)
         lam, res, stats = native.lobpcg(pat, self._Kval, self._Mblk, X, nev=need, tol=self.eig_tol, maxit=self.eig_maxit,
                                         cheb_degree=deg, cheb_ratio=0.4 * deg * deg, n_rigid=6, **kw)
         if stats["status"] != 0:

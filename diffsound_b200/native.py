@@ -333,7 +333,7 @@ def pmg_prolong_add32(coarse, zc, z):
 
 def lobpcg(pattern, Kval, Mblk, X, nev, tol=1e-4, maxit=200, cheb_degree=8, sigma=0.0, cheb_ratio=30.0, n_rigid=6,
            verbose=0, coarse=None, smooth_steps=3, smooth_ratio=8.0, coarse_degree=20, coarse_ratio=160.0, nested=True,
-           nested_tol=1e-2):
+           nested_tol=3e-2, nested_degree=0):
     """Lowest `nev` pairs of K u = lam M u from the start block X (n, m) fp64 (overwritten with the
     M-orthonormal Ritz vectors).  `coarse`: a CoarseLevel with assembled Kval -> two-level
     preconditioner.  Returns (lam (m,), resid (m,), stats dict)."""
@@ -347,7 +347,8 @@ def lobpcg(pattern, Kval, Mblk, X, nev, tol=1e-4, maxit=200, cheb_degree=8, sigm
                            sigma=float(sigma), cheb_ratio=float(cheb_ratio), n_rigid=int(n_rigid), verbose=int(verbose),
                            smooth_steps=int(smooth_steps), coarse_degree=int(coarse_degree),
                            smooth_ratio=float(smooth_ratio), coarse_ratio=float(coarse_ratio),
-                           nested=int(bool(nested) and coarse is not None), nested_tol=float(nested_tol))
+                           nested=int(bool(nested) and coarse is not None), nested_tol=float(nested_tol),
+                           nested_degree=int(nested_degree))
     stats = (C.c_int64 * 12)()
     ws = workspace(dev)
     lvl = coarse.struct() if coarse is not None else None

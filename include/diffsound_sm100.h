@@ -158,7 +158,8 @@ typedef struct ds_lobpcg_opts {
     double coarse_ratio;/* lmax / lmin of the coarse Chebyshev interval */
     int nested;         /* two-level only (needs coarse->Mblk): solve the P1 eigenproblem first and start
                            the P2 iteration from its prolonged Ritz vectors (nested iteration) */
-    double nested_tol;  /* residual tolerance of that coarse solve (default 1e-2) */
+    double nested_tol;  /* residual tolerance of that coarse solve (default 3e-2) */
+    int nested_degree;  /* Chebyshev degree of the coarse solve's one-level preconditioner (0: automatic) */
 } ds_lobpcg_opts;
 /* Coarse level of the two-level preconditioner: the P1 operator on the corner nodes of a quadratic
  * mesh (pattern + values from ds_pattern_* / ds_assemble_km at order 1 on ds_pmg_coarse_fill's
