@@ -63,6 +63,13 @@ SIGNATURES = {
     "ds_k32_record_bytes": (i64, [i64]),
     "ds_k32_pack": (cint, [i32p, i32p, i64, i64, f64p, f64p, dbl, ptr, f32p, ptr]),
     "ds_spmm32": (cint, [cint, i32p, ptr, i64, cint, f32p, f32p, f32p, f32p, f32p, dbl, dbl, ptr]),
+    "ds_k32_pack_slab": (cint, [i32p, i32p, i64, i64, i64, f64p, f64p, dbl, ptr, ptr, f32p, ptr]),
+    "ds_spmm32_rowpart": (cint, [cint, i32p, ptr, i64, cint, C.POINTER(C.c_void_p), cint, cint, f32p, f32p, f32p, f32p,
+                                 dbl, dbl, ptr]),
+    "ds_peer_alloc": (cint, [i64, C.POINTER(C.c_void_p), C.POINTER(C.c_ubyte)]),
+    "ds_peer_open": (cint, [C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]),
+    "ds_peer_close": (cint, [ptr]),
+    "ds_peer_free": (cint, [ptr]),
     "ds_pmg_coarse_count": (cint, [ptr, i32p, i64, i64, i32p, C.POINTER(C.c_int64), ptr]),
     "ds_pmg_coarse_fill": (cint, [ptr, f32p, i32p, i64, i64, i32p, i64, i32p, f32p, i32p, i32p, i32p, ptr]),
     "ds_pmg_restrict32": (cint, [i32p, i32p, i64, f32p, cint, f32p, ptr]),

@@ -27,7 +27,8 @@ enum { S32_MODE_PLAIN = 0, S32_MODE_RESID = 1, S32_MODE_CHEB = 2 };
 int spmm32(int mode, const int32_t* brow, const void* rec, int64_t n_nodes, int ncols, const float* X, const float* R,
            const float* invD, const float* Zprev, float* Out, float ab, float cc, int prof_cls, cudaStream_t st);
 int pack_k32(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, const double* Kval, const double* Mblk,
-             double shift, void* rec, float* invD, cudaStream_t st);
+             double shift, void* rec, float* invD, cudaStream_t st, const uint32_t* colmap = nullptr,
+             int64_t row_offset = 0);
 int jacobi32(const float* invD, const float* R, int64_t n_nodes, int ncols, float cc, float* Out, cudaStream_t st);
 int restrict32(const int32_t* rptr, const int32_t* rlist, int64_t n_coarse, const float* res, int ncols, float* rc,
                cudaStream_t st);

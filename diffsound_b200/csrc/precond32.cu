@@ -24,6 +24,7 @@
 #include "kernels.cuh"
 #include "ptx.cuh"
 #include <utility>
+#include <cstring>
 
 namespace ds {
 
@@ -91,13 +92,26 @@ __device__ __forceinline__ void st_row(float* row, int l, const float* v) {
     if constexpr (CPT == 8) st_vec<4>(row + 4 * LPR + 4 * l, v + 4);
 }
 
+// Row-partitioned operation (one slab of node rows per GPU): the column id of a record is packed as
+// owner << 28 | node index inside the owner's slab, and the gathered block is addressed through a
+// table of per-rank base pointers -- the peers' slabs are mapped into this process (CUDA IPC) and read
+// over NVLink by plain loads.
+struct PeerTable {
+    const float* p[8];
+};
+template <bool PEER, int C>
+__device__ __forceinline__ const float* node_rows(const float* __restrict__ X, const PeerTable& tab, uint32_t j) {
+    if constexpr (PEER) return tab.p[j >> 28] + (int64_t)(j & 0x0fffffffu) * (3 * C);
+    else return X + (int64_t)(int)j * (3 * C);
+}
+
 // acc[c][t] += K[c][d] * X[3j+d][cols of this lane] for one block record
-template <int LPR, int CPT>
-__device__ __forceinline__ void block_fma(const uint2* __restrict__ r, const float* __restrict__ X, int l,
-                                          float (&acc)[3][CPT]) {
+template <int LPR, int CPT, bool PEER>
+__device__ __forceinline__ void block_fma(const uint2* __restrict__ r, const float* __restrict__ X,
+                                          const PeerTable& tab, int l, float (&acc)[3][CPT]) {
     constexpr int C = LPR * CPT;
     const uint2 a0 = r[0], a1 = r[1], a2 = r[2], a3 = r[3], a4 = r[4];
-    const float* xr = X + (int64_t)(int)a4.y * (3 * C);
+    const float* xr = node_rows<PEER, C>(X, tab, a4.y);
     float x[3][CPT];
 #pragma unroll
     for (int d = 0; d < 3; ++d) ld_row<LPR, CPT>(xr + d * C, l, x[d]);
@@ -113,14 +127,15 @@ __device__ __forceinline__ void block_fma(const uint2* __restrict__ r, const flo
 }
 
 // two independent blocks with all loads issued before the first FMA (memory-level parallelism)
-template <int LPR, int CPT>
+template <int LPR, int CPT, bool PEER>
 __device__ __forceinline__ void block_fma2(const uint2* __restrict__ ra, const uint2* __restrict__ rb,
-                                           const float* __restrict__ X, int l, float (&acc)[3][CPT]) {
+                                           const float* __restrict__ X, const PeerTable& tab, int l,
+                                           float (&acc)[3][CPT]) {
     constexpr int C = LPR * CPT;
     const uint2 a0 = ra[0], a1 = ra[1], a2 = ra[2], a3 = ra[3], a4 = ra[4];
     const uint2 b0 = rb[0], b1 = rb[1], b2 = rb[2], b3 = rb[3], b4 = rb[4];
-    const float* xa = X + (int64_t)(int)a4.y * (3 * C);
-    const float* xb = X + (int64_t)(int)b4.y * (3 * C);
+    const float* xa = node_rows<PEER, C>(X, tab, a4.y);
+    const float* xb = node_rows<PEER, C>(X, tab, b4.y);
     float x[3][CPT], y[3][CPT];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -154,11 +169,12 @@ __device__ __forceinline__ void block_fma2(const uint2* __restrict__ ra, const u
 // MODE PLAIN:  Out = A X
 //      RESID:  Out = R - A X
 //      CHEB:   Out = X + ab (X - Zprev) + cc invD (R - A X)      (Zprev may alias Out)
-template <int LPR, int CPT, int MODE>
+// PEER: X is this rank's own slab (rows of the epilogue), the gather goes through `tab`.
+template <int LPR, int CPT, int MODE, bool PEER>
 __global__ void __launch_bounds__(S32_THREADS)
 k_spmm32(const int32_t* __restrict__ brow, const uint2* __restrict__ rec, int64_t n_nodes,
          const float* __restrict__ X, const float* __restrict__ R, const float* __restrict__ invD,
-         const float* Zprev, float* Out, float ab, float cc) {
+         const float* Zprev, float* Out, float ab, float cc, const __grid_constant__ PeerTable tab) {
     constexpr int C = LPR * CPT;
     constexpr int NG = 32 / LPR;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -234,14 +250,15 @@ k_spmm32(const int32_t* __restrict__ brow, const uint2* __restrict__ rec, int64_
             const int64_t se = min(rb1, staged_hi);          // blocks [rb0, se) are in shared memory
             int64_t p = rb0 + g;
             for (; p + NG < se; p += 2 * NG)
-                block_fma2<LPR, CPT>(reinterpret_cast<const uint2*>(stage + (p - sb) * S32_REC_BYTES),
-                                     reinterpret_cast<const uint2*>(stage + (p + NG - sb) * S32_REC_BYTES), X, l, acc);
+                block_fma2<LPR, CPT, PEER>(reinterpret_cast<const uint2*>(stage + (p - sb) * S32_REC_BYTES),
+                                           reinterpret_cast<const uint2*>(stage + (p + NG - sb) * S32_REC_BYTES), X, tab,
+                                           l, acc);
             if (p < se) {
-                block_fma<LPR, CPT>(reinterpret_cast<const uint2*>(stage + (p - sb) * S32_REC_BYTES), X, l, acc);
+                block_fma<LPR, CPT, PEER>(reinterpret_cast<const uint2*>(stage + (p - sb) * S32_REC_BYTES), X, tab, l, acc);
                 p += NG;
             }
             for (; p < rb1; p += NG)                         // overflow of an oversized tile: straight from global
-                block_fma<LPR, CPT>(reinterpret_cast<const uint2*>(gbase + p * S32_REC_BYTES), X, l, acc);
+                block_fma<LPR, CPT, PEER>(reinterpret_cast<const uint2*>(gbase + p * S32_REC_BYTES), X, tab, l, acc);
 #pragma unroll
             for (int off = LPR; off < 32; off <<= 1)
 #pragma unroll
@@ -286,15 +303,17 @@ k_spmm32(const int32_t* __restrict__ brow, const uint2* __restrict__ rec, int64_
 }
 
 // records + block-Jacobi inverse from the FP64 matrix: one warp per node row
+// colmap (optional): record column id = colmap[global column]; row_offset: global id of local row 0
 __global__ void __launch_bounds__(256)
 k_pack_k32(const int32_t* __restrict__ brow, const int32_t* __restrict__ bcol, int64_t n_nodes,
            const double* __restrict__ Kval, const double* __restrict__ Mblk, double shift,
-           uint32_t* __restrict__ rec, float* __restrict__ invD) {
+           uint32_t* __restrict__ rec, float* __restrict__ invD, const uint32_t* __restrict__ colmap,
+           int64_t row_offset) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (row >= n_nodes) return;
-    const int64_t b0 = brow[row];
-    const int deg = (int)(brow[row + 1] - b0);
+    const int64_t b0 = brow[row] - brow[0];      // a slab passes a window of the global brow
+    const int deg = (int)(brow[row + 1] - brow[row]);
     const double* kb = Kval + 9 * b0;
     const int64_t rs = 3 * (int64_t)deg;
     for (int p = lane; p < deg; p += 32) {
@@ -311,8 +330,8 @@ k_pack_k32(const int32_t* __restrict__ brow, const int32_t* __restrict__ bcol, i
         uint32_t* o = rec + (b0 + p) * 10;
 #pragma unroll
         for (int q = 0; q < 9; ++q) o[q] = __float_as_uint((float)k[q]);
-        o[9] = (uint32_t)j;
-        if (j == row) {
+        o[9] = colmap ? colmap[j] : (uint32_t)j;
+        if (j == row + row_offset) {
             const double c00 = k[4] * k[8] - k[5] * k[7];
             const double c01 = k[5] * k[6] - k[3] * k[8];
             const double c02 = k[3] * k[7] - k[4] * k[6];
@@ -472,7 +491,8 @@ static int s32_grid(int64_t n_nodes) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_spmm32<8, 6, S32_CHEB>, S32_THREADS, S32_SMEM);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_spmm32<8, 6, S32_CHEB, false>, S32_THREADS,
+                                                      S32_SMEM);
         if (ctas_per_sm < 1) ctas_per_sm = 1;
     }
     const int64_t tiles = ceil_div(n_nodes, S32_ROWS);
@@ -480,20 +500,34 @@ static int s32_grid(int64_t n_nodes) {
     return (int)(tiles < g ? tiles : g);
 }
 
-template <int LPR, int CPT>
+template <int LPR, int CPT, bool PEER>
 static int launch_spmm32(int mode, const int32_t* brow, const void* rec, int64_t n_nodes, const float* X, const float* R,
-                         const float* invD, const float* Zprev, float* Out, float ab, float cc, cudaStream_t st) {
+                         const float* invD, const float* Zprev, float* Out, float ab, float cc, const PeerTable& tab,
+                         cudaStream_t st) {
     const int grid = s32_grid(n_nodes);
     auto go = [&](auto kern) -> int {
         kern<<<grid, S32_THREADS, S32_SMEM, st>>>(brow, reinterpret_cast<const uint2*>(rec), n_nodes, X, R, invD, Zprev,
-                                                  Out, ab, cc);
+                                                  Out, ab, cc, tab);
         DS_LAUNCH_CHECK();
         return DS_OK;
     };
     switch (mode) {
-        case S32_PLAIN: return go(k_spmm32<LPR, CPT, S32_PLAIN>);
-        case S32_RESID: return go(k_spmm32<LPR, CPT, S32_RESID>);
-        default: return go(k_spmm32<LPR, CPT, S32_CHEB>);
+        case S32_PLAIN: return go(k_spmm32<LPR, CPT, S32_PLAIN, PEER>);
+        case S32_RESID: return go(k_spmm32<LPR, CPT, S32_RESID, PEER>);
+        default: return go(k_spmm32<LPR, CPT, S32_CHEB, PEER>);
+    }
+}
+
+template <bool PEER>
+static int dispatch_spmm32(int mode, const int32_t* brow, const void* rec, int64_t n_nodes, int ncols, const float* X,
+                           const float* R, const float* invD, const float* Zprev, float* Out, float ab, float cc,
+                           const PeerTable& tab, cudaStream_t st) {
+    switch (ncols) {
+        case 16: return launch_spmm32<4, 4, PEER>(mode, brow, rec, n_nodes, X, R, invD, Zprev, Out, ab, cc, tab, st);
+        case 32: return launch_spmm32<8, 4, PEER>(mode, brow, rec, n_nodes, X, R, invD, Zprev, Out, ab, cc, tab, st);
+        case 48: return launch_spmm32<8, 6, PEER>(mode, brow, rec, n_nodes, X, R, invD, Zprev, Out, ab, cc, tab, st);
+        case 64: return launch_spmm32<8, 8, PEER>(mode, brow, rec, n_nodes, X, R, invD, Zprev, Out, ab, cc, tab, st);
+        default: set_error("spmm32: ncols=%d must be 16, 32, 48 or 64", ncols); return DS_ERR_ARG;
     }
 }
 
@@ -504,22 +538,37 @@ int spmm32(int mode, const int32_t* brow, const void* rec, int64_t n_nodes, int 
     DS_REQUIRE(mode == S32_PLAIN || R, "spmm32: this mode needs R");
     DS_REQUIRE(mode != S32_CHEB || (invD && Zprev), "spmm32: Chebyshev mode needs invD and Zprev");
     ProfScope prof(prof_cls, st);
-    switch (ncols) {
-        case 16: return launch_spmm32<4, 4>(mode, brow, rec, n_nodes, X, R, invD, Zprev, Out, ab, cc, st);
-        case 32: return launch_spmm32<8, 4>(mode, brow, rec, n_nodes, X, R, invD, Zprev, Out, ab, cc, st);
-        case 48: return launch_spmm32<8, 6>(mode, brow, rec, n_nodes, X, R, invD, Zprev, Out, ab, cc, st);
-        case 64: return launch_spmm32<8, 8>(mode, brow, rec, n_nodes, X, R, invD, Zprev, Out, ab, cc, st);
-        default: set_error("spmm32: ncols=%d must be 16, 32, 48 or 64", ncols); return DS_ERR_ARG;
+    PeerTable none = {};
+    return dispatch_spmm32<false>(mode, brow, rec, n_nodes, ncols, X, R, invD, Zprev, Out, ab, cc, none, st);
+}
+
+// row-partitioned: Xparts[r] = base of rank r's slab of the gathered block (device pointers valid in this
+// process); X_own = this rank's slab (Xparts[rank]); all other arrays are local slabs
+int spmm32_rowpart(int mode, const int32_t* brow, const void* rec, int64_t n_local, int ncols, const float* const* Xparts,
+                   int world, int rank, const float* R, const float* invD, const float* Zprev, float* Out, float ab,
+                   float cc, cudaStream_t st) {
+    DS_REQUIRE(brow && rec && Xparts && Out, "spmm32_rowpart: null argument");
+    DS_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "spmm32_rowpart: world=%d rank=%d (max 8 ranks)", world, rank);
+    DS_REQUIRE(mode == S32_PLAIN || R, "spmm32_rowpart: this mode needs R");
+    DS_REQUIRE(mode != S32_CHEB || (invD && Zprev), "spmm32_rowpart: Chebyshev mode needs invD and Zprev");
+    PeerTable tab = {};
+    for (int r = 0; r < world; ++r) {
+        DS_REQUIRE(Xparts[r] != nullptr, "spmm32_rowpart: missing slab pointer of rank %d", r);
+        tab.p[r] = Xparts[r];
     }
+    DS_REQUIRE(tab.p[rank] != Out, "spmm32_rowpart: the gathered block must not alias the output");
+    ProfScope prof(PROF_CHEB, st);
+    return dispatch_spmm32<true>(mode, brow, rec, n_local, ncols, tab.p[rank], R, invD, Zprev, Out, ab, cc, tab, st);
 }
 
 int pack_k32(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, const double* Kval, const double* Mblk,
-             double shift, void* rec, float* invD, cudaStream_t st) {
+             double shift, void* rec, float* invD, cudaStream_t st, const uint32_t* colmap, int64_t row_offset) {
     DS_REQUIRE(brow && bcol && Kval && rec && invD, "pack_k32: null argument");
     DS_REQUIRE(((uintptr_t)rec & 15) == 0, "pack_k32: records must be 16-byte aligned");
     ProfScope prof(PROF_COPY, st);
     k_pack_k32<<<(unsigned)ceil_div(n_nodes * 32, 256), 256, 0, st>>>(brow, bcol, n_nodes, Kval, Mblk, shift,
-                                                                      reinterpret_cast<uint32_t*>(rec), invD);
+                                                                      reinterpret_cast<uint32_t*>(rec), invD, colmap,
+                                                                      row_offset);
     DS_LAUNCH_CHECK();
     return DS_OK;
 }
@@ -667,6 +716,51 @@ extern "C" int ds_spmm32(int mode, const int32_t* brow, const void* rec, int64_t
     DS_REQUIRE(mode >= 0 && mode <= 2, "ds_spmm32: mode must be 0 (A X), 1 (R - A X) or 2 (Chebyshev step)");
     return spmm32(mode, brow, rec, n_nodes, ncols, X, R, invD, Zprev, Out, (float)ab, (float)cc, PROF_CHEB,
                   (cudaStream_t)stream);
+}
+
+/* slab variant: brow_win = &brow[row0] (n_local + 1 entries of the GLOBAL row pointer), bcol / Kval / Mblk start
+ * at the slab's first block; colmap[n_global_nodes] packs owner << 28 | index inside the owner's slab */
+extern "C" int ds_k32_pack_slab(const int32_t* brow_win, const int32_t* bcol_slab, int64_t n_local, int64_t nnzb_local,
+                                int64_t row0, const double* Kval_slab, const double* Mblk_slab, double shift,
+                                const uint32_t* colmap, void* rec, float* invD, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    DS_REQUIRE(rec && colmap, "ds_k32_pack_slab: null argument");
+    DS_CUDA(cudaMemsetAsync(reinterpret_cast<unsigned char*>(rec) + nnzb_local * S32_REC_BYTES, 0, 64, st));
+    return pack_k32(brow_win, bcol_slab, n_local, Kval_slab, Mblk_slab, shift, rec, invD, st, colmap, row0);
+}
+
+extern "C" int ds_spmm32_rowpart(int mode, const int32_t* brow_local, const void* rec, int64_t n_local, int ncols,
+                                 const float* const* Xparts_host, int world, int rank, const float* R, const float* invD,
+                                 const float* Zprev, float* Out, double ab, double cc, void* stream) {
+    DS_REQUIRE(mode >= 0 && mode <= 2, "ds_spmm32_rowpart: mode must be 0, 1 or 2");
+    return spmm32_rowpart(mode, brow_local, rec, n_local, ncols, Xparts_host, world, rank, R, invD, Zprev, Out, (float)ab,
+                          (float)cc, (cudaStream_t)stream);
+}
+
+/* peer-visible device memory: cudaMalloc + CUDA IPC handle (64 bytes) for the other ranks of the node */
+extern "C" int ds_peer_alloc(int64_t bytes, void** ptr, unsigned char* handle64) {
+    DS_REQUIRE(bytes > 0 && ptr && handle64, "ds_peer_alloc: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DS_CUDA(cudaMalloc(ptr, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    DS_CUDA(cudaIpcGetMemHandle(&h, *ptr));
+    memcpy(handle64, &h, 64);
+    return DS_OK;
+}
+extern "C" int ds_peer_open(const unsigned char* handle64, void** ptr) {
+    DS_REQUIRE(handle64 && ptr, "ds_peer_open: bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    DS_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return DS_OK;
+}
+extern "C" int ds_peer_close(void* ptr) {
+    if (ptr) DS_CUDA(cudaIpcCloseMemHandle(ptr));
+    return DS_OK;
+}
+extern "C" int ds_peer_free(void* ptr) {
+    if (ptr) DS_CUDA(cudaFree(ptr));
+    return DS_OK;
 }
 
 extern "C" int ds_pmg_restrict32(const int32_t* rptr, const int32_t* rlist, int64_t n_coarse, const float* res,

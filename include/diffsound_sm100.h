@@ -194,6 +194,26 @@ int ds_k32_pack(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, int64
 int ds_spmm32(int mode, const int32_t* brow, const void* rec, int64_t n_nodes, int ncols,
               const float* X, const float* R, const float* invD, const float* Zprev, float* Out,
               double ab, double cc, void* stream);
+/* Row-partitioned SpMM for one large mesh on several GPUs of a node: rank r owns
+ * a contiguous slab of node rows; the records of its slab carry column ids packed as
+ * owner << 28 | index inside the owner's slab (colmap), and the kernel gathers the dense block through
+ * Xparts_host[world] -- device pointers, valid in THIS process, of every rank's slab (the peers' come
+ * from ds_peer_open; loads cross NVLink).  No collective: the caller orders the ranks (barrier) between
+ * a step that writes a slab and the step that gathers it.  Replaces the all-gather + torch.sparse.mm a
+ * torch implementation of the reference's K @ U would need. */
+int ds_k32_pack_slab(const int32_t* brow_win, const int32_t* bcol_slab, int64_t n_local,
+                     int64_t nnzb_local, int64_t row0, const double* Kval_slab,
+                     const double* Mblk_slab, double shift, const uint32_t* colmap, void* rec,
+                     float* invD, void* stream);
+int ds_spmm32_rowpart(int mode, const int32_t* brow_local, const void* rec, int64_t n_local, int ncols,
+                      const float* const* Xparts_host, int world, int rank, const float* R,
+                      const float* invD, const float* Zprev, float* Out, double ab, double cc,
+                      void* stream);
+/* peer-visible device memory (cudaMalloc + 64-byte CUDA IPC handle) */
+int ds_peer_alloc(int64_t bytes, void** ptr, unsigned char* handle64);
+int ds_peer_open(const unsigned char* handle64, void** ptr);
+int ds_peer_close(void* ptr);
+int ds_peer_free(void* ptr);
 /* Quadratic -> linear coarsening (integer work).  tets: int32 [T*10] in the reference's local
  * order (mesh.py:139-154: corners at 0,2,4,9).  cid[n_nodes]: coarse id of each corner node
  * (ascending fine id) or -1; ds_pmg_coarse_count synchronises and returns n_coarse.
