@@ -1,7 +1,7 @@
 """Sharding of independent modal solves across ranks.
 
 Reference behaviour replaced: the sequential candidate loops of the experiment scripts
-(/root/reference/experiments/thickness_train.py:127-141, material_sync_train.py:95-118): every
+(experiments/thickness_train.py:127-141, experiments/material_sync_train.py:95-118 of the reference): every
 candidate builds its own mesh / model and is solved independently, so candidate i simply goes to rank
 i mod world; the only communication is one gather of the per-candidate results at the end.
 """
