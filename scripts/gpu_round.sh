@@ -1,0 +1,17 @@
+#!/bin/bash
+# One GPU-box pass: parity tests, bench, ncu launch list, ncu --set full of the top kernels.
+# usage (from the repo root on the GPU box): bash scripts/gpu_round.sh TAG
+TAG=${1:-rXX}
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/${TAG}_smi.txt
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?"
+tail -3 gpurun_out/${TAG}_pytest_gpu.log
+timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
+cat gpurun_out/${TAG}_bench.json
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/${TAG}_launches.csv \
+    python scripts/profile_step.py 32 1 > gpurun_out/${TAG}_launches.log 2>&1; echo "ncu list rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on \
+    -k regex:'k_spmm32|k_gram_sym|k_assemble_rows|k_eigval_grad_shape|k_block_gemm|k_spmm_dual|k_coarse|k_eigh' \
+    --launch-skip 40 --launch-count 24 -f -o gpurun_out/${TAG}_full python scripts/profile_step.py 32 1 > gpurun_out/${TAG}_full.log 2>&1; echo "ncu full rc=$?"
+ncu -i gpurun_out/${TAG}_full.ncu-rep --page raw --csv > gpurun_out/${TAG}_full_raw.csv 2>/dev/null
+ls -la gpurun_out
