@@ -62,7 +62,12 @@ SIGNATURES = {
                          f64p, f64p, C.POINTER(C.c_int64), ptr]),
     "ds_k32_record_bytes": (i64, [i64]),
     "ds_k32_pack": (cint, [i32p, i32p, i64, i64, f64p, f64p, dbl, ptr, f32p, ptr]),
-    "ds_spmm32": (cint, [cint, i32p, ptr, i64, cint, f32p, f32p, f32p, f32p, f32p, dbl, dbl, ptr]),
+    "ds_unique_rows3_count": (cint, [ptr, f32p, i64, C.POINTER(C.c_int64), ptr]),
+    "ds_unique_rows3_fill": (cint, [ptr, ptr, ptr, ptr]),
+    "ds_set_spmm32_variant": (None, [cint]),
+    "ds_spmm32": (cint, [cint, i32p, ptr, i64, cint, f32p, f32p, f32p, f32p, f32p, dbl, dbl, i32p, ptr]),
+    "ds_spmm32_chunk_count": (cint, [i64]),
+    "ds_spmm32_chunks": (cint, [i32p, i64, i32p, ptr]),
     "ds_k32_pack_slab": (cint, [i32p, i32p, i64, i64, i64, f64p, f64p, dbl, ptr, ptr, f32p, ptr]),
     "ds_spmm32_rowpart": (cint, [cint, i32p, ptr, i64, cint, C.POINTER(C.c_void_p), cint, cint, f32p, f32p, f32p, f32p,
                                  dbl, dbl, ptr]),

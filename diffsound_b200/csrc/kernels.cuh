@@ -25,7 +25,10 @@ struct ColIdx {
 enum { S32_MODE_PLAIN = 0, S32_MODE_RESID = 1, S32_MODE_CHEB = 2 };
 // Out = A X | R - A X | X + ab (X - Zprev) + cc invD (R - A X) on 40-byte block records; ncols in {16,32,48,64}
 int spmm32(int mode, const int32_t* brow, const void* rec, int64_t n_nodes, int ncols, const float* X, const float* R,
-           const float* invD, const float* Zprev, float* Out, float ab, float cc, int prof_cls, cudaStream_t st);
+           const float* invD, const float* Zprev, float* Out, float ab, float cc, int prof_cls, cudaStream_t st,
+           const int32_t* chunk_row = nullptr);
+// row chunks of the SpMM grid (one contiguous chunk per CTA, balanced by blocks + rows); chunk_row: >= 1024 ints
+int spmm32_chunks(const int32_t* brow, int64_t n_nodes, int32_t* chunk_row, cudaStream_t st);
 int pack_k32(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, const double* Kval, const double* Mblk,
              double shift, void* rec, float* invD, cudaStream_t st, const uint32_t* colmap = nullptr,
              int64_t row_offset = 0);
@@ -49,6 +52,7 @@ struct Level32 {
     int64_t n_nodes = 0, nnzb = 0;
     unsigned char* rec = nullptr;
     float* invD = nullptr;
+    int32_t* chunk_row = nullptr;
     double lmax = 0.0;
     int prof_cls = PROF_CHEB;
     int64_t launches = 0, cols = 0;          // SpMM launches and the sum of their column counts

@@ -243,7 +243,8 @@ struct Driver {
         for (int it = 0; it < iters; ++it) {
             if (it == iters - 1) DS_TRY(norms_of(a, n0));
             // b = a + 0 (a - a) + (-1) invD (0 - A a) = (I + invD A) a
-            DS_TRY(spmm32(S32_MODE_CHEB, L.brow, L.rec, L.n_nodes, w, a, zero_r, L.invD, a, b, 0.f, -1.f, L.prof_cls, st));
+            DS_TRY(spmm32(S32_MODE_CHEB, L.brow, L.rec, L.n_nodes, w, a, zero_r, L.invD, a, b, 0.f, -1.f, L.prof_cls, st,
+                          L.chunk_row));
             std::swap(a, b);
             L.launches++;
             L.cols += w;
@@ -268,7 +269,7 @@ struct Driver {
         const double sr = o.smooth_ratio > 1.0 ? o.smooth_ratio : 8.0;
         DS_TRY(fine.cheb(R32, w, nu, sr, true, &zc, &zp, st));                               // pre-smooth from zero
         DS_TRY(spmm32(S32_MODE_RESID, fine.brow, fine.rec, n_nodes, w, zc, R32, nullptr, nullptr, zp, 0.f, 0.f,
-                      PROF_CHEB, st));                                                       // zp = r - A z
+                      PROF_CHEB, st, fine.chunk_row));                                                       // zp = r - A z
         fine.launches++; fine.cols += w;
         DS_TRY(restrict32(cl->rptr, cl->rlist, cl->n_nodes, zp, w, RC32, st));
         float* cc = ZCa;

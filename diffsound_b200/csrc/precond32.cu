@@ -302,6 +302,268 @@ k_spmm32(const int32_t* __restrict__ brow, const uint2* __restrict__ rec, int64_
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// v2: L1-resident gather.  One 1024-thread CTA per SM sweeps a CONTIGUOUS chunk of node rows (chunks
+// balanced by blocks + rows), its 32 warps taking consecutive rows through a shared-memory ticket, so
+// the X rows gathered by the ~32 rows in flight overlap heavily and are served by the SM's L1
+// (no shared-memory staging: the whole 256 KB stays L1).  Everything that is read once -- block
+// records, R, Zprev -- is loaded with L1::no_allocate so it does not evict the gathered rows, and
+// is pulled into L2 64 rows ahead by bulk prefetches (cp.async.bulk.prefetch.L2), which takes the
+// DRAM latency off the warps.  The 3x3 block FMAs are packed (FFMA2: fma.rn.f32x2 with the K entry
+// broadcast), halving the dominant instruction count.
+// ---------------------------------------------------------------------------------------------
+constexpr int S32V_THREADS = 1024;
+constexpr int S32V_PF = 64;                  // rows of look-ahead of the L2 prefetch
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ uint2 ldg_na_u2(const uint2* p) {
+    uint2 v;
+    asm("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void ldg_v2u64(const float* p, u64& a, u64& b) {
+    asm("ld.global.nc.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
+}
+__device__ __forceinline__ u64 ldg_u64(const float* p) {
+    u64 a;
+    asm("ld.global.nc.u64 %0, [%1];" : "=l"(a) : "l"(p));
+    return a;
+}
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ void ffma2(u64& acc, float k, u64 x) {
+    u64 kk;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(kk) : "f"(k));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(kk), "l"(x));
+}
+__device__ __forceinline__ u64 fadd2(u64 a, u64 b) {
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+
+// the lane's CPT columns of one fp32 row as CPT/2 packed pairs (same ownership as ld_row)
+template <int LPR, int CPT>
+__device__ __forceinline__ void ld_row2(const float* row, int l, u64* out) {
+    ldg_v2u64(row + 4 * l, out[0], out[1]);
+    if constexpr (CPT == 6) out[2] = ldg_u64(row + 4 * LPR + 2 * l);
+    if constexpr (CPT == 8) ldg_v2u64(row + 4 * LPR + 4 * l, out[2], out[3]);
+}
+// streamed-once variants (R: read-only; Zprev: may alias Out)
+template <int LPR, int CPT>
+__device__ __forceinline__ void ld_row_stream(const float* row, int l, float* out) {
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+        : "=f"(out[0]), "=f"(out[1]), "=f"(out[2]), "=f"(out[3]) : "l"(row + 4 * l));
+    if constexpr (CPT == 6)
+        asm("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(out[4]), "=f"(out[5]) : "l"(row + 4 * LPR + 2 * l));
+    if constexpr (CPT == 8)
+        asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+            : "=f"(out[4]), "=f"(out[5]), "=f"(out[6]), "=f"(out[7]) : "l"(row + 4 * LPR + 4 * l));
+}
+template <int LPR, int CPT>
+__device__ __forceinline__ void ld_row_stream_plain(const float* row, int l, float* out) {
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(out[0]), "=f"(out[1]), "=f"(out[2]), "=f"(out[3]) : "l"(row + 4 * l) : "memory");
+    if constexpr (CPT == 6)
+        asm volatile("ld.global.L1::no_allocate.v2.f32 {%0,%1}, [%2];"
+                     : "=f"(out[4]), "=f"(out[5]) : "l"(row + 4 * LPR + 2 * l) : "memory");
+    if constexpr (CPT == 8)
+        asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(out[4]), "=f"(out[5]), "=f"(out[6]), "=f"(out[7]) : "l"(row + 4 * LPR + 4 * l) : "memory");
+}
+template <int LPR, int CPT>
+__device__ __forceinline__ void st_row_stream(float* row, int l, const float* v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(row + 4 * l), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                 "f"(v[3]) : "memory");
+    if constexpr (CPT == 6)
+        asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(row + 4 * LPR + 2 * l), "f"(v[4]), "f"(v[5])
+                     : "memory");
+    if constexpr (CPT == 8)
+        asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(row + 4 * LPR + 4 * l), "f"(v[4]),
+                     "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+
+// acc[c][:] += K[c][:] . X[3j..3j+2][cols of this lane] for one block record read from global
+template <int LPR, int CPT, bool PEER>
+__device__ __forceinline__ void block_fma_v(const uint2* __restrict__ r, const float* __restrict__ X,
+                                            const PeerTable& tab, int l, u64 (&acc)[3][CPT / 2]) {
+    constexpr int C = LPR * CPT, NP = CPT / 2;
+    const uint2 a0 = ldg_na_u2(r), a1 = ldg_na_u2(r + 1), a2 = ldg_na_u2(r + 2), a3 = ldg_na_u2(r + 3),
+                a4 = ldg_na_u2(r + 4);
+    const float* xr = node_rows<PEER, C>(X, tab, a4.y);
+    u64 x[3][NP];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) ld_row2<LPR, CPT>(xr + d * C, l, x[d]);
+    const float k[9] = {__uint_as_float(a0.x), __uint_as_float(a0.y), __uint_as_float(a1.x),
+                        __uint_as_float(a1.y), __uint_as_float(a2.x), __uint_as_float(a2.y),
+                        __uint_as_float(a3.x), __uint_as_float(a3.y), __uint_as_float(a4.x)};
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+#pragma unroll
+            for (int t = 0; t < NP; ++t) ffma2(acc[c][t], k[3 * c + d], x[d][t]);
+}
+
+template <int LPR, int CPT, bool PEER>
+__device__ __forceinline__ void block_fma2_v(const uint2* __restrict__ ra, const uint2* __restrict__ rb,
+                                             const float* __restrict__ X, const PeerTable& tab, int l,
+                                             u64 (&acc)[3][CPT / 2]) {
+    constexpr int C = LPR * CPT, NP = CPT / 2;
+    const uint2 a4 = ldg_na_u2(ra + 4), b4 = ldg_na_u2(rb + 4);
+    const uint2 a0 = ldg_na_u2(ra), a1 = ldg_na_u2(ra + 1), a2 = ldg_na_u2(ra + 2), a3 = ldg_na_u2(ra + 3);
+    const uint2 b0 = ldg_na_u2(rb), b1 = ldg_na_u2(rb + 1), b2 = ldg_na_u2(rb + 2), b3 = ldg_na_u2(rb + 3);
+    const float* xa = node_rows<PEER, C>(X, tab, a4.y);
+    const float* xb = node_rows<PEER, C>(X, tab, b4.y);
+    u64 x[3][NP], y[3][NP];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        ld_row2<LPR, CPT>(xa + d * C, l, x[d]);
+        ld_row2<LPR, CPT>(xb + d * C, l, y[d]);
+    }
+    {
+        const float k[9] = {__uint_as_float(a0.x), __uint_as_float(a0.y), __uint_as_float(a1.x),
+                            __uint_as_float(a1.y), __uint_as_float(a2.x), __uint_as_float(a2.y),
+                            __uint_as_float(a3.x), __uint_as_float(a3.y), __uint_as_float(a4.x)};
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+#pragma unroll
+                for (int t = 0; t < NP; ++t) ffma2(acc[c][t], k[3 * c + d], x[d][t]);
+    }
+    {
+        const float k[9] = {__uint_as_float(b0.x), __uint_as_float(b0.y), __uint_as_float(b1.x),
+                            __uint_as_float(b1.y), __uint_as_float(b2.x), __uint_as_float(b2.y),
+                            __uint_as_float(b3.x), __uint_as_float(b3.y), __uint_as_float(b4.x)};
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+#pragma unroll
+                for (int t = 0; t < NP; ++t) ffma2(acc[c][t], k[3 * c + d], y[d][t]);
+    }
+}
+
+template <int LPR, int CPT, int MODE, bool PEER>
+__global__ void __launch_bounds__(S32V_THREADS, 1)
+k_spmm32v(const int32_t* __restrict__ brow, const uint2* __restrict__ rec, const int32_t* __restrict__ chunk_row,
+          const float* __restrict__ X, const float* __restrict__ R, const float* __restrict__ invD,
+          const float* Zprev, float* Out, float ab, float cc, const __grid_constant__ PeerTable tab) {
+    constexpr int C = LPR * CPT;
+    constexpr int NG = 32 / LPR;
+    constexpr int NP = CPT / 2;
+    __shared__ int s_ticket;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane / LPR, l = lane % LPR;
+    const int r_lo = chunk_row[blockIdx.x], r_hi = chunk_row[blockIdx.x + 1];
+    if (tid == 0) s_ticket = 0;
+
+    // pull what row r streams exactly once into L2 (lane 0 of the calling warp)
+    auto prefetch_row = [&](int r) {
+        const int64_t b0 = brow[r], b1 = brow[r + 1];
+        if (b1 > b0) {
+            const int64_t lo = (b0 * S32_REC_BYTES) & ~int64_t(15);
+            const int64_t hi = (b1 * S32_REC_BYTES + 15) & ~int64_t(15);
+            prefetch_l2_bulk(reinterpret_cast<const unsigned char*>(rec) + lo, (uint32_t)(hi - lo));
+        }
+        const int64_t ob = (int64_t)3 * r * C;
+        if (MODE != S32_PLAIN) prefetch_l2_bulk(R + ob, 3 * C * 4);
+        if (MODE == S32_CHEB) {
+            prefetch_l2_bulk(Zprev + ob, 3 * C * 4);
+            prefetch_l2(invD + 9 * (int64_t)r);
+        }
+        if ((r & 15) == 0) prefetch_l2(brow + min(r + 2 * S32V_PF, r_hi));      // the row pointers themselves
+    };
+    if (lane == 0) {
+        if (r_lo + warp < r_hi) prefetch_row(r_lo + warp);
+        if (r_lo + 32 + warp < r_hi) prefetch_row(r_lo + 32 + warp);
+    }
+    __syncthreads();
+
+    for (;;) {
+        int rr = 0;
+        if (lane == 0) rr = atomicAdd(&s_ticket, 1);
+        rr = __shfl_sync(0xffffffffu, rr, 0);
+        const int row = r_lo + rr;
+        if (row >= r_hi) break;
+        if (lane == 0 && row + S32V_PF < r_hi) prefetch_row(row + S32V_PF);
+        const int rb0 = brow[row], rb1 = brow[row + 1];
+        u64 acc[3][NP];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int t = 0; t < NP; ++t) acc[c][t] = 0ull;
+        int p = rb0 + g;
+        for (; p + NG < rb1; p += 2 * NG)
+            block_fma2_v<LPR, CPT, PEER>(rec + (int64_t)5 * p, rec + (int64_t)5 * (p + NG), X, tab, l, acc);
+        if (p < rb1) block_fma_v<LPR, CPT, PEER>(rec + (int64_t)5 * p, X, tab, l, acc);
+#pragma unroll
+        for (int off = LPR; off < 32; off <<= 1)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int t = 0; t < NP; ++t) acc[c][t] = fadd2(acc[c][t], __shfl_xor_sync(0xffffffffu, acc[c][t], off));
+        if (g < 3) {
+            const int64_t o = ((int64_t)3 * row + g) * C;          // output row of this lane group
+            float a[3][CPT];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int t = 0; t < NP; ++t) unpack2(acc[c][t], a[c][2 * t], a[c][2 * t + 1]);
+            float v[CPT];
+            if (MODE == S32_PLAIN) {
+#pragma unroll
+                for (int t = 0; t < CPT; ++t) v[t] = g == 0 ? a[0][t] : (g == 1 ? a[1][t] : a[2][t]);
+            } else if (MODE == S32_RESID) {
+                float rv[CPT];
+                ld_row_stream<LPR, CPT>(R + o, l, rv);
+#pragma unroll
+                for (int t = 0; t < CPT; ++t) v[t] = rv[t] - (g == 0 ? a[0][t] : (g == 1 ? a[1][t] : a[2][t]));
+            } else {
+                const float d0 = __ldg(invD + 9 * (int64_t)row + 3 * g), d1 = __ldg(invD + 9 * (int64_t)row + 3 * g + 1),
+                            d2 = __ldg(invD + 9 * (int64_t)row + 3 * g + 2);
+                float r0v[CPT], r1v[CPT], r2v[CPT], z[CPT], zp[CPT];
+                const int64_t ob = (int64_t)3 * row * C;
+                ld_row_stream<LPR, CPT>(R + ob, l, r0v);
+                ld_row_stream<LPR, CPT>(R + ob + C, l, r1v);
+                ld_row_stream<LPR, CPT>(R + ob + 2 * C, l, r2v);
+                ld_row<LPR, CPT>(X + o, l, z);
+                ld_row_stream_plain<LPR, CPT>(Zprev + o, l, zp);
+#pragma unroll
+                for (int t = 0; t < CPT; ++t) {
+                    const float dr = d0 * (r0v[t] - a[0][t]) + d1 * (r1v[t] - a[1][t]) + d2 * (r2v[t] - a[2][t]);
+                    v[t] = z[t] + ab * (z[t] - zp[t]) + cc * dr;
+                }
+            }
+            st_row_stream<LPR, CPT>(Out + o, l, v);
+        }
+    }
+}
+
+// chunk_row[c] = first row of chunk c: chunks of equal weight w(r) = brow[r] + 15 r (blocks + per-row overhead)
+__global__ void k_chunk_rows(const int32_t* __restrict__ brow, int n_nodes, int nchunks, int32_t* __restrict__ chunk_row) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > nchunks) return;
+    if (c == nchunks) { chunk_row[c] = n_nodes; return; }
+    const int64_t total = (int64_t)(brow[n_nodes] - brow[0]) + 15 * (int64_t)n_nodes;
+    const int64_t target = total * c / nchunks;
+    int lo = 0, hi = n_nodes;                    // first r with w(r) >= target
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((int64_t)(brow[mid] - brow[0]) + 15 * (int64_t)mid < target) lo = mid + 1; else hi = mid;
+    }
+    chunk_row[c] = lo;
+}
+
 // records + block-Jacobi inverse from the FP64 matrix: one warp per node row
 // colmap (optional): record column id = colmap[global column]; row_offset: global id of local row 0
 __global__ void __launch_bounds__(256)
@@ -500,46 +762,105 @@ static int s32_grid(int64_t n_nodes) {
     return (int)(tiles < g ? tiles : g);
 }
 
+static int g_spmm32_variant = 2;      // 1: TMA-staged tiles (k_spmm32), 2: L1-resident gather (k_spmm32v)
+
+static int s32v_grid(int64_t n_nodes) {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int64_t want = ceil_div(n_nodes, 32);
+    return (int)(want < sms ? want : sms);
+}
+
+int spmm32_chunks(const int32_t* brow, int64_t n_nodes, int32_t* chunk_row, cudaStream_t st) {
+    const int nchunks = s32v_grid(n_nodes);
+    k_chunk_rows<<<ceil_div(nchunks + 1, 128), 128, 0, st>>>(brow, (int)n_nodes, nchunks, chunk_row);
+    DS_LAUNCH_CHECK();
+    return DS_OK;
+}
+
 template <int LPR, int CPT, bool PEER>
-static int launch_spmm32(int mode, const int32_t* brow, const void* rec, int64_t n_nodes, const float* X, const float* R,
-                         const float* invD, const float* Zprev, float* Out, float ab, float cc, const PeerTable& tab,
-                         cudaStream_t st) {
-    const int grid = s32_grid(n_nodes);
+static int launch_spmm32(int mode, const int32_t* brow, const void* rec, int64_t n_nodes, const int32_t* chunk_row,
+                         const float* X, const float* R, const float* invD, const float* Zprev, float* Out, float ab,
+                         float cc, const PeerTable& tab, cudaStream_t st) {
+    if (g_spmm32_variant == 1) {
+        const int grid = s32_grid(n_nodes);
+        auto go = [&](auto kern) -> int {
+            kern<<<grid, S32_THREADS, S32_SMEM, st>>>(brow, reinterpret_cast<const uint2*>(rec), n_nodes, X, R, invD,
+                                                      Zprev, Out, ab, cc, tab);
+            DS_LAUNCH_CHECK();
+            return DS_OK;
+        };
+        switch (mode) {
+            case S32_PLAIN: return go(k_spmm32<LPR, CPT, S32_PLAIN, PEER>);
+            case S32_RESID: return go(k_spmm32<LPR, CPT, S32_RESID, PEER>);
+            default: return go(k_spmm32<LPR, CPT, S32_CHEB, PEER>);
+        }
+    }
+    DS_REQUIRE(chunk_row != nullptr, "spmm32: missing row chunks");
+    const int grid = s32v_grid(n_nodes);
     auto go = [&](auto kern) -> int {
-        kern<<<grid, S32_THREADS, S32_SMEM, st>>>(brow, reinterpret_cast<const uint2*>(rec), n_nodes, X, R, invD, Zprev,
-                                                  Out, ab, cc, tab);
+        static bool carved = false;          // per instantiation: all of the SM's 256 KB as L1
+        if (!carved) {
+            DS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
+            carved = true;
+        }
+        kern<<<grid, S32V_THREADS, 0, st>>>(brow, reinterpret_cast<const uint2*>(rec), chunk_row, X, R, invD, Zprev, Out,
+                                            ab, cc, tab);
         DS_LAUNCH_CHECK();
         return DS_OK;
     };
     switch (mode) {
-        case S32_PLAIN: return go(k_spmm32<LPR, CPT, S32_PLAIN, PEER>);
-        case S32_RESID: return go(k_spmm32<LPR, CPT, S32_RESID, PEER>);
-        default: return go(k_spmm32<LPR, CPT, S32_CHEB, PEER>);
+        case S32_PLAIN: return go(k_spmm32v<LPR, CPT, S32_PLAIN, PEER>);
+        case S32_RESID: return go(k_spmm32v<LPR, CPT, S32_RESID, PEER>);
+        default: return go(k_spmm32v<LPR, CPT, S32_CHEB, PEER>);
     }
 }
 
 template <bool PEER>
-static int dispatch_spmm32(int mode, const int32_t* brow, const void* rec, int64_t n_nodes, int ncols, const float* X,
-                           const float* R, const float* invD, const float* Zprev, float* Out, float ab, float cc,
-                           const PeerTable& tab, cudaStream_t st) {
+static int dispatch_spmm32(int mode, const int32_t* brow, const void* rec, int64_t n_nodes, const int32_t* chunk_row,
+                           int ncols, const float* X, const float* R, const float* invD, const float* Zprev, float* Out,
+                           float ab, float cc, const PeerTable& tab, cudaStream_t st) {
     switch (ncols) {
-        case 16: return launch_spmm32<4, 4, PEER>(mode, brow, rec, n_nodes, X, R, invD, Zprev, Out, ab, cc, tab, st);
-        case 32: return launch_spmm32<8, 4, PEER>(mode, brow, rec, n_nodes, X, R, invD, Zprev, Out, ab, cc, tab, st);
-        case 48: return launch_spmm32<8, 6, PEER>(mode, brow, rec, n_nodes, X, R, invD, Zprev, Out, ab, cc, tab, st);
-        case 64: return launch_spmm32<8, 8, PEER>(mode, brow, rec, n_nodes, X, R, invD, Zprev, Out, ab, cc, tab, st);
+        case 16: return launch_spmm32<4, 4, PEER>(mode, brow, rec, n_nodes, chunk_row, X, R, invD, Zprev, Out, ab, cc, tab, st);
+        case 32: return launch_spmm32<8, 4, PEER>(mode, brow, rec, n_nodes, chunk_row, X, R, invD, Zprev, Out, ab, cc, tab, st);
+        case 48: return launch_spmm32<8, 6, PEER>(mode, brow, rec, n_nodes, chunk_row, X, R, invD, Zprev, Out, ab, cc, tab, st);
+        case 64: return launch_spmm32<8, 8, PEER>(mode, brow, rec, n_nodes, chunk_row, X, R, invD, Zprev, Out, ab, cc, tab, st);
         default: set_error("spmm32: ncols=%d must be 16, 32, 48 or 64", ncols); return DS_ERR_ARG;
     }
 }
 
+// chunk_row: s32v_grid(n_nodes) + 1 row offsets from spmm32_chunks (NULL: built into a stream-ordered temporary)
+struct ChunkTmp {
+    int32_t* p = nullptr;
+    cudaStream_t st;
+    int get(const int32_t* brow, int64_t n_nodes, const int32_t* given, cudaStream_t s, const int32_t** out) {
+        st = s;
+        if (given || g_spmm32_variant == 1) { *out = given; return DS_OK; }
+        DS_CUDA(cudaMallocAsync(&p, sizeof(int32_t) * (s32v_grid(n_nodes) + 1), s));
+        DS_TRY(spmm32_chunks(brow, n_nodes, p, s));
+        *out = p;
+        return DS_OK;
+    }
+    ~ChunkTmp() { if (p) cudaFreeAsync(p, st); }
+};
+
 int spmm32(int mode, const int32_t* brow, const void* rec, int64_t n_nodes, int ncols, const float* X, const float* R,
-           const float* invD, const float* Zprev, float* Out, float ab, float cc, int prof_cls, cudaStream_t st) {
+           const float* invD, const float* Zprev, float* Out, float ab, float cc, int prof_cls, cudaStream_t st,
+           const int32_t* chunk_row) {
     DS_REQUIRE(brow && rec && X && Out, "spmm32: null argument");
     DS_REQUIRE(X != Out, "spmm32: the gathered block must not alias the output");
     DS_REQUIRE(mode == S32_PLAIN || R, "spmm32: this mode needs R");
     DS_REQUIRE(mode != S32_CHEB || (invD && Zprev), "spmm32: Chebyshev mode needs invD and Zprev");
+    ChunkTmp tmp;
+    const int32_t* chunks = nullptr;
+    DS_TRY(tmp.get(brow, n_nodes, chunk_row, st, &chunks));
     ProfScope prof(prof_cls, st);
     PeerTable none = {};
-    return dispatch_spmm32<false>(mode, brow, rec, n_nodes, ncols, X, R, invD, Zprev, Out, ab, cc, none, st);
+    return dispatch_spmm32<false>(mode, brow, rec, n_nodes, chunks, ncols, X, R, invD, Zprev, Out, ab, cc, none, st);
 }
 
 // row-partitioned: Xparts[r] = base of rank r's slab of the gathered block (device pointers valid in this
@@ -557,8 +878,11 @@ int spmm32_rowpart(int mode, const int32_t* brow, const void* rec, int64_t n_loc
         tab.p[r] = Xparts[r];
     }
     DS_REQUIRE(tab.p[rank] != Out, "spmm32_rowpart: the gathered block must not alias the output");
+    ChunkTmp tmp;
+    const int32_t* chunks = nullptr;
+    DS_TRY(tmp.get(brow, n_local, nullptr, st, &chunks));
     ProfScope prof(PROF_CHEB, st);
-    return dispatch_spmm32<true>(mode, brow, rec, n_local, ncols, tab.p[rank], R, invD, Zprev, Out, ab, cc, tab, st);
+    return dispatch_spmm32<true>(mode, brow, rec, n_local, chunks, ncols, tab.p[rank], R, invD, Zprev, Out, ab, cc, tab, st);
 }
 
 int pack_k32(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, const double* Kval, const double* Mblk,
@@ -648,7 +972,7 @@ int colnorm2_f32(const float* V, int w, int64_t n, double* partial, int ctas, cu
 // ---- Level32 -----------------------------------------------------------------------------------
 size_t Level32::bytes(int64_t n_nodes, int64_t nnzb) {
     auto al = [](size_t b) { return ((b + 255) & ~size_t(255)) + 256; };
-    return al((size_t)nnzb * S32_REC_BYTES + 64) + al((size_t)n_nodes * 9 * sizeof(float));
+    return al((size_t)nnzb * S32_REC_BYTES + 64) + al((size_t)n_nodes * 9 * sizeof(float)) + al(1024 * sizeof(int32_t));
 }
 
 int Level32::setup(Arena& a, const int32_t* brow_, const int32_t* bcol, int64_t n_nodes_, int64_t nnzb_,
@@ -658,7 +982,10 @@ int Level32::setup(Arena& a, const int32_t* brow_, const int32_t* bcol, int64_t 
     nnzb = nnzb_;
     rec = a.take<unsigned char>((size_t)nnzb * S32_REC_BYTES + 64);
     invD = a.take<float>((size_t)n_nodes * 9);
-    DS_REQUIRE(rec && invD, "Level32: workspace arena exhausted");
+    chunk_row = a.take<int32_t>(1024);
+    DS_REQUIRE(rec && invD && chunk_row, "Level32: workspace arena exhausted");
+    DS_REQUIRE(s32v_grid(n_nodes) < 1024, "Level32: more than 1023 SMs");
+    DS_TRY(spmm32_chunks(brow, n_nodes, chunk_row, st));
     DS_CUDA(cudaMemsetAsync(rec + (size_t)nnzb * S32_REC_BYTES, 0, 64, st));    // TMA reads up to 8 bytes past the end
     return pack_k32(brow, bcol, n_nodes, Kval, Mblk, shift, rec, invD, st);
 }
@@ -676,7 +1003,7 @@ int Level32::cheb(const float* r, int ncols, int degree, double ratio, bool from
         DS_TRY(jacobi32(invD, r, n_nodes, ncols, (float)(1.0 / theta), *zc, st));
     } else {
         DS_TRY(spmm32(S32_CHEB, brow, rec, n_nodes, ncols, *zc, r, invD, *zc, *zp, 0.f, (float)(1.0 / theta), prof_cls,
-                      st));
+                      st, chunk_row));
         std::swap(*zc, *zp);
         ++launches;
         cols += ncols;
@@ -687,7 +1014,7 @@ int Level32::cheb(const float* r, int ncols, int degree, double ratio, bool from
         const float cc = (float)(2.0 * rho_new / delta);
         // z_{k+1} = z_k + ab (z_k - z_{k-1}) + cc invD (r - A z_k); for k == 1 from zero, z_0 = 0
         if (k == 1 && from_zero) DS_CUDA(cudaMemsetAsync(*zp, 0, sizeof(float) * 3 * (size_t)n_nodes * ncols, st));
-        DS_TRY(spmm32(S32_CHEB, brow, rec, n_nodes, ncols, *zc, r, invD, *zp, *zp, ab, cc, prof_cls, st));
+        DS_TRY(spmm32(S32_CHEB, brow, rec, n_nodes, ncols, *zc, r, invD, *zp, *zp, ab, cc, prof_cls, st, chunk_row));
         std::swap(*zc, *zp);
         rho = rho_new;
         ++launches;
@@ -699,6 +1026,8 @@ int Level32::cheb(const float* r, int ncols, int degree, double ratio, bool from
 }  // namespace ds
 
 using namespace ds;
+
+extern "C" void ds_set_spmm32_variant(int v) { g_spmm32_variant = v == 1 ? 1 : 2; }
 
 extern "C" int64_t ds_k32_record_bytes(int64_t nnzb) { return nnzb * S32_REC_BYTES + 64; }
 
@@ -712,10 +1041,17 @@ extern "C" int ds_k32_pack(const int32_t* brow, const int32_t* bcol, int64_t n_n
 
 extern "C" int ds_spmm32(int mode, const int32_t* brow, const void* rec, int64_t n_nodes, int ncols, const float* X,
                          const float* R, const float* invD, const float* Zprev, float* Out, double ab, double cc,
-                         void* stream) {
+                         const int32_t* chunk_row, void* stream) {
     DS_REQUIRE(mode >= 0 && mode <= 2, "ds_spmm32: mode must be 0 (A X), 1 (R - A X) or 2 (Chebyshev step)");
     return spmm32(mode, brow, rec, n_nodes, ncols, X, R, invD, Zprev, Out, (float)ab, (float)cc, PROF_CHEB,
-                  (cudaStream_t)stream);
+                  (cudaStream_t)stream, chunk_row);
+}
+
+extern "C" int ds_spmm32_chunk_count(int64_t n_nodes) { return s32v_grid(n_nodes); }
+
+extern "C" int ds_spmm32_chunks(const int32_t* brow, int64_t n_nodes, int32_t* chunk_row, void* stream) {
+    DS_REQUIRE(brow && chunk_row && n_nodes > 0, "ds_spmm32_chunks: bad argument");
+    return spmm32_chunks(brow, n_nodes, chunk_row, (cudaStream_t)stream);
 }
 
 /* slab variant: brow_win = &brow[row0] (n_local + 1 entries of the GLOBAL row pointer), bcol / Kval / Mblk start

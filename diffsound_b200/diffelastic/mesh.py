@@ -18,6 +18,8 @@ import struct
 import numpy as np
 import torch
 
+from .. import native
+
 CORNER_LOCAL = {1: (0, 1, 2, 3), 2: (0, 2, 4, 9), 3: (0, 3, 6, 16)}
 
 
@@ -184,12 +186,10 @@ class TetMesh:
 
     def remove_duplicate_vertices(self):
         """Renumber nodes by lexicographic coordinate order; representative = smallest original
-        index (mesh.py:162-179: torch.unique(dim=0) + scatter-min)."""
-        _, inv = torch.unique(self.vertices.detach(), dim=0, return_inverse=True)
-        n_new = int(inv.max()) + 1 if inv.numel() else 0
-        src = torch.arange(self.vertices.shape[0], device=inv.device)
-        first = torch.full((n_new,), self.vertices.shape[0], dtype=torch.long, device=inv.device)
-        first.scatter_reduce_(0, inv, src, "amin")
+        index (mesh.py:162-179: torch.unique(dim=0) + scatter-min).  The sort runs in csrc/mesh.cu."""
+        if not self.vertices.is_cuda:
+            raise RuntimeError("diffsound_b200: mesh tensors must live on a CUDA device (there is no CPU path)")
+        inv, first = native.unique_rows3(self.vertices.detach().to(torch.float32).contiguous())
         self.tets = inv[self.tets]
         self.vertices = self.vertices[first]
         if hasattr(self, "_transform_matrix"):

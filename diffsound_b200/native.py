@@ -70,6 +70,26 @@ def workspace(device=None):
     return _ws_cache[dev]
 
 
+def unique_rows3(rows_f32):
+    """(inverse, first) of the distinct rows of an (N, 3) fp32 array in ascending lexicographic order
+    (ds_unique_rows3_*): what torch.unique(dim=0, return_inverse=True) + scatter(min) give the reference."""
+    lib = _lib.load()
+    assert rows_f32.dtype == torch.float32 and rows_f32.dim() == 2 and rows_f32.shape[1] == 3
+    dev = rows_f32.device
+    ws = workspace(dev)
+    N = rows_f32.shape[0]
+    if N == 0:
+        e = torch.empty(0, dtype=torch.int64, device=dev)
+        return e, e.clone()
+    nu = C.c_int64(0)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ds_unique_rows3_count(ws.handle, _p(rows_f32), N, C.byref(nu), _stream()), "ds_unique_rows3_count")
+        inverse = torch.empty(N, dtype=torch.int64, device=dev)
+        first = torch.empty(int(nu.value), dtype=torch.int64, device=dev)
+        _lib.check(lib.ds_unique_rows3_fill(ws.handle, _p(inverse), _p(first), _stream()), "ds_unique_rows3_fill")
+    return inverse, first
+
+
 class Pattern:
     """Block-CSR sparsity pattern of K and M plus per-slot contributor lists."""
 
@@ -302,6 +322,19 @@ def k32_pack(pattern, Kval, Mblk=None, shift=0.0):
     return rec, invD
 
 
+def spmm32_chunks(pattern):
+    """Row chunks of the SpMM grid (ds_spmm32_chunks), cached on the pattern."""
+    ch = getattr(pattern, "_chunks32", None)
+    if ch is None:
+        lib = _lib.load()
+        dev = pattern.brow.device
+        with torch.cuda.device(dev):
+            ch = torch.empty(lib.ds_spmm32_chunk_count(pattern.n_nodes) + 1, dtype=torch.int32, device=dev)
+            _lib.check(lib.ds_spmm32_chunks(_p(pattern.brow), pattern.n_nodes, _p(ch), _stream()), "ds_spmm32_chunks")
+        pattern._chunks32 = ch
+    return ch
+
+
 def spmm32(pattern, rec, X, mode=0, R=None, invD=None, Zprev=None, ab=0.0, cc=0.0, out=None):
     """mode 0: A X; 1: R - A X; 2: X + ab (X - Zprev) + cc invD (R - A X).  fp32 (n, ncols) contiguous."""
     lib = _lib.load()
@@ -310,7 +343,8 @@ def spmm32(pattern, rec, X, mode=0, R=None, invD=None, Zprev=None, ab=0.0, cc=0.
         out = torch.empty_like(X)
     with torch.cuda.device(X.device):
         _lib.check(lib.ds_spmm32(int(mode), _p(pattern.brow), _p(rec), pattern.n_nodes, X.shape[1], _p(X), _p(R),
-                                 _p(invD), _p(Zprev), _p(out), float(ab), float(cc), _stream()), "ds_spmm32")
+                                 _p(invD), _p(Zprev), _p(out), float(ab), float(cc), _p(spmm32_chunks(pattern)),
+                                 _stream()), "ds_spmm32")
     return out
 
 

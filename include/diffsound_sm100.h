@@ -180,6 +180,16 @@ int ds_lobpcg(ds_workspace* ws, const int32_t* brow, const int32_t* bcol, int64_
               double* X, int m, const ds_lobpcg_opts* opts, double* lambda_out, double* resid_out,
               int64_t* stats_host, void* stream);
 
+/* ---- mesh promotion: node numbering -----------------------------------------------------------
+ * Replaces torch.unique(vertices, dim=0, return_inverse=True) + scatter(min) in
+ * TetMesh.remove_duplicate_vertices (diffelastic/mesh.py:162-179), called by to_high_order
+ * (mesh.py:101-160) on the V + 6T candidate nodes and by import_from_file (mesh.py:196).
+ * rows: device fp32 [N x 3].  count: sorts and returns the number of distinct rows (one stream sync);
+ * fill: inverse[N] (int64, id of every input row = rank of its coordinates in ascending (x, y, z)
+ * order) and first[n_unique] (int64, smallest input index of every group).  -0.0 == +0.0. */
+int ds_unique_rows3_count(ds_workspace* ws, const float* rows, int64_t N, int64_t* n_unique_host, void* stream);
+int ds_unique_rows3_fill(ds_workspace* ws, int64_t* inverse, int64_t* first, void* stream);
+
 /* ---- FP32 preconditioner pieces (exported for tests and for callers that build their own cycle) ---
  * No reference counterpart: the reference factorises K - sigma M with SuperLU on the CPU
  * (diff_model.py:356-358).  rec: ds_k32_record_bytes(nnzb) bytes, 16-byte aligned, one 40-byte
@@ -193,7 +203,15 @@ int ds_k32_pack(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, int64
                 void* stream);
 int ds_spmm32(int mode, const int32_t* brow, const void* rec, int64_t n_nodes, int ncols,
               const float* X, const float* R, const float* invD, const float* Zprev, float* Out,
-              double ab, double cc, void* stream);
+              double ab, double cc, const int32_t* chunk_row, void* stream);
+/* Row chunks of the SpMM grid: one 1024-thread CTA per SM sweeps a contiguous chunk of node rows so that
+ * the gathered rows of X stay in that SM's L1; chunk_row[ds_spmm32_chunk_count(n_nodes) + 1] (device)
+ * holds the first row of every chunk, balanced by blocks + rows.  ds_spmm32 accepts chunk_row = NULL and
+ * then builds the chunks into a stream-ordered temporary on every call. */
+int ds_spmm32_chunk_count(int64_t n_nodes);
+int ds_spmm32_chunks(const int32_t* brow, int64_t n_nodes, int32_t* chunk_row, void* stream);
+/* tuning hook: 1 = TMA-staged tile kernel (k_spmm32), 2 = L1-resident gather kernel (k_spmm32v, default) */
+void ds_set_spmm32_variant(int variant);
 /* Row-partitioned SpMM for one large mesh on several GPUs of a node: rank r owns
  * a contiguous slab of node rows; the records of its slab carry column ids packed as
  * owner << 28 | index inside the owner's slab (colmap), and the kernel gathers the dense block through

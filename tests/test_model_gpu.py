@@ -34,6 +34,42 @@ def _obj(meshes, name, order, g, requires_grad=True):
     return leaf, obj
 
 
+@pytest.mark.parametrize("name", ["cube2", "cube3", "grid16", "bowl"])
+def test_tetmesh_promotion_matches_reference(meshes, name):
+    """P1 -> P2 promotion: node numbering by the native row sort (csrc/mesh.cu) is bit-identical to the
+    reference's torch.unique(dim=0) numbering (mesh.py:101-179)."""
+    from diffsound_b200.diffelastic.mesh import TetMesh
+    g = golden(f"modal_{name}_o2")
+    v, t = meshes[name]
+    leaf = torch.tensor(v, device=DEV, requires_grad=True)
+    m2 = TetMesh(leaf, torch.tensor(t, device=DEV)).to_high_order(2)
+    assert m2.order == 2 and m2.tets.shape[1] == 10 and m2.tets.dtype == torch.int64
+    assert _sha(m2.vertices.detach().cpu().numpy()) == str(g["pverts_sha"])
+    assert _sha(m2.tets.cpu().numpy()) == str(g["ptets_sha"])
+    # autograd link to the caller's vertices survives the renumbering (mesh.py:178)
+    m2.vertices.sum().backward()
+    assert leaf.grad is not None and leaf.grad.shape == leaf.shape
+    A = m2.transform_matrix
+    assert A.shape == (t.shape[0], 3, 3) and A.dtype == torch.float32
+
+
+def test_unique_rows3_edge_cases():
+    """duplicates, -0.0 == +0.0, negative coordinates, single row; against torch.unique on the host."""
+    from diffsound_b200 import native
+    gen = torch.Generator().manual_seed(3)
+    base = torch.randint(-3, 4, (5000, 3), generator=gen).float() * 0.25
+    base[::7, 1] = -0.0
+    base[1::7, 1] = 0.0
+    for rows in (base, base[:1], torch.tensor([[1.0, 2.0, 3.0]] * 4)):
+        inv, first = native.unique_rows3(rows.to(DEV).contiguous())
+        u, ref_inv = torch.unique(rows, dim=0, return_inverse=True)
+        assert first.numel() == u.shape[0]
+        assert torch.equal(inv.cpu(), ref_inv)
+        ref_first = torch.full((u.shape[0],), rows.shape[0], dtype=torch.long)
+        ref_first.scatter_reduce_(0, ref_inv, torch.arange(rows.shape[0]), "amin")
+        assert torch.equal(first.cpu(), ref_first)
+
+
 @pytest.mark.parametrize("name,order", [("cube2", 1), ("cube2", 2), ("cube3", 1), ("cube3", 2), ("grid16", 1),
                                         ("grid16", 2), ("bowl", 1), ("bowl", 2)])
 def test_diffsoundobj_matches_reference(meshes, name, order):
