@@ -232,7 +232,9 @@ def main():
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = lib.ds_launch_count()
-    with native.prof() as pf:
+    # only the dominant kernel class is bracketed by events inside the timed region (the roofline's launch time);
+    # the per-class breakdown comes from a second, untimed pass below
+    with native.prof(classes=["cheb_step"]) as pf:
         e0.record()
         for _ in range(args.steps):
             vals, grad = solve(obj, leaf)
@@ -242,6 +244,11 @@ def main():
     launches = int(lib.ds_launch_count() - launches0)
     sampler.stop_flag = True
     ms = e0.elapsed_time(e1)
+    with native.prof() as pf_all:
+        for _ in range(2):
+            solve(obj, leaf)
+        torch.cuda.synchronize()
+    prof_all = pf_all.read()
     tms = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -250,17 +257,22 @@ def main():
     value = world * args.steps / (ms_max * 1e-3)
     stats = obj.eig_stats
 
-    # ---- end to end through the public API from host buffers
+    # ---- end to end through the public API from host buffers (a new model per step, as the sweeps build one
+    # per candidate); one untimed pass first so that the caching allocator owns the blocks a second model needs
     e2e_steps = max(2, min(args.steps, 3))
-    barrier()
-    t_e2e = time.perf_counter()
-    for _ in range(e2e_steps):
+
+    def e2e_step():
         lf, ob = build(v_host, t_host)
         ob.eigen_decomposition()
         vv = ob.get_vals()
         (vv[:, 0] * (1.0 / ob.eigenvalues).float()).sum().backward()
-        lam_h = ob.eigenvalues.cpu()
-        grad_h = lf.grad.cpu()
+        return ob.eigenvalues.cpu(), lf.grad.cpu()
+
+    lam_h, grad_h = e2e_step()
+    barrier()
+    t_e2e = time.perf_counter()
+    for _ in range(e2e_steps):
+        lam_h, grad_h = e2e_step()
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t_e2e], device=dev, dtype=torch.float64)
     if world > 1:
@@ -312,7 +324,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps},
             "gpu_launches": launches, "clocks": sampler.summary(),
-            "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
+            "kernel_ms_per_step": {k: v["ms"] / 2 for k, v in prof_all.items()},
             "roofline": roof}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"], _ = cpu_baseline(7)

@@ -55,6 +55,7 @@ SIGNATURES = {
     "ds_gram_f64": (cint, [f64p, i64, cint, f64p, i64, cint, i64, f64p, i64, f64p, ptr]),
     "ds_gram_sym2_scratch_elems": (i64, []),
     "ds_gram_sym2_f64": (cint, [f64p, f64p, f64p, i64, i64, C.POINTER(C.c_int), cint, f64p, f64p, i64, f64p, ptr]),
+    "ds_rr_update_f64": (cint, [f64p, f64p, f64p, i64, cint, cint, f64p, f64p, cint, i64, i64, f64p, f64p, f64p, i64, ptr]),
     "ds_block_gemm_f64": (cint, [f64p, i64, cint, f64p, i64, cint, i64, dbl, f64p, i64, ptr]),
     "ds_eigh_scratch_elems": (i64, [cint]),
     "ds_eigh_generalized_f64": (cint, [f64p, f64p, cint, i64, dbl, f64p, f64p, i64, f64p, ptr, ptr]),
@@ -87,6 +88,7 @@ SIGNATURES = {
     "ds_synth_scratch_elems": (i64, [i64, cint, i64]),
     "ds_modal_synth_fwd": (cint, [f32p, f32p, f32p, i64, cint, i64, dbl, f32p, f32p, ptr]),
     "ds_prof_enable": (cint, [cint]),
+    "ds_prof_enable_classes": (cint, [C.c_uint32]),
     "ds_prof_reset": (cint, []),
     "ds_prof_num_classes": (cint, []),
     "ds_launch_count": (i64, []),

@@ -76,12 +76,12 @@ enum ProfClass {
     PROF_PATTERN = 0, PROF_GEOMETRY, PROF_ASSEMBLE, PROF_SPMM, PROF_CHEB, PROF_GRAM, PROF_GEMM, PROF_EIGH,
     PROF_RESIDUAL, PROF_COPY, PROF_GRAD, PROF_QUADFORM, PROF_SYNTH, PROF_OTHER, PROF_COARSE, PROF_TRANSFER, PROF_NCLASS
 };
-bool prof_enabled();
+bool prof_enabled(int cls);
 void prof_begin(int cls, cudaStream_t s);
 void prof_end(int cls, cudaStream_t s);
 struct ProfScope {
     int cls; cudaStream_t s; bool on;
-    ProfScope(int c, cudaStream_t st) : cls(c), s(st), on(prof_enabled()) { if (on) prof_begin(cls, s); }
+    ProfScope(int c, cudaStream_t st) : cls(c), s(st), on(prof_enabled(c)) { if (on) prof_begin(cls, s); }
     ~ProfScope() { if (on) prof_end(cls, s); }
 };
 

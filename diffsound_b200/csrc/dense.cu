@@ -252,6 +252,129 @@ int block_gemm_f64(const double* A, int64_t lda, int p, const double* C, int64_t
     return DS_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Fused Rayleigh-Ritz update of one LOBPCG step, all three wide buffers in one launch:
+//   Ynew[:, 0:m]           = A[:, 0:prow] C1      (the new X block)
+//   Ynew[:, 2m:2m + q2]    = A[:, m:prow] C2      (the new P block, active columns only)
+// for A in {S, KS, MS} (blockIdx.y).  A is read ONCE for both products (the separate GEMMs read the
+// W and P columns twice); both coefficient matrices sit in shared memory; the A fragments of the next
+// 16 columns are in flight while the DMMAs of the current 16 run.
+// ---------------------------------------------------------------------------
+struct RRUpdateArgs {
+    const double* A[3];
+    double* Y[3];
+    int64_t lda, ldy, n;
+    const double* C1;       // prow x m
+    const double* C2;       // (prow - m) x q2
+    int64_t ldc;
+    int prow, m, q2;
+};
+
+template <int QT1, int QT2>
+__global__ void __launch_bounds__(BG_THREADS)
+k_rr_update(const __grid_constant__ RRUpdateArgs g) {
+    extern __shared__ __align__(16) double Cs[];  // C1s [prow][qs1] | C2s [prow - m][qs2]
+    constexpr int q1 = 8 * QT1, q2 = 8 * QT2;
+    const int qs1 = pad8mod16(q1), qs2 = QT2 ? pad8mod16(q2) : 0;
+    double* C1s = Cs;
+    double* C2s = Cs + (size_t)g.prow * qs1;
+    for (int t = threadIdx.x; t < g.prow * q1; t += blockDim.x) {
+        const int r = t / q1, c = t - r * q1;
+        C1s[r * qs1 + c] = g.C1[(int64_t)r * g.ldc + c];
+    }
+    if (QT2)
+        for (int t = threadIdx.x; t < (g.prow - g.m) * q2; t += blockDim.x) {
+            const int r = t / q2, c = t - r * q2;
+            C2s[r * qs2 + c] = g.C2[(int64_t)r * g.ldc + c];
+        }
+    __syncthreads();
+    const double* __restrict__ A = g.A[blockIdx.y];
+    double* __restrict__ Y = g.Y[blockIdx.y];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kk = lane & 3, mm = lane >> 2;
+    const int64_t n_strips = (g.n + 7) / 8;
+    const int p = g.prow, m = g.m;
+    for (int64_t strip = blockIdx.x * 8 + warp; strip < n_strips; strip += (int64_t)gridDim.x * 8) {
+        const int64_t row = strip * 8 + mm;
+        const bool ok = row < g.n;
+        const double* ap = A + (ok ? row : 0) * g.lda + kk;
+        double acc1[QT1][2], acc2[QT2 ? QT2 : 1][2];
+#pragma unroll
+        for (int t = 0; t < QT1; ++t) acc1[t][0] = acc1[t][1] = 0.0;
+#pragma unroll
+        for (int t = 0; t < (QT2 ? QT2 : 1); ++t) acc2[t][0] = acc2[t][1] = 0.0;
+        double a[4], an[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a[u] = (ok && 4 * u < p) ? __ldg(ap + 4 * u) : 0.0;
+        for (int k0 = 0; k0 < p; k0 += 16) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) an[u] = (ok && (k0 + 16 + 4 * u) < p) ? __ldg(ap + k0 + 16 + 4 * u) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = k0 + 4 * u;
+                if (k < p) {
+                    const double* bp = C1s + (k + kk) * qs1 + mm;
+#pragma unroll
+                    for (int t = 0; t < QT1; ++t) dmma_m8n8k4(acc1[t][0], acc1[t][1], a[u], bp[8 * t]);
+                    if (QT2 && k >= m) {
+                        const double* cp = C2s + (k - m + kk) * qs2 + mm;
+#pragma unroll
+                        for (int t = 0; t < QT2; ++t) dmma_m8n8k4(acc2[t][0], acc2[t][1], a[u], cp[8 * t]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) a[u] = an[u];
+        }
+        if (ok) {
+            double* yp = Y + row * g.ldy + 2 * kk;
+#pragma unroll
+            for (int t = 0; t < QT1; ++t)
+                *reinterpret_cast<double2*>(yp + 8 * t) = make_double2(acc1[t][0], acc1[t][1]);
+            if (QT2) {
+                double* zp = yp + 2 * m;
+#pragma unroll
+                for (int t = 0; t < QT2; ++t)
+                    *reinterpret_cast<double2*>(zp + 8 * t) = make_double2(acc2[t][0], acc2[t][1]);
+            }
+        }
+    }
+}
+
+int rr_update_f64(const double* const A[3], int64_t lda, int prow, int m, const double* C1, const double* C2, int q2,
+                  int64_t ldc, int64_t n, double* const Y[3], int64_t ldy, cudaStream_t stream) {
+    DS_REQUIRE(m > 0 && m % 16 == 0 && m <= 48 && prow >= m && prow % 4 == 0 && prow <= 144,
+               "rr_update: m=%d (16, 32 or 48), prow=%d (multiple of 4 in [m, 144])", m, prow);
+    DS_REQUIRE(q2 >= 0 && q2 % 16 == 0 && q2 <= 48 && (q2 == 0 || prow > m), "rr_update: q2=%d must be 0, 16, 32 or 48", q2);
+    DS_REQUIRE(C1 && (q2 == 0 || C2), "rr_update: null coefficient matrix");
+    RRUpdateArgs g;
+    for (int b = 0; b < 3; ++b) {
+        DS_REQUIRE(A[b] && Y[b] && A[b] != Y[b], "rr_update: bad buffer %d", b);
+        DS_REQUIRE((uintptr_t)Y[b] % 16 == 0, "rr_update: Y must be 16-byte aligned");
+        g.A[b] = A[b];
+        g.Y[b] = Y[b];
+    }
+    DS_REQUIRE(ldy % 2 == 0, "rr_update: ldy must be even");
+    g.lda = lda; g.ldy = ldy; g.n = n; g.C1 = C1; g.C2 = C2; g.ldc = ldc; g.prow = prow; g.m = m; g.q2 = q2;
+    ProfScope prof(PROF_GEMM, stream);
+    const size_t smem = ((size_t)prow * pad8mod16(m) + (q2 ? (size_t)(prow - m) * pad8mod16(q2) : 0)) * sizeof(double);
+    const int64_t strips = (n + 7) / 8;
+    const int per_buf = (int)std::min<int64_t>((strips + 7) / 8, 148 * 2);
+    auto launch = [&](auto kern) -> int {
+        DS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<dim3(per_buf, 3), BG_THREADS, smem, stream>>>(g);
+        DS_LAUNCH_CHECK();
+        return DS_OK;
+    };
+#define DS_RR_CASE(Q1, Q2) if (m == 8 * Q1 && q2 == 8 * Q2) return launch(k_rr_update<Q1, Q2>)
+    DS_RR_CASE(2, 0); DS_RR_CASE(2, 2);
+    DS_RR_CASE(4, 0); DS_RR_CASE(4, 2); DS_RR_CASE(4, 4);
+    DS_RR_CASE(6, 0); DS_RR_CASE(6, 2); DS_RR_CASE(6, 4); DS_RR_CASE(6, 6);
+#undef DS_RR_CASE
+    set_error("rr_update: unsupported shape m=%d q2=%d", m, q2);
+    return DS_ERR_ARG;
+}
+
 }  // namespace ds
 
 using namespace ds;
@@ -266,4 +389,12 @@ extern "C" int ds_gram_f64(const double* A, int64_t lda, int p, const double* B,
 extern "C" int ds_block_gemm_f64(const double* A, int64_t lda, int p, const double* C, int64_t ldc, int q, int64_t n,
                                  double beta, double* Y, int64_t ldy, void* stream) {
     return block_gemm_f64(A, lda, p, C, ldc, q, n, 1.0, beta, Y, ldy, (cudaStream_t)stream);
+}
+
+extern "C" int ds_rr_update_f64(const double* S, const double* KS, const double* MS, int64_t lda, int prow, int m,
+                                const double* C1, const double* C2, int q2, int64_t ldc, int64_t n, double* S_out,
+                                double* KS_out, double* MS_out, int64_t ldy, void* stream) {
+    const double* A[3] = {S, KS, MS};
+    double* Y[3] = {S_out, KS_out, MS_out};
+    return rr_update_f64(A, lda, prow, m, C1, C2, q2, ldc, n, Y, ldy, (cudaStream_t)stream);
 }

@@ -76,6 +76,9 @@ int gram_sym2(const double* S, const double* KS, const double* MS, int64_t ld, i
 // Y = beta Y + alpha A C
 int block_gemm_f64(const double* A, int64_t lda, int p, const double* C, int64_t ldc, int q, int64_t n, double alpha,
                    double beta, double* Y, int64_t ldy, cudaStream_t stream);
+// fused Rayleigh-Ritz update of the three wide buffers: Y[:, :m] = A[:, :prow] C1, Y[:, 2m:2m+q2] = A[:, m:prow] C2
+int rr_update_f64(const double* const A[3], int64_t lda, int prow, int m, const double* C1, const double* C2, int q2,
+                  int64_t ldc, int64_t n, double* const Y[3], int64_t ldy, cudaStream_t stream);
 // idx_host (may be NULL = identity): slot of compact index i inside the ldg x ldg Gram storage;
 // only the upper triangle of the storage is read; rows of C are written at the mapped slots.
 // sigma < 0 selects an automatic shift |sigma| * mean(diag(scaled GK)).

@@ -224,7 +224,8 @@ struct Driver {
         return DS_OK;
     }
 
-    // largest eigenvalue of invD A by power iteration on I + invD A (16 fp32 columns)
+    // largest eigenvalue of invD A by power iteration on invD A itself (16 fp32 columns, 12 steps; the
+    // un-shifted iteration reaches 0.95 lmax where I + invD A needs 16-20 steps, scripts/proto_pmg.py)
     int estimate_lmax(Level32& L, float* a, float* b, float* zero_r) {
         const int w = 16;
         const int64_t nl = 3 * L.n_nodes;
@@ -239,12 +240,12 @@ struct Driver {
             DS_CUDA(cudaStreamSynchronize(st));
             return DS_OK;
         };
-        const int iters = 20;
+        const int iters = 12;
         for (int it = 0; it < iters; ++it) {
             if (it == iters - 1) DS_TRY(norms_of(a, n0));
-            // b = a + 0 (a - a) + (-1) invD (0 - A a) = (I + invD A) a
-            DS_TRY(spmm32(S32_MODE_CHEB, L.brow, L.rec, L.n_nodes, w, a, zero_r, L.invD, a, b, 0.f, -1.f, L.prof_cls, st,
-                          L.chunk_row));
+            // b = a + (-1) (a - 0) + (-1) invD (0 - A a) = invD A a     (Zprev = R = the zero block)
+            DS_TRY(spmm32(S32_MODE_CHEB, L.brow, L.rec, L.n_nodes, w, a, zero_r, L.invD, zero_r, b, -1.f, -1.f, L.prof_cls,
+                          st, L.chunk_row));
             std::swap(a, b);
             L.launches++;
             L.cols += w;
@@ -252,7 +253,7 @@ struct Driver {
         DS_TRY(norms_of(a, n1));
         double best = 0.0;
         for (int c = 0; c < w; ++c) best = std::max(best, std::sqrt(n1[c] / n0[c]));
-        L.lmax = 1.1 * (best - 1.0);
+        L.lmax = 1.1 * best;
         return DS_OK;
     }
 
@@ -455,19 +456,16 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
         // ---- update: X' = [X W P] C[:, :m];  P' = [W P] C[m:, act]
         int nxt = cur ^ 1;
         const int prow = useP ? 3 * m : 2 * m;   // rows of C in play (slots beyond are zero anyway)
-        DS_TRY(block_gemm_f64(S[cur], ld, prow, Cm, 144, m, n, 1.0, 0.0, S[nxt], ld, st));
-        DS_TRY(block_gemm_f64(KS[cur], ld, prow, Cm, 144, m, n, 1.0, 0.0, KS[nxt], ld, st));
-        DS_TRY(block_gemm_f64(MS[cur], ld, prow, Cm, 144, m, n, 1.0, 0.0, MS[nxt], ld, st));
-        // gather the active columns of C (rows m..prow) into a compact (prow-m) x wpad matrix in GK storage
+        // gather the active columns of C (rows m..prow) into a compact (prow-m) x wpad matrix (GM storage, zeroed):
+        // rows = slots m.., cols = active list; then both products in one pass over each buffer
+        DS_CUDA(cudaMemsetAsync(GM, 0, sizeof(double) * 144 * 144, st));
+        k_gather_cols<<<(unsigned)ceil_div((int64_t)(prow - m) * wpad, 256), 256, 0, st>>>(
+            Cm + (size_t)m * 144, 144, ci, na, wpad, prow - m, GM, 144);
+        DS_LAUNCH_CHECK();
         {
-            // reuse GM storage as the compact coefficient matrix (zeroed): rows = slots m.., cols = active list
-            DS_CUDA(cudaMemsetAsync(GM, 0, sizeof(double) * 144 * 144, st));
-            k_gather_cols<<<(unsigned)ceil_div((int64_t)(prow - m) * wpad, 256), 256, 0, st>>>(
-                Cm + (size_t)m * 144, 144, ci, na, wpad, prow - m, GM, 144);
-            DS_LAUNCH_CHECK();
-            DS_TRY(block_gemm_f64(S[cur] + m, ld, prow - m, GM, 144, wpad, n, 1.0, 0.0, S[nxt] + 2 * m, ld, st));
-            DS_TRY(block_gemm_f64(KS[cur] + m, ld, prow - m, GM, 144, wpad, n, 1.0, 0.0, KS[nxt] + 2 * m, ld, st));
-            DS_TRY(block_gemm_f64(MS[cur] + m, ld, prow - m, GM, 144, wpad, n, 1.0, 0.0, MS[nxt] + 2 * m, ld, st));
+            const double* Ain[3] = {S[cur], KS[cur], MS[cur]};
+            double* Yout[3] = {S[nxt], KS[nxt], MS[nxt]};
+            DS_TRY(rr_update_f64(Ain, ld, prow, m, Cm, GM, wpad, 144, n, Yout, ld, st));
         }
         pslot_col = act;
         np = na;

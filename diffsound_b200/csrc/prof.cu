@@ -12,6 +12,7 @@ namespace ds {
 
 struct ProfState {
     bool on = false;
+    uint32_t mask = 0xffffffffu;      // classes being timed while `on`
     std::mutex mu;
     struct Rec { cudaEvent_t a, b; int cls; };
     std::vector<Rec> pending;
@@ -22,7 +23,7 @@ struct ProfState {
 };
 static ProfState g_prof;
 
-bool prof_enabled() { return g_prof.on; }
+bool prof_enabled(int cls) { return g_prof.on && ((g_prof.mask >> cls) & 1u); }
 
 static std::atomic<int64_t> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -76,6 +77,14 @@ using namespace ds;
 extern "C" int ds_prof_enable(int on) {
     std::lock_guard<std::mutex> lk(g_prof.mu);
     g_prof.on = on != 0;
+    g_prof.mask = 0xffffffffu;
+    return DS_OK;
+}
+
+extern "C" int ds_prof_enable_classes(uint32_t mask) {
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    g_prof.on = mask != 0;
+    g_prof.mask = mask;
     return DS_OK;
 }
 

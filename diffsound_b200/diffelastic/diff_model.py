@@ -158,6 +158,10 @@ class DiffSoundObj:
     nested_start = True     # ... and a P1 eigen-solve for the start block (skipped on a warm start)
     nested_tol = 3e-2
     nested_degree = 0       # 0: automatic
+    smooth_steps = 3        # Chebyshev-Jacobi smoothing steps on the P2 operator before / after the coarse correction
+    smooth_ratio = 8.0      # ... damping the upper [lmax / ratio, lmax] of the spectrum
+    coarse_degree = 0       # Chebyshev steps of the P1 coarse solve (0: automatic, ~ n_coarse^(1/3) / 1.2)
+    coarse_ratio = 0.0      # 0: automatic, 0.4 * degree^2
     eig_maxit = 400
 
     def __init__(self, vertices=None, tets=None, mode_num=16, mat=MatSet.Ceramic, order=1, mat_model=FixedLinear,
@@ -321,9 +325,10 @@ class DiffSoundObj:
             # two-level p-multigrid preconditioner: P1 operator of the same mesh, same material
             mu, la = self._lame_used
             coarse.assemble(self._verts32, mu, la, coarse.ctab, self.deform.coarse_mtab(self._density_used))
-            cdeg = int(min(64, max(6, round((3 * coarse.n_nodes) ** (1.0 / 3.0) / 1.2))))
-            kw = dict(coarse=coarse, smooth_steps=3, smooth_ratio=8.0, coarse_degree=cdeg,
-                      coarse_ratio=0.4 * cdeg * cdeg, nested=self.nested_start and self._X is not X,
+            cdeg = int(self.coarse_degree) or int(min(64, max(6, round((3 * coarse.n_nodes) ** (1.0 / 3.0) / 1.2))))
+            cratio = float(self.coarse_ratio) or 0.4 * cdeg * cdeg
+            kw = dict(coarse=coarse, smooth_steps=int(self.smooth_steps), smooth_ratio=float(self.smooth_ratio),
+                      coarse_degree=cdeg, coarse_ratio=cratio, nested=self.nested_start and self._X is not X,
                       nested_tol=self.nested_tol, nested_degree=self.nested_degree)
         lam, res, stats = native.lobpcg(pat, self._Kval, self._Mblk, X, nev=need, tol=self.eig_tol, maxit=self.eig_maxit,
                                         cheb_degree=deg, cheb_ratio=0.4 * deg * deg, n_rigid=6, **kw)

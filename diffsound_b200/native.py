@@ -229,6 +229,21 @@ def gram(A, B, out=None):
     return out
 
 
+def rr_update(bufs, prow, m, C1, C2, q2):
+    """Fused LOBPCG basis update (ds_rr_update_f64): for each wide buffer A (n x 3m, fp64) returns A_out with
+    A_out[:, :m] = A[:, :prow] C1 and A_out[:, 2m:2m+q2] = A[:, m:prow] C2 (other columns zero)."""
+    lib = _lib.load()
+    outs = [torch.zeros_like(b) for b in bufs]
+    ld = bufs[0].shape[1]
+    assert C1.stride(0) == C2.stride(0) and C1.stride(1) == 1 and C2.stride(1) == 1
+    with torch.cuda.device(bufs[0].device):
+        _lib.check(lib.ds_rr_update_f64(_p(bufs[0]), _p(bufs[1]), _p(bufs[2]), ld, int(prow), int(m),
+                                        C.c_void_p(C1.data_ptr()), C.c_void_p(C2.data_ptr()), int(q2), C1.stride(0),
+                                        bufs[0].shape[0], _p(outs[0]), _p(outs[1]), _p(outs[2]), ld, _stream()),
+                   "ds_rr_update_f64")
+    return outs
+
+
 def block_gemm(A, Cm, beta=0.0, out=None):
     """out = beta*out + A Cm, A (n, p), Cm (p, q)."""
     lib = _lib.load()
@@ -476,12 +491,24 @@ def modal_synth_bwd(amp, damp, freq, gy, sr):
 
 
 class prof:
-    """Per-kernel-class device timing (ds_prof_*): `with native.prof() as p: ...; p.read()`."""
+    """Per-kernel-class device timing (ds_prof_*): `with native.prof() as p: ...; p.read()`.
+    classes: names of the classes to time (None: all) -- a short list keeps the event overhead out of a
+    timed region."""
+
+    def __init__(self, classes=None):
+        self.classes = classes
 
     def __enter__(self):
         lib = _lib.load()
         lib.ds_prof_reset()
-        lib.ds_prof_enable(1)
+        if self.classes is None:
+            lib.ds_prof_enable(1)
+        else:
+            names = [lib.ds_prof_class_name(c).decode() for c in range(lib.ds_prof_num_classes())]
+            mask = 0
+            for n in self.classes:
+                mask |= 1 << names.index(n)
+            lib.ds_prof_enable_classes(mask)
         return self
 
     def __exit__(self, *exc):

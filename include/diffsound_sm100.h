@@ -117,6 +117,13 @@ int ds_gram_sym2_f64(const double* S, const double* KS, const double* MS, int64_
 /* Y (n x q) = beta*Y + A (n x p) C (p x q, row-major ldc) */
 int ds_block_gemm_f64(const double* A, int64_t lda, int p, const double* C, int64_t ldc, int q,
                       int64_t n, double beta, double* Y, int64_t ldy, void* stream);
+/* Fused Rayleigh-Ritz update of a LOBPCG step (_lobpcg.py:463-466, X = S Z and the new P block), for the
+ * three wide buffers A in {S, KS, MS} (n x lda, columns [X | W | P], m columns each) in one launch:
+ *   A_out[:, 0:m] = A[:, 0:prow] C1 (prow x m);   A_out[:, 2m:2m+q2] = A[:, m:prow] C2 ((prow-m) x q2).
+ * m in {16, 32, 48}; q2 in {0, 16, 32, 48}; prow a multiple of 4 in [m, 144]; C1, C2 row-major, ldc. */
+int ds_rr_update_f64(const double* S, const double* KS, const double* MS, int64_t lda, int prow, int m,
+                     const double* C1, const double* C2, int q2, int64_t ldc, int64_t n, double* S_out,
+                     double* KS_out, double* MS_out, int64_t ldy, void* stream);
 /* Generalised symmetric eigenproblem GK c = theta GM c, N <= 144: Cholesky of GM and of
  * GK + sigma*GM (one CTA), one-sided Jacobi on a thread-block cluster of 8 CTAs (rows in registers,
  * row exchange through distributed shared memory), back substitution (one CTA).
@@ -291,6 +298,8 @@ int ds_modal_synth_bwd(const float* amp, const float* damp, const float* freq, c
  * accumulated per class ("spmm", "cheb_step", "gram", ...).  Off by default.  ds_prof_read
  * synchronises on the recorded events. */
 int ds_prof_enable(int on);
+/* time only the classes whose bit (1 << class index, see ds_prof_class_name) is set; 0 turns timing off */
+int ds_prof_enable_classes(uint32_t mask);
 int ds_prof_reset(void);
 int ds_prof_num_classes(void);
 /* kernels launched by this library in this process so far (cub and memcpy/memset excluded) */

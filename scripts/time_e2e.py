@@ -20,7 +20,7 @@ def tick(name, t0, acc):
     return t1
 
 
-for rep in range(4):
+for rep in range(6):
     acc = {}
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -45,5 +45,8 @@ for rep in range(4):
     lam_h = obj.eigenvalues.cpu()
     g_h = leaf.grad.cpu()
     t0 = tick("d2h", t0, acc)
+    st = torch.cuda.memory_stats()
+    acc["cudaMallocs"] = st.get("num_device_alloc", 0)
+    acc["reserved GB"] = st.get("reserved_bytes.all.current", 0) / 1e9
     if rep:
         print("  ".join(f"{k}: {v:.2f} ms" for k, v in acc.items()), flush=True)

@@ -135,6 +135,26 @@ def test_gram_dmma(n, p, q):
     assert float((G - ref).abs().max()) <= 1e-12 * float(ref.abs().max()) * np.sqrt(n)
 
 
+@pytest.mark.parametrize("n,m,prow,q2", [(1003, 48, 144, 48), (777, 48, 96, 32), (4099, 32, 96, 16), (515, 16, 48, 16),
+                                         (100000, 48, 144, 16)])
+def test_rr_update_fused(n, m, prow, q2):
+    """Fused LOBPCG basis update against torch matmul: X' = [X W P] C1, P' = [W P] C2 for S, KS, MS at once."""
+    from diffsound_b200 import native
+    DEV = "cuda:0"
+    g = torch.Generator(device=DEV).manual_seed(5)
+    bufs = [torch.randn(n, 3 * m, dtype=torch.float64, device=DEV, generator=g) for _ in range(3)]
+    Cfull = torch.randn(144, 144, dtype=torch.float64, device=DEV, generator=g)
+    C2full = torch.randn(144, 144, dtype=torch.float64, device=DEV, generator=g)
+    C1, C2 = Cfull[:prow, :m], C2full[:prow - m, :q2]
+    outs = native.rr_update(bufs, prow, m, C1, C2, q2)
+    for A, Y in zip(bufs, outs):
+        ref1 = A[:, :prow] @ C1
+        ref2 = A[:, m:prow] @ C2
+        assert torch.allclose(Y[:, :m], ref1, rtol=1e-12, atol=1e-11)
+        assert torch.allclose(Y[:, 2 * m:2 * m + q2], ref2, rtol=1e-12, atol=1e-11)
+        assert float(Y[:, m:2 * m].abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("n,p,q", [(1000, 16, 16), (4099, 48, 48), (30011, 144, 48), (5, 4, 8), (50000, 32, 64)])
 def test_block_gemm_dmma(n, p, q):
     from diffsound_b200 import native
