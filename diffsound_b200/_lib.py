@@ -26,13 +26,13 @@ class LobpcgOpts(C.Structure):
                 ("sigma", C.c_double), ("cheb_ratio", C.c_double), ("n_rigid", C.c_int), ("verbose", C.c_int),
                 ("smooth_steps", C.c_int), ("coarse_degree", C.c_int), ("smooth_ratio", C.c_double),
                 ("coarse_ratio", C.c_double), ("nested", C.c_int), ("nested_tol", C.c_double),
-                ("nested_degree", C.c_int)]
+                ("nested_degree", C.c_int), ("coords", C.c_void_p)]
 
 
 class PmgLevel(C.Structure):
     _fields_ = [("brow", C.c_void_p), ("bcol", C.c_void_p), ("n_nodes", C.c_int64), ("nnzb", C.c_int64),
                 ("Kval", C.c_void_p), ("Mblk", C.c_void_p), ("parents", C.c_void_p), ("rptr", C.c_void_p),
-                ("rlist", C.c_void_p)]
+                ("rlist", C.c_void_p), ("coords", C.c_void_p)]
 
 
 # name -> (restype, argtypes); mirrors include/diffsound_sm100.h one to one

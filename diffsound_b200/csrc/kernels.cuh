@@ -31,24 +31,29 @@ int spmm32(int mode, const int32_t* brow, const void* rec, int64_t n_nodes, int 
 int spmm32_chunks(const int32_t* brow, int64_t n_nodes, int32_t* chunk_row, cudaStream_t st);
 int pack_k32(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, const double* Kval, const double* Mblk,
              double shift, void* rec, float* invD, cudaStream_t st, const uint32_t* colmap = nullptr,
-             int64_t row_offset = 0);
+             int64_t row_offset = 0, const int32_t* perm = nullptr, const int32_t* inv = nullptr,
+             const int32_t* brow_out = nullptr);
 int jacobi32(const float* invD, const float* R, int64_t n_nodes, int ncols, float cc, float* Out, cudaStream_t st);
+// perm_* / inv_*: node renumberings of the levels' private (Morton) orderings, NULL = identity
 int restrict32(const int32_t* rptr, const int32_t* rlist, int64_t n_coarse, const float* res, int ncols, float* rc,
-               cudaStream_t st);
-int prolong_add32(const int32_t* par, int64_t n_fine, const float* zc, int ncols, float* z, cudaStream_t st);
+               cudaStream_t st, const int32_t* perm_c = nullptr, const int32_t* inv_f = nullptr);
+int prolong_add32(const int32_t* par, int64_t n_fine, const float* zc, int ncols, float* z, cudaStream_t st,
+                  const int32_t* perm_f = nullptr, const int32_t* inv_c = nullptr);
 int prolong64(const int32_t* par, int64_t n_fine, const double* xc, int64_t ldc, int w, double* x, int64_t ldx,
               cudaStream_t st);
 int inject64(const int32_t* rptr, const int32_t* rlist, int64_t n_coarse, const double* x, int64_t ldx, int w,
              double* xc, int64_t ldc, cudaStream_t st);
 int gather_cols_f32(const double* src, int64_t lds, const ColIdx& idx, int count, int width, int64_t n, float* dst,
-                    cudaStream_t st);
-int widen_f32(const float* src, int width, int64_t n, double* dst, int64_t ldd, cudaStream_t st);
+                    cudaStream_t st, const int32_t* perm = nullptr);
+int widen_f32(const float* src, int width, int64_t n, double* dst, int64_t ldd, cudaStream_t st,
+              const int32_t* perm = nullptr);
 int colnorm2_f32(const float* V, int w, int64_t n, double* partial, int ctas, cudaStream_t st);
 int fill_random_f32(float* V, int64_t count, uint64_t seed, cudaStream_t st);
 
 // one level of the FP32 preconditioner: records + block-Jacobi inverse + spectral bound of invD A
 struct Level32 {
-    const int32_t* brow = nullptr;
+    const int32_t* brow = nullptr;           // row pointers in the level's own numbering
+    const int32_t *perm = nullptr, *inv = nullptr;   // own row -> matrix row and back (NULL: identity)
     int64_t n_nodes = 0, nnzb = 0;
     unsigned char* rec = nullptr;
     float* invD = nullptr;
@@ -58,7 +63,7 @@ struct Level32 {
     int64_t launches = 0, cols = 0;          // SpMM launches and the sum of their column counts
     static size_t bytes(int64_t n_nodes, int64_t nnzb);
     int setup(Arena& a, const int32_t* brow, const int32_t* bcol, int64_t n_nodes, int64_t nnzb, const double* Kval,
-              const double* Mblk, double shift, cudaStream_t st);
+              const double* Mblk, double shift, const float* coords, cudaStream_t st);
     // z = p(invD A) invD r, `degree` Chebyshev steps on [lmax/ratio, lmax]; from_zero: z0 = 0, else z0 = *zc.
     // zc / zp ping-pong; the result is in *zc on return.
     int cheb(const float* r, int ncols, int degree, double ratio, bool from_zero, float** zc, float** zp,

@@ -182,11 +182,11 @@ struct Driver {
             DS_CUDA(cudaMemsetAsync(MS[i], 0, 3 * blk * 8, st));
         }
         // FP32 copies of the operators (records + block-Jacobi inverses)
-        DS_TRY(fine.setup(a, brow, bcol, n_nodes, nnzb, Kval, Mblk, o.sigma > 0.0 ? o.sigma : 0.0, st));
+        DS_TRY(fine.setup(a, brow, bcol, n_nodes, nnzb, Kval, Mblk, o.sigma > 0.0 ? o.sigma : 0.0, o.coords, st));
         fine.prof_cls = fine_prof_cls;
         if (cl) {
             DS_TRY(coarse.setup(a, cl->brow, cl->bcol, cl->n_nodes, nnzb_c, cl->Kval, cl->Mblk,
-                                o.sigma > 0.0 ? o.sigma : 0.0, st));
+                                o.sigma > 0.0 ? o.sigma : 0.0, cl->coords, st));
             coarse.prof_cls = PROF_COARSE;
         }
         return DS_OK;
@@ -272,11 +272,11 @@ struct Driver {
         DS_TRY(spmm32(S32_MODE_RESID, fine.brow, fine.rec, n_nodes, w, zc, R32, nullptr, nullptr, zp, 0.f, 0.f,
                       PROF_CHEB, st, fine.chunk_row));                                                       // zp = r - A z
         fine.launches++; fine.cols += w;
-        DS_TRY(restrict32(cl->rptr, cl->rlist, cl->n_nodes, zp, w, RC32, st));
+        DS_TRY(restrict32(cl->rptr, cl->rlist, cl->n_nodes, zp, w, RC32, st, coarse.perm, fine.inv));
         float* cc = ZCa;
         float* cp = ZCb;
         DS_TRY(coarse.cheb(RC32, w, o.coarse_degree, o.coarse_ratio > 1.0 ? o.coarse_ratio : 30.0, true, &cc, &cp, st));
-        DS_TRY(prolong_add32(cl->parents, n_nodes, cc, w, zc, st));
+        DS_TRY(prolong_add32(cl->parents, n_nodes, cc, w, zc, st, fine.perm, coarse.inv));
         DS_TRY(fine.cheb(R32, w, nu, sr, false, &zc, &zp, st));                              // post-smooth
         *out = zc;
         return DS_OK;
@@ -303,6 +303,7 @@ struct Driver {
         dc.fine_prof_cls = PROF_COARSE;
         dc.o = o;
         dc.o.nested = 0;
+        dc.o.coords = cl->coords;
         dc.o.tol = o.nested_tol > 0.0 ? o.nested_tol : 3e-2;
         dc.o.maxit = 40;
         const int deg = o.nested_degree > 0
@@ -422,10 +423,10 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
         ColIdx ci;
         for (int s = 0; s < 128; ++s) ci.v[s] = (short)(s < na ? act[s] : 0);
         // ---- W = T(R[:, act])
-        DS_TRY(gather_cols_f32(R, m, ci, na, wpad, n, R32, st));
+        DS_TRY(gather_cols_f32(R, m, ci, na, wpad, n, R32, st, fine.perm));
         float* Zres = nullptr;
         DS_TRY(apply_precond(wpad, &Zres));
-        DS_TRY(widen_f32(Zres, wpad, n, Wb(cur), ld, st));
+        DS_TRY(widen_f32(Zres, wpad, n, Wb(cur), ld, st, fine.perm));
         // ---- W <- W - X (MX^T W)
         DS_TRY(gram_f64(MS[cur], ld, m, Wb(cur), ld, wpad, n, GK, 144, gram_partial, st));
         DS_TRY(block_gemm_f64(Xb(cur), ld, m, GK, 144, wpad, n, -1.0, 1.0, Wb(cur), ld, st));

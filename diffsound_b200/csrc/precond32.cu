@@ -25,6 +25,7 @@
 #include "ptx.cuh"
 #include <utility>
 #include <cstring>
+#include <cub/cub.cuh>
 
 namespace ds {
 
@@ -564,18 +565,23 @@ __global__ void k_chunk_rows(const int32_t* __restrict__ brow, int n_nodes, int 
     chunk_row[c] = lo;
 }
 
-// records + block-Jacobi inverse from the FP64 matrix: one warp per node row
-// colmap (optional): record column id = colmap[global column]; row_offset: global id of local row 0
+// records + block-Jacobi inverse from the FP64 matrix: one warp per node row of the OPERATOR's numbering.
+// perm (optional): operator row r is matrix row perm[r] and column j becomes inv[j] (Morton renumbering inside
+// the preconditioner; brow_out then holds the row pointers of the permuted rows).  colmap (optional, slabs):
+// record column id = colmap[global column]; row_offset: global id of local row 0.
 __global__ void __launch_bounds__(256)
 k_pack_k32(const int32_t* __restrict__ brow, const int32_t* __restrict__ bcol, int64_t n_nodes,
            const double* __restrict__ Kval, const double* __restrict__ Mblk, double shift,
            uint32_t* __restrict__ rec, float* __restrict__ invD, const uint32_t* __restrict__ colmap,
-           int64_t row_offset) {
+           int64_t row_offset, const int32_t* __restrict__ perm, const int32_t* __restrict__ inv,
+           const int32_t* __restrict__ brow_out) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (row >= n_nodes) return;
-    const int64_t b0 = brow[row] - brow[0];      // a slab passes a window of the global brow
-    const int deg = (int)(brow[row + 1] - brow[row]);
+    const int64_t src = perm ? (int64_t)perm[row] : row;
+    const int64_t b0 = brow[src] - brow[0];      // a slab passes a window of the global brow
+    const int deg = (int)(brow[src + 1] - brow[src]);
+    const int64_t o0 = perm ? (int64_t)brow_out[row] : b0;
     const double* kb = Kval + 9 * b0;
     const int64_t rs = 3 * (int64_t)deg;
     for (int p = lane; p < deg; p += 32) {
@@ -589,11 +595,11 @@ k_pack_k32(const int32_t* __restrict__ brow, const int32_t* __restrict__ bcol, i
             const double m = shift * Mblk[b0 + p];
             k[0] += m; k[4] += m; k[8] += m;
         }
-        uint32_t* o = rec + (b0 + p) * 10;
+        uint32_t* o = rec + (o0 + p) * 10;
 #pragma unroll
         for (int q = 0; q < 9; ++q) o[q] = __float_as_uint((float)k[q]);
-        o[9] = colmap ? colmap[j] : (uint32_t)j;
-        if (j == row + row_offset) {
+        o[9] = colmap ? colmap[j] : (inv ? (uint32_t)inv[j] : (uint32_t)j);
+        if (j == src + row_offset) {
             const double c00 = k[4] * k[8] - k[5] * k[7];
             const double c01 = k[5] * k[6] - k[3] * k[8];
             const double c02 = k[3] * k[7] - k[4] * k[6];
@@ -610,6 +616,103 @@ k_pack_k32(const int32_t* __restrict__ brow, const int32_t* __restrict__ bcol, i
             iv[8] = (float)((k[0] * k[4] - k[1] * k[3]) * id);
         }
     }
+}
+
+// ---- Morton renumbering of the operator's rows (locality of the gathered X rows) ------------------
+__device__ __forceinline__ uint32_t ordered_key(float f) {
+    const uint32_t u = __float_as_uint(f + 0.0f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+// mm[0..2] = min key per axis, mm[3..5] = max key per axis (initialised to 0xffffffff / 0 by the caller)
+__global__ void k_bbox(const float* __restrict__ coords, int64_t n, uint32_t* __restrict__ mm) {
+    uint32_t lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const uint32_t k = ordered_key(coords[3 * i + d]);
+            lo[d] = min(lo[d], k);
+            hi[d] = max(hi[d], k);
+        }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[d] = min(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+            hi[d] = max(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&mm[d], lo[d]);
+            atomicMax(&mm[3 + d], hi[d]);
+        }
+    }
+}
+__device__ __forceinline__ uint32_t spread3(uint32_t v) {     // 10 bits -> every third bit
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__global__ void k_morton_codes(const float* __restrict__ coords, int64_t n, const uint32_t* __restrict__ mm,
+                               uint32_t* __restrict__ codes, uint32_t* __restrict__ iota) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t code = 0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const float lo = key_to_float(mm[d]), hi = key_to_float(mm[3 + d]);
+        const float ext = hi - lo;
+        float t = ext > 0.f ? (coords[3 * i + d] - lo) / ext : 0.f;
+        t = fminf(fmaxf(t, 0.f), 1.f);
+        code |= spread3((uint32_t)(t * 1023.f)) << (2 - d);
+    }
+    codes[i] = code;
+    iota[i] = (uint32_t)i;
+}
+__global__ void k_invert_perm(const int32_t* __restrict__ perm, int64_t n, int32_t* __restrict__ inv) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) inv[perm[i]] = (int32_t)i;
+}
+// out[r] = sum_{q < r} deg(perm[q]), out[n] = total: one CTA, block scans of 1024 rows
+__global__ void __launch_bounds__(1024) k_perm_brow(const int32_t* __restrict__ brow, const int32_t* __restrict__ perm,
+                                                    int n, int32_t* __restrict__ out) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + tid;
+        int v = 0;
+        if (i < n) { const int s = perm[i]; v = brow[s + 1] - brow[s]; }
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const int excl = x - v + (warp ? s_warp[warp - 1] : 0) + s_carry;
+        if (i < n) out[i] = excl;
+        __syncthreads();
+        if (tid == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) out[n] = s_carry;
 }
 
 // Out = cc * invD R   (first Chebyshev step from a zero initial guess); one thread per (node, 4 columns)
@@ -636,23 +739,30 @@ __global__ void k_jacobi32(const float* __restrict__ invD, const float* __restri
     }
 }
 
-// dst32[:, s] = (float) src64[:, idx[s]] for s < count, 0 for count <= s < width
+// dst32[:, s] = (float) src64[:, idx[s]] for s < count, 0 for count <= s < width; with perm, dof row 3 r + c of
+// dst is dof row 3 perm[r] + c of src (the preconditioner's own node numbering)
 __global__ void k_gather_cols_f32(const double* __restrict__ src, int64_t lds, const __grid_constant__ ColIdx idx,
-                                  int count, int width, int64_t n, float* __restrict__ dst) {
+                                  int count, int width, int64_t n, float* __restrict__ dst,
+                                  const int32_t* __restrict__ perm) {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n * width) return;
     const int64_t row = t / width;
     const int s = (int)(t - row * width);
-    dst[t] = s < count ? (float)src[row * lds + idx.v[s]] : 0.f;
+    int64_t srow = row;
+    if (perm) { const int64_t node = row / 3; srow = 3 * (int64_t)perm[node] + (row - 3 * node); }
+    dst[t] = s < count ? (float)src[srow * lds + idx.v[s]] : 0.f;
 }
 
-// dst64[:, :width] (ld) = (double) src32 (n x width)
-__global__ void k_widen_f32(const float* __restrict__ src, int width, int64_t n, double* __restrict__ dst, int64_t ldd) {
+// dst64[:, :width] (ld) = (double) src32 (n x width); with perm, dof row 3 perm[r] + c of dst from row 3 r + c of src
+__global__ void k_widen_f32(const float* __restrict__ src, int width, int64_t n, double* __restrict__ dst, int64_t ldd,
+                            const int32_t* __restrict__ perm) {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n * width) return;
     const int64_t row = t / width;
     const int s = (int)(t - row * width);
-    dst[row * ldd + s] = (double)src[t];
+    int64_t drow = row;
+    if (perm) { const int64_t node = row / 3; drow = 3 * (int64_t)perm[node] + (row - 3 * node); }
+    dst[drow * ldd + s] = (double)src[t];
 }
 
 // per-column sum of squares of an fp32 block (n x w), fp64 accumulation; partial[cta][w]
@@ -678,16 +788,20 @@ __global__ void k_colnorm2_f32(const float* __restrict__ V, int w, int64_t n, do
 
 // ---- two-level transfer operators (nodes; 3 components x c columns per node) -------------------
 // rc[I] = 0.5 * sum_{t in rptr[I]..rptr[I+1]} res[rlist[t]]      (P^T, gather form, fixed order)
+// perm_c / inv_f (optional): coarse row I of rc is coarse node perm_c[I]; fine node f lives at row inv_f[f] of res
 __global__ void k_restrict32(const int32_t* __restrict__ rptr, const int32_t* __restrict__ rlist, int64_t n_coarse,
-                             const float* __restrict__ res, int c4x3, float* __restrict__ rc) {
+                             const float* __restrict__ res, int c4x3, float* __restrict__ rc,
+                             const int32_t* __restrict__ perm_c, const int32_t* __restrict__ inv_f) {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n_coarse * c4x3) return;
     const int64_t I = t / c4x3;
     const int q = (int)(t - I * c4x3);
+    const int64_t Is = perm_c ? (int64_t)perm_c[I] : I;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int e = rptr[I + 1];
-    for (int u = rptr[I]; u < e; ++u) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(res) + (int64_t)rlist[u] * c4x3 + q);
+    const int e = rptr[Is + 1];
+    for (int u = rptr[Is]; u < e; ++u) {
+        const int f = inv_f ? inv_f[rlist[u]] : rlist[u];
+        const float4 v = __ldg(reinterpret_cast<const float4*>(res) + (int64_t)f * c4x3 + q);
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
     s.x *= 0.5f; s.y *= 0.5f; s.z *= 0.5f; s.w *= 0.5f;
@@ -695,13 +809,16 @@ __global__ void k_restrict32(const int32_t* __restrict__ rptr, const int32_t* __
 }
 
 // z[i] += 0.5 * (zc[par[2i]] + zc[par[2i+1]])                  (P)
+// perm_f / inv_c (optional): row i of z is fine node perm_f[i]; coarse node c lives at row inv_c[c] of zc
 __global__ void k_prolong_add32(const int32_t* __restrict__ par, int64_t n_fine, const float* __restrict__ zc, int c4x3,
-                                float* __restrict__ z) {
+                                float* __restrict__ z, const int32_t* __restrict__ perm_f,
+                                const int32_t* __restrict__ inv_c) {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n_fine * c4x3) return;
     const int64_t i = t / c4x3;
     const int q = (int)(t - i * c4x3);
-    const int2 pp = __ldg(reinterpret_cast<const int2*>(par) + i);
+    int2 pp = __ldg(reinterpret_cast<const int2*>(par) + (perm_f ? (int64_t)perm_f[i] : i));
+    if (inv_c) { pp.x = inv_c[pp.x]; pp.y = inv_c[pp.y]; }
     const float4 a = __ldg(reinterpret_cast<const float4*>(zc) + (int64_t)pp.x * c4x3 + q);
     const float4 b = __ldg(reinterpret_cast<const float4*>(zc) + (int64_t)pp.y * c4x3 + q);
     float4 v = reinterpret_cast<float4*>(z)[t];
@@ -886,13 +1003,15 @@ int spmm32_rowpart(int mode, const int32_t* brow, const void* rec, int64_t n_loc
 }
 
 int pack_k32(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, const double* Kval, const double* Mblk,
-             double shift, void* rec, float* invD, cudaStream_t st, const uint32_t* colmap, int64_t row_offset) {
+             double shift, void* rec, float* invD, cudaStream_t st, const uint32_t* colmap, int64_t row_offset,
+             const int32_t* perm, const int32_t* inv, const int32_t* brow_out) {
     DS_REQUIRE(brow && bcol && Kval && rec && invD, "pack_k32: null argument");
     DS_REQUIRE(((uintptr_t)rec & 15) == 0, "pack_k32: records must be 16-byte aligned");
+    DS_REQUIRE(!perm || (inv && brow_out && !colmap), "pack_k32: a row permutation needs inv and brow_out (and no colmap)");
     ProfScope prof(PROF_COPY, st);
     k_pack_k32<<<(unsigned)ceil_div(n_nodes * 32, 256), 256, 0, st>>>(brow, bcol, n_nodes, Kval, Mblk, shift,
                                                                       reinterpret_cast<uint32_t*>(rec), invD, colmap,
-                                                                      row_offset);
+                                                                      row_offset, perm, inv, brow_out);
     DS_LAUNCH_CHECK();
     return DS_OK;
 }
@@ -906,18 +1025,19 @@ int jacobi32(const float* invD, const float* R, int64_t n_nodes, int ncols, floa
 }
 
 int restrict32(const int32_t* rptr, const int32_t* rlist, int64_t n_coarse, const float* res, int ncols, float* rc,
-               cudaStream_t st) {
+               cudaStream_t st, const int32_t* perm_c, const int32_t* inv_f) {
     ProfScope prof(PROF_TRANSFER, st);
     const int q = 3 * ncols / 4;
-    k_restrict32<<<(unsigned)ceil_div(n_coarse * q, 256), 256, 0, st>>>(rptr, rlist, n_coarse, res, q, rc);
+    k_restrict32<<<(unsigned)ceil_div(n_coarse * q, 256), 256, 0, st>>>(rptr, rlist, n_coarse, res, q, rc, perm_c, inv_f);
     DS_LAUNCH_CHECK();
     return DS_OK;
 }
 
-int prolong_add32(const int32_t* par, int64_t n_fine, const float* zc, int ncols, float* z, cudaStream_t st) {
+int prolong_add32(const int32_t* par, int64_t n_fine, const float* zc, int ncols, float* z, cudaStream_t st,
+                  const int32_t* perm_f, const int32_t* inv_c) {
     ProfScope prof(PROF_TRANSFER, st);
     const int q = 3 * ncols / 4;
-    k_prolong_add32<<<(unsigned)ceil_div(n_fine * q, 256), 256, 0, st>>>(par, n_fine, zc, q, z);
+    k_prolong_add32<<<(unsigned)ceil_div(n_fine * q, 256), 256, 0, st>>>(par, n_fine, zc, q, z, perm_f, inv_c);
     DS_LAUNCH_CHECK();
     return DS_OK;
 }
@@ -931,16 +1051,16 @@ int prolong64(const int32_t* par, int64_t n_fine, const double* xc, int64_t ldc,
 }
 
 int gather_cols_f32(const double* src, int64_t lds, const ColIdx& idx, int count, int width, int64_t n, float* dst,
-                    cudaStream_t st) {
+                    cudaStream_t st, const int32_t* perm) {
     ProfScope prof(PROF_COPY, st);
-    k_gather_cols_f32<<<(unsigned)ceil_div(n * width, 256), 256, 0, st>>>(src, lds, idx, count, width, n, dst);
+    k_gather_cols_f32<<<(unsigned)ceil_div(n * width, 256), 256, 0, st>>>(src, lds, idx, count, width, n, dst, perm);
     DS_LAUNCH_CHECK();
     return DS_OK;
 }
 
-int widen_f32(const float* src, int width, int64_t n, double* dst, int64_t ldd, cudaStream_t st) {
+int widen_f32(const float* src, int width, int64_t n, double* dst, int64_t ldd, cudaStream_t st, const int32_t* perm) {
     ProfScope prof(PROF_COPY, st);
-    k_widen_f32<<<(unsigned)ceil_div(n * width, 256), 256, 0, st>>>(src, width, n, dst, ldd);
+    k_widen_f32<<<(unsigned)ceil_div(n * width, 256), 256, 0, st>>>(src, width, n, dst, ldd, perm);
     DS_LAUNCH_CHECK();
     return DS_OK;
 }
@@ -970,14 +1090,25 @@ int colnorm2_f32(const float* V, int w, int64_t n, double* partial, int ctas, cu
 }
 
 // ---- Level32 -----------------------------------------------------------------------------------
-size_t Level32::bytes(int64_t n_nodes, int64_t nnzb) {
-    auto al = [](size_t b) { return ((b + 255) & ~size_t(255)) + 256; };
-    return al((size_t)nnzb * S32_REC_BYTES + 64) + al((size_t)n_nodes * 9 * sizeof(float)) + al(1024 * sizeof(int32_t));
+static size_t morton_sort_temp(int64_t n_nodes) {
+    size_t t = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, t, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (int)n_nodes, 0, 30);
+    return t;
 }
 
+size_t Level32::bytes(int64_t n_nodes, int64_t nnzb) {
+    auto al = [](size_t b) { return ((b + 255) & ~size_t(255)) + 256; };
+    return al((size_t)nnzb * S32_REC_BYTES + 64) + al((size_t)n_nodes * 9 * sizeof(float)) + al(1024 * sizeof(int32_t)) +
+           6 * al((size_t)(n_nodes + 1) * sizeof(int32_t)) + al(morton_sort_temp(n_nodes)) + al(64);
+}
+
+// coords (optional, fp32 [n_nodes x 3]): the operator is stored with its rows and columns renumbered along a
+// Morton curve through the node coordinates, so that consecutive rows gather overlapping sets of X rows (served by
+// the SM's L1 in k_spmm32v).  The numbering is private to the level: perm / inv translate at its boundary
+// (gather_cols_f32, widen_f32, restrict32, prolong_add32).
 int Level32::setup(Arena& a, const int32_t* brow_, const int32_t* bcol, int64_t n_nodes_, int64_t nnzb_,
-                   const double* Kval, const double* Mblk, double shift, cudaStream_t st) {
-    brow = brow_;
+                   const double* Kval, const double* Mblk, double shift, const float* coords, cudaStream_t st) {
     n_nodes = n_nodes_;
     nnzb = nnzb_;
     rec = a.take<unsigned char>((size_t)nnzb * S32_REC_BYTES + 64);
@@ -985,9 +1116,41 @@ int Level32::setup(Arena& a, const int32_t* brow_, const int32_t* bcol, int64_t 
     chunk_row = a.take<int32_t>(1024);
     DS_REQUIRE(rec && invD && chunk_row, "Level32: workspace arena exhausted");
     DS_REQUIRE(s32v_grid(n_nodes) < 1024, "Level32: more than 1023 SMs");
-    DS_TRY(spmm32_chunks(brow, n_nodes, chunk_row, st));
-    DS_CUDA(cudaMemsetAsync(rec + (size_t)nnzb * S32_REC_BYTES, 0, 64, st));    // TMA reads up to 8 bytes past the end
-    return pack_k32(brow, bcol, n_nodes, Kval, Mblk, shift, rec, invD, st);
+    DS_CUDA(cudaMemsetAsync(rec + (size_t)nnzb * S32_REC_BYTES, 0, 64, st));    // bulk prefetches read up to 8 bytes past the end
+    perm = inv = nullptr;
+    brow = brow_;
+    if (coords) {
+        ProfScope prof(PROF_COPY, st);
+        int32_t* perm_w = a.take<int32_t>(n_nodes + 1);
+        int32_t* inv_w = a.take<int32_t>(n_nodes + 1);
+        int32_t* brow_w = a.take<int32_t>(n_nodes + 1);
+        uint32_t* codes = a.take<uint32_t>(n_nodes + 1);
+        uint32_t* codes2 = a.take<uint32_t>(n_nodes + 1);
+        uint32_t* iota = a.take<uint32_t>(n_nodes + 1);
+        size_t tmp = morton_sort_temp(n_nodes);
+        void* scratch = a.take<char>(tmp);
+        uint32_t* mm = a.take<uint32_t>(8);
+        DS_REQUIRE(scratch && mm, "Level32: workspace arena exhausted");
+        DS_CUDA(cudaMemsetAsync(mm, 0xff, 3 * sizeof(uint32_t), st));
+        DS_CUDA(cudaMemsetAsync(mm + 3, 0, 3 * sizeof(uint32_t), st));
+        k_bbox<<<148, 256, 0, st>>>(coords, n_nodes, mm);
+        DS_LAUNCH_CHECK();
+        const unsigned blocks = (unsigned)ceil_div(n_nodes, 256);
+        k_morton_codes<<<blocks, 256, 0, st>>>(coords, n_nodes, mm, codes, iota);
+        DS_LAUNCH_CHECK();
+        DS_CUDA(cub::DeviceRadixSort::SortPairs(scratch, tmp, codes, codes2, iota, reinterpret_cast<uint32_t*>(perm_w),
+                                                (int)n_nodes, 0, 30, st));
+        count_launch();
+        k_invert_perm<<<blocks, 256, 0, st>>>(perm_w, n_nodes, inv_w);
+        DS_LAUNCH_CHECK();
+        k_perm_brow<<<1, 1024, 0, st>>>(brow_, perm_w, (int)n_nodes, brow_w);
+        DS_LAUNCH_CHECK();
+        perm = perm_w;
+        inv = inv_w;
+        brow = brow_w;
+    }
+    DS_TRY(pack_k32(brow_, bcol, n_nodes, Kval, Mblk, shift, rec, invD, st, nullptr, 0, perm, inv, perm ? brow : nullptr));
+    return spmm32_chunks(brow, n_nodes, chunk_row, st);
 }
 
 // z = p(invD A) invD r by `degree` Chebyshev steps on [lmax/ratio, lmax].

@@ -162,6 +162,7 @@ class DiffSoundObj:
     smooth_ratio = 8.0      # ... damping the upper [lmax / ratio, lmax] of the spectrum
     coarse_degree = 0       # Chebyshev steps of the P1 coarse solve (0: automatic, ~ n_coarse^(1/3) / 1.2)
     coarse_ratio = 0.0      # 0: automatic, 0.4 * degree^2
+    morton = True           # the FP32 preconditioner keeps its operator in a Morton node numbering (SpMM locality)
     eig_maxit = 400
 
     def __init__(self, vertices=None, tets=None, mode_num=16, mat=MatSet.Ceramic, order=1, mat_model=FixedLinear,
@@ -331,7 +332,8 @@ class DiffSoundObj:
                       coarse_degree=cdeg, coarse_ratio=cratio, nested=self.nested_start and self._X is not X,
                       nested_tol=self.nested_tol, nested_degree=self.nested_degree)
         lam, res, stats = native.lobpcg(pat, self._Kval, self._Mblk, X, nev=need, tol=self.eig_tol, maxit=self.eig_maxit,
-                                        cheb_degree=deg, cheb_ratio=0.4 * deg * deg, n_rigid=6, **kw)
+                                        cheb_degree=deg, cheb_ratio=0.4 * deg * deg, n_rigid=6,
+                                        coords=self._verts32 if self.morton else None, **kw)
         if stats["status"] != 0:
             raise RuntimeError(f"eigensolver did not converge: {stats}, max residual {float(res[:need].max()):.3e}")
         self.eig_stats = stats

@@ -308,6 +308,7 @@ class CoarseLevel:
         self.pattern = Pattern(self.tets, self.n_nodes)
         self.corner_nodes = torch.nonzero(self.cid >= 0).squeeze(1)     # fine id of coarse node c, ascending
         self.Kval = self.Mblk = self.geom = None
+        self.use_coords = True
 
     def assemble(self, verts_f32, mu, lam, ctab1, mtab1):
         """P1 stiffness (and mass) on the corner nodes at the current vertex positions."""
@@ -322,7 +323,8 @@ class CoarseLevel:
         return _lib.PmgLevel(brow=self.pattern.brow.data_ptr(), bcol=self.pattern.bcol.data_ptr(),
                              n_nodes=self.n_nodes, nnzb=self.pattern.nnzb, Kval=self.Kval.data_ptr(),
                              Mblk=self.Mblk.data_ptr() if self.Mblk is not None else None,
-                             parents=self.parents.data_ptr(), rptr=self.rptr.data_ptr(), rlist=self.rlist.data_ptr())
+                             parents=self.parents.data_ptr(), rptr=self.rptr.data_ptr(), rlist=self.rlist.data_ptr(),
+                             coords=self.verts.data_ptr() if self.use_coords else None)
 
 
 def k32_pack(pattern, Kval, Mblk=None, shift=0.0):
@@ -382,7 +384,7 @@ def pmg_prolong_add32(coarse, zc, z):
 
 def lobpcg(pattern, Kval, Mblk, X, nev, tol=1e-4, maxit=200, cheb_degree=8, sigma=0.0, cheb_ratio=30.0, n_rigid=6,
            verbose=0, coarse=None, smooth_steps=3, smooth_ratio=8.0, coarse_degree=20, coarse_ratio=160.0, nested=True,
-           nested_tol=3e-2, nested_degree=0):
+           nested_tol=3e-2, nested_degree=0, coords=None):
     """Lowest `nev` pairs of K u = lam M u from the start block X (n, m) fp64 (overwritten with the
     M-orthonormal Ritz vectors).  `coarse`: a CoarseLevel with assembled Kval -> two-level
     preconditioner.  Returns (lam (m,), resid (m,), stats dict)."""
@@ -397,9 +399,14 @@ def lobpcg(pattern, Kval, Mblk, X, nev, tol=1e-4, maxit=200, cheb_degree=8, sigm
                            smooth_steps=int(smooth_steps), coarse_degree=int(coarse_degree),
                            smooth_ratio=float(smooth_ratio), coarse_ratio=float(coarse_ratio),
                            nested=int(bool(nested) and coarse is not None), nested_tol=float(nested_tol),
-                           nested_degree=int(nested_degree))
+                           nested_degree=int(nested_degree), coords=None)
+    if coords is not None:
+        assert coords.dtype == torch.float32 and coords.is_contiguous() and coords.shape == (pattern.n_nodes, 3)
+        opts.coords = coords.data_ptr()
     stats = (C.c_int64 * 12)()
     ws = workspace(dev)
+    if coarse is not None:
+        coarse.use_coords = coords is not None
     lvl = coarse.struct() if coarse is not None else None
     with torch.cuda.device(dev):
         _lib.check(lib.ds_lobpcg(ws.handle, _p(pattern.brow), _p(pattern.bcol), pattern.n_nodes, _p(Kval), _p(Mblk),

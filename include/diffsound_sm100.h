@@ -167,6 +167,9 @@ typedef struct ds_lobpcg_opts {
                            the P2 iteration from its prolonged Ritz vectors (nested iteration) */
     double nested_tol;  /* residual tolerance of that coarse solve (default 3e-2) */
     int nested_degree;  /* Chebyshev degree of the coarse solve's one-level preconditioner (0: automatic) */
+    const float* coords;/* device fp32 [n_nodes x 3] node coordinates or NULL.  When given, the FP32 preconditioner
+                           stores its operator renumbered along a Morton curve through the nodes (a private
+                           numbering: locality for the gathered rows of the SpMM); results are unaffected */
 } ds_lobpcg_opts;
 /* Coarse level of the two-level preconditioner: the P1 operator on the corner nodes of a quadratic
  * mesh (pattern + values from ds_pattern_* / ds_assemble_km at order 1 on ds_pmg_coarse_fill's
@@ -181,6 +184,7 @@ typedef struct ds_pmg_level {
     const int32_t* parents;   /* [2*n_fine_nodes]: fine node i = 0.5 (coarse parents[2i] + parents[2i+1]) */
     const int32_t* rptr;      /* [n_nodes+1]  transpose (gather) lists of the prolongation */
     const int32_t* rlist;     /* [2*n_fine_nodes] */
+    const float* coords;      /* fp32 [n_nodes x 3] coarse node coordinates or NULL (see ds_lobpcg_opts.coords) */
 } ds_pmg_level;
 int ds_lobpcg(ds_workspace* ws, const int32_t* brow, const int32_t* bcol, int64_t n_nodes,
               const double* Kval, const double* Mblk, const ds_pmg_level* coarse /* may be NULL */,
