@@ -42,27 +42,82 @@ __host__ __device__ inline size_t eig_off_scale(int N) { return eig_off_Y(N) + (
 __host__ __device__ inline size_t eig_off_meta(int N) { return eig_off_scale(N) + N; }
 int64_t eigh_scratch_elems(int N) { return (int64_t)eig_off_meta(N) + 8; }
 
-// in-place Cholesky (lower) of the N x N matrix in shared memory (row stride ld).
-// returns 0 or failing column + 1 (same value in every thread).
+constexpr int EIG_NB = 16;                        // block size of the blocked factorisations / substitutions
+
+// in-place Cholesky (lower) of the N x N matrix in shared memory (row stride ld), right-looking with
+// EIG_NB-wide panels: the diagonal block is factorised by warp 0 alone (warp-synchronous), the panel
+// below it by one thread per row, the trailing update by the whole CTA -- 3 CTA barriers per panel
+// instead of 3 per column.  returns 0 or failing column + 1 (same value in every thread).
 __device__ int chol_lower(double* S, int N, int ld, int* s_flag) {
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int tpr = nt / N > 0 ? nt / N : 1;            // threads per row of the trailing update
-    for (int k = 0; k < N; ++k) {
-        if (tid == 0) {
-            double d = S[k * ld + k];
-            if (!(d > 0.0)) *s_flag = k + 1;
-            else S[k * ld + k] = sqrt(d);
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    for (int kb = 0; kb < N; kb += EIG_NB) {
+        const int nb = min(EIG_NB, N - kb);
+        double* D = S + (size_t)kb * ld + kb;        // diagonal block, D[i * ld + j]
+        if (tid < 32) {
+            // lane i holds row i of the block in registers; column k is broadcast by shuffles
+            double a[EIG_NB];
+#pragma unroll
+            for (int j = 0; j < EIG_NB; ++j) a[j] = (lane < nb && j <= lane && j < nb) ? D[lane * ld + j] : 0.0;
+            int fail = 0;
+#pragma unroll
+            for (int k = 0; k < EIG_NB; ++k) {
+                if (k < nb) {                                       // warp-uniform
+                    const double d = __shfl_sync(0xffffffffu, a[k], k);
+                    if (!(d > 0.0)) { if (!fail) fail = kb + k + 1; }
+                    const double sq = sqrt(d > 0.0 ? d : 1.0), rd = 1.0 / sq;
+                    if (lane == k) a[k] = sq;
+                    else if (lane > k) a[k] *= rd;
+                    const double lik = a[k];
+#pragma unroll
+                    for (int j = k + 1; j < EIG_NB; ++j) {
+                        const double ljk = __shfl_sync(0xffffffffu, a[k], j);
+                        if (j < nb && lane >= j) a[j] -= lik * ljk;
+                    }
+                }
+            }
+            if (fail) { if (lane == 0) *s_flag = fail; }
+            else if (lane < nb) {
+#pragma unroll
+                for (int j = 0; j < EIG_NB; ++j)
+                    if (j <= lane && j < nb) D[lane * ld + j] = a[j];
+            }
         }
         __syncthreads();
         if (*s_flag) return *s_flag;
-        const double rdk = 1.0 / S[k * ld + k];
-        for (int i = k + 1 + tid; i < N; i += nt) S[i * ld + k] *= rdk;
-        __syncthreads();
-        for (int i = k + 1 + tid / tpr; i < N; i += nt / tpr) {
-            const double lik = S[i * ld + k];
-            for (int j = k + 1 + tid % tpr; j <= i; j += tpr) S[i * ld + j] -= lik * S[j * ld + k];
+        const int r = N - kb - nb;                   // rows below the panel
+        if (r > 0) {
+            // panel: x L_d^T = a for every row below (forward substitution, one thread per row)
+            if (tid < r) {
+                double* ap = S + (size_t)(kb + nb + tid) * ld + kb;
+                double a[EIG_NB];
+#pragma unroll
+                for (int k = 0; k < EIG_NB; ++k) a[k] = k < nb ? ap[k] : 0.0;
+#pragma unroll
+                for (int k = 0; k < EIG_NB; ++k) {
+                    if (k < nb) {
+                        double v = a[k];
+#pragma unroll
+                        for (int q = 0; q < EIG_NB; ++q)
+                            if (q < k) v -= a[q] * D[k * ld + q];
+                        a[k] = v / D[k * ld + k];
+                        ap[k] = a[k];
+                    }
+                }
+            }
+            __syncthreads();
+            // trailing update S[i][j] -= sum_k S[i][kb+k] S[j][kb+k], i >= j in the trailing block
+            for (int t = tid; t < r * r; t += nt) {
+                const int i = t / r, j = t - i * r;
+                if (j <= i) {
+                    const double* pi = S + (size_t)(kb + nb + i) * ld + kb;
+                    const double* pj = S + (size_t)(kb + nb + j) * ld + kb;
+                    double v = 0.0;
+                    for (int k = 0; k < nb; ++k) v = fma(pi[k], pj[k], v);
+                    S[(size_t)(kb + nb + i) * ld + kb + nb + j] -= v;
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
     return 0;
 }
@@ -134,17 +189,40 @@ k_eigh_prepare(const double* __restrict__ GK, const double* __restrict__ GM, int
     }
     __threadfence_block();
     __syncthreads();
-    // ---- Y = L^-1 R in place (Y lower triangular), right-looking: once row i is final it is
-    //      eliminated from all later rows by the whole CTA (column i of L = row i of Lt, contiguous)
-    for (int i = 0; i < N; ++i) {
-        const double* Lcol = Lt + (size_t)i * N;     // Lcol[i'] = L[i'][i]
-        const double rd = 1.0 / Lcol[i];
-        for (int j = tid; j <= i; j += nt) S[i * ld + j] *= rd;
+    // ---- Y = L^-1 R in place (Y lower triangular), blocked forward substitution: the EIG_NB rows of a
+    //      block are solved by one thread per column against the diagonal block of L (staged in shared
+    //      memory), then eliminated from all later rows by the whole CTA -- 3 barriers per block of rows
+    double* Ld = s_scale + N + 4;                    // [EIG_NB][EIG_NB] diagonal block of L
+    for (int kb = 0; kb < N; kb += EIG_NB) {
+        const int nb = min(EIG_NB, N - kb);
+        for (int t = tid; t < nb * nb; t += nt) {
+            const int k = t / nb, q = t - k * nb;    // Ld[k][q] = L[kb+k][kb+q] = Lt[(kb+q) * N + kb+k]
+            Ld[k * EIG_NB + q] = Lt[(size_t)(kb + q) * N + kb + k];
+        }
         __syncthreads();
-        const int w = i + 1, cnt = (N - i - 1) * w;
-        for (int t = tid; t < cnt; t += nt) {
-            const int ii = i + 1 + t / w, j = t % w;
-            S[ii * ld + j] -= Lcol[ii] * S[i * ld + j];
+        const int w = kb + nb;                       // non-zero columns of these rows
+        if (tid < w) {
+            double y[EIG_NB];
+#pragma unroll
+            for (int k = 0; k < EIG_NB; ++k) {
+                if (k < nb) {
+                    double v = S[(size_t)(kb + k) * ld + tid];
+#pragma unroll
+                    for (int q = 0; q < EIG_NB; ++q)
+                        if (q < k) v -= Ld[k * EIG_NB + q] * y[q];
+                    y[k] = v / Ld[k * EIG_NB + k];
+                    S[(size_t)(kb + k) * ld + tid] = y[k];
+                }
+            }
+        }
+        __syncthreads();
+        const int r = N - kb - nb;
+        for (int t = tid; t < r * w; t += nt) {
+            const int ii = t / w, j = t - ii * w;
+            const int i = kb + nb + ii;
+            double v = 0.0;
+            for (int q = 0; q < nb; ++q) v = fma(Lt[(size_t)(kb + q) * N + i], S[(size_t)(kb + q) * ld + j], v);
+            S[(size_t)i * ld + j] -= v;
         }
         __syncthreads();
     }
@@ -376,18 +454,40 @@ k_eigh_finish(int N, const __grid_constant__ EigIdx ix, double* __restrict__ the
         theta[rk] = tj;
     }
     __syncthreads();
-    // ---- c_j^T = y_j R^-1 for all rows j at once (x R = y, R lower triangular), right-looking:
-    //      column k of every x is final after the division, then it is eliminated from columns k' < k
-    //      with row k of R (contiguous); scaled and placed in column rank_j below
-    for (int k = N - 1; k >= 0; --k) {
-        const double* Rk = Rg + (size_t)k * N;       // Rk[k'] = R[k][k'], k' <= k
-        const double rd = 1.0 / Rk[k];
-        for (int j = tid; j < N; j += nt) S[(size_t)j * ld + k] *= rd;
+    // ---- c_j^T = y_j R^-1 for all rows j at once (x R = y, R lower triangular), blocked back substitution from
+    //      the last block of columns: one thread per row solves the EIG_NB unknowns of the block against the
+    //      diagonal block of R (staged in shared memory), then the whole CTA eliminates them from the columns to
+    //      the left -- 3 barriers per block of columns; scaled and placed in column rank_j below
+    double* Rd = reinterpret_cast<double*>(s_flag + 2 + (N & 1));   // 8-byte aligned, [EIG_NB][EIG_NB]
+    for (int kb = ((N - 1) / EIG_NB) * EIG_NB; kb >= 0; kb -= EIG_NB) {
+        const int nb = min(EIG_NB, N - kb);
+        for (int t = tid; t < nb * nb; t += nt) {
+            const int k = t / nb, q = t - k * nb;    // Rd[k][q] = R[kb+k][kb+q]
+            Rd[k * EIG_NB + q] = Rg[(size_t)(kb + k) * N + kb + q];
+        }
         __syncthreads();
-        const int cnt = N * k;
-        for (int t = tid; t < cnt; t += nt) {
-            const int j = t / k, kp = t - j * k;
-            S[(size_t)j * ld + kp] -= S[(size_t)j * ld + k] * Rk[kp];
+        if (tid < N) {
+            double* xr = S + (size_t)tid * ld + kb;
+            double x[EIG_NB];
+#pragma unroll
+            for (int k = EIG_NB - 1; k >= 0; --k) {
+                if (k < nb) {
+                    double v = xr[k];
+#pragma unroll
+                    for (int q = EIG_NB - 1; q >= 0; --q)
+                        if (q > k && q < nb) v -= x[q] * Rd[q * EIG_NB + k];
+                    x[k] = v / Rd[k * EIG_NB + k];
+                    xr[k] = x[k];
+                }
+            }
+        }
+        __syncthreads();
+        for (int t = tid; t < N * kb; t += nt) {
+            const int j = t / kb, kp = t - j * kb;
+            const double* xr = S + (size_t)j * ld + kb;
+            double v = 0.0;
+            for (int q = 0; q < nb; ++q) v = fma(xr[q], Rg[(size_t)(kb + q) * N + kp], v);
+            S[(size_t)j * ld + kp] -= v;
         }
         __syncthreads();
     }
@@ -405,10 +505,12 @@ int eigh_generalized_f64(const double* GK, const double* GM, int N, int64_t ldg,
     ProfScope prof(PROF_EIGH, stream);
     EigIdx ix;
     for (int i = 0; i < EIG_MAXN; ++i) ix.v[i] = (short)(i < N ? (idx_host ? idx_host[i] : i) : 0);
-    const size_t smem = ((size_t)N * (N + 2) + 2 * N + 2) * sizeof(double) + (N + 4) * sizeof(int);
+    const size_t smem = ((size_t)N * (N + 2) + 2 * N + 2) * sizeof(double) + (N + 4) * sizeof(int) +
+                        (EIG_NB * EIG_NB + 8) * sizeof(double);
     static bool attr = false;
     if (!attr) {
-        const int mx = (int)(((size_t)EIG_MAXN * (EIG_MAXN + 2) + 2 * EIG_MAXN + 2) * sizeof(double) + (EIG_MAXN + 4) * sizeof(int));
+        const int mx = (int)(((size_t)EIG_MAXN * (EIG_MAXN + 2) + 2 * EIG_MAXN + 2) * sizeof(double) +
+                             (EIG_MAXN + 4) * sizeof(int) + (EIG_NB * EIG_NB + 8) * sizeof(double));
         DS_CUDA(cudaFuncSetAttribute(k_eigh_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
         DS_CUDA(cudaFuncSetAttribute(k_eigh_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
         attr = true;

@@ -10,7 +10,8 @@ int spmm_km(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, const dou
             int64_t ldy0, double* Y, int64_t ldy, cudaStream_t stream);
 int spmm_dual(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, const double* Kval, const double* Mblk,
               const double* X, int64_t ldx, int ncols, double* YK, int64_t ldyk, double* YM, int64_t ldym,
-              cudaStream_t stream);
+              cudaStream_t stream, const int32_t* order = nullptr, const int32_t* chunk_row = nullptr, int nchunks = 0);
+int spmm32_chunk_count(int64_t n_nodes);
 int block_jacobi(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, const double* Kval, const double* Mblk,
                  double shift, double* invD, cudaStream_t stream);
 // `degree` block-Jacobi Chebyshev steps on K + shift*M applied to R; result points at Z0 or Z1.

@@ -342,7 +342,8 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
     // ---- initial Rayleigh-Ritz on X
     cur = 0;
     DS_CUDA(cudaMemcpy2DAsync(Xb(0), ld * 8, X, m * 8, m * 8, n, cudaMemcpyDeviceToDevice, st));
-    DS_TRY(spmm_dual(brow, bcol, n_nodes, Kval, Mblk, Xb(0), ld, m, KS[0], ld, MS[0], ld, st));
+    DS_TRY(spmm_dual(brow, bcol, n_nodes, Kval, Mblk, Xb(0), ld, m, KS[0], ld, MS[0], ld, st, fine.perm, fine.chunk_row,
+                     spmm32_chunk_count(n_nodes)));
     spmm_count += 2;
     std::vector<int> idx(144);
     auto rr = [&](int w, int nx, int nw, int np, const std::vector<int>& slots) -> int {
@@ -430,7 +431,8 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
         // ---- W <- W - X (MX^T W)
         DS_TRY(gram_f64(MS[cur], ld, m, Wb(cur), ld, wpad, n, GK, 144, gram_partial, st));
         DS_TRY(block_gemm_f64(Xb(cur), ld, m, GK, 144, wpad, n, -1.0, 1.0, Wb(cur), ld, st));
-        DS_TRY(spmm_dual(brow, bcol, n_nodes, Kval, Mblk, Wb(cur), ld, wpad, KS[cur] + m, ld, MS[cur] + m, ld, st));
+        DS_TRY(spmm_dual(brow, bcol, n_nodes, Kval, Mblk, Wb(cur), ld, wpad, KS[cur] + m, ld, MS[cur] + m, ld, st, fine.perm,
+                         fine.chunk_row, spmm32_chunk_count(n_nodes)));
         spmm_count += 2;
         // ---- Rayleigh-Ritz on [X, W(na), P(valid slots)]
         std::vector<int> pvalid;   // P slots whose X column is still active

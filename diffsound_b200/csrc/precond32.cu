@@ -892,6 +892,8 @@ static int s32v_grid(int64_t n_nodes) {
     return (int)(want < sms ? want : sms);
 }
 
+int spmm32_chunk_count(int64_t n_nodes) { return s32v_grid(n_nodes); }
+
 int spmm32_chunks(const int32_t* brow, int64_t n_nodes, int32_t* chunk_row, cudaStream_t st) {
     const int nchunks = s32v_grid(n_nodes);
     k_chunk_rows<<<ceil_div(nchunks + 1, 128), 128, 0, st>>>(brow, (int)n_nodes, nchunks, chunk_row);

@@ -134,6 +134,123 @@ k_spmm_dual(const int32_t* __restrict__ brow, const int32_t* __restrict__ bcol, 
         }
 }
 
+// L1-resident variant used inside the eigensolver: one 768-thread CTA per SM sweeps a contiguous chunk of an
+// ORDERED row list (order[r]: the Morton order of the preconditioner level, or identity), 23 warps taking
+// consecutive list entries through a shared-memory ticket, so the X rows gathered by the rows in flight overlap
+// and are served by the SM's L1 (nothing is permuted in memory: only the order in which rows are visited changes).
+// K values, column ids and M scalars are read once: loaded with L1::no_allocate and pulled into L2 ahead of
+// the consumers by the 24th warp (bulk L2 prefetches, one row per lane).
+constexpr int SD2_THREADS = 768;
+constexpr int SD2_AHEAD = 96;
+
+__device__ __forceinline__ double ldg_na_f64(const double* p) {
+    double v;
+    asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ldg_na_s32(const int32_t* p) {
+    int v;
+    asm("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_na_f64(double* p, double v) {
+    asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2_run(const void* p, int64_t bytes) {      // any alignment
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uintptr_t lo = a & ~uintptr_t(15), hi = (a + bytes + 15) & ~uintptr_t(15);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"((uint32_t)(hi - lo)) : "memory");
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(SD2_THREADS, 1)
+k_spmm_dual_v2(const int32_t* __restrict__ brow, const int32_t* __restrict__ bcol, const int32_t* __restrict__ order,
+               const int32_t* __restrict__ chunk_row, const double* __restrict__ Kval,
+               const double* __restrict__ Mblk, const double* __restrict__ X, int64_t ldx, double* __restrict__ YK,
+               int64_t ldyk, double* __restrict__ YM, int64_t ldym) {
+    __shared__ int s_ticket;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, half = lane >> 4, cl = lane & 15;
+    const int r_lo = chunk_row[blockIdx.x], r_hi = chunk_row[blockIdx.x + 1];
+    if (tid == 0) s_ticket = 0;
+    __syncthreads();
+    if (warp == SD2_THREADS / 32 - 1) {
+        // prefetcher: stay SD2_AHEAD list entries ahead of the ticket
+        for (int base = r_lo; base < r_hi; base += 32) {
+            while (base > r_lo + *(volatile int*)&s_ticket + SD2_AHEAD) __nanosleep(200);
+            const int r = base + lane;
+            if (r < r_hi) {
+                const int row = order ? order[r] : r;
+                const int64_t b0 = brow[row];
+                const int64_t deg = brow[row + 1] - b0;
+                if (deg > 0) {
+                    prefetch_l2_run(Kval + 9 * b0, 72 * deg);
+                    prefetch_l2_run(bcol + b0, 4 * deg);
+                    prefetch_l2_run(Mblk + b0, 8 * deg);
+                }
+            }
+        }
+        return;
+    }
+    for (;;) {
+        int rr = 0;
+        if (lane == 0) rr = atomicAdd(&s_ticket, 1);
+        rr = __shfl_sync(0xffffffffu, rr, 0);
+        if (r_lo + rr >= r_hi) break;
+        const int64_t row = order ? order[r_lo + rr] : r_lo + rr;
+        const int64_t b0 = brow[row];
+        const int deg = (int)(brow[row + 1] - b0);
+        double acc[3][CPL], accm[3][CPL];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int t = 0; t < CPL; ++t) acc[c][t] = accm[c][t] = 0.0;
+        const double* kbase = Kval + 9 * b0;
+        const int64_t rs = 3 * (int64_t)deg;
+        for (int p = half; p < deg; p += 2) {
+            const int64_t j = __ldg(bcol + b0 + p);
+            const double* xr = X + 3 * j * ldx + cl;
+            double x[3][CPL];
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+#pragma unroll
+                for (int t = 0; t < CPL; ++t) x[d][t] = __ldg(xr + d * ldx + 16 * t);
+            const double* kp = kbase + 3 * p;
+            double k[3][3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int d = 0; d < 3; ++d) k[c][d] = __ldg(kp + c * rs + d);      // line reuse across p: keep in L1
+            const double m = __ldg(Mblk + b0 + p);
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int t = 0; t < CPL; ++t) {
+                    double a = acc[c][t];
+                    a = fma(k[c][0], x[0][t], a);
+                    a = fma(k[c][1], x[1][t], a);
+                    a = fma(k[c][2], x[2][t], a);
+                    acc[c][t] = a;
+                    accm[c][t] = fma(m, x[c][t], accm[c][t]);
+                }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int t = 0; t < CPL; ++t) {
+                acc[c][t] += __shfl_xor_sync(0xffffffffu, acc[c][t], 16);
+                accm[c][t] += __shfl_xor_sync(0xffffffffu, accm[c][t], 16);
+            }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int t = 0; t < CPL; ++t) {
+                const int64_t col = cl + 16 * t;
+                if (half == 0) st_na_f64(YK + (3 * row + c) * ldyk + col, acc[c][t]);
+                else st_na_f64(YM + (3 * row + c) * ldym + col, accm[c][t]);
+            }
+    }
+}
+
 // One Chebyshev step on A = K + shift*M with block-Jacobi scaling:
 //   z_new = z + ab (z - z_prev) + cc * invD (R - A z)      (z_prev buffer is overwritten by z_new)
 // first == true:  z_new = cc * invD R   (z = 0)
@@ -265,12 +382,26 @@ int spmm_km(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, const dou
 
 int spmm_dual(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, const double* Kval, const double* Mblk,
               const double* X, int64_t ldx, int ncols, double* YK, int64_t ldyk, double* YM, int64_t ldym,
-              cudaStream_t stream) {
+              cudaStream_t stream, const int32_t* order, const int32_t* chunk_row, int nchunks) {
     DS_REQUIRE(ncols > 0 && ncols % 16 == 0 && ncols <= 128, "spmm: ncols=%d must be a multiple of 16 <= 128", ncols);
     DS_REQUIRE(brow && bcol && Kval && Mblk && X && YK && YM, "spmm_k_and_m: null argument");
     unsigned g = row_blocks(n_nodes);
     int cpl = ncols / 16;
     ProfScope prof(PROF_SPMM, stream);
+    if (chunk_row && nchunks > 0 && cpl <= 3) {
+        // ordered sweep, one CTA per chunk (= per SM), all of the SM's 256 KB as L1
+        auto go = [&](auto kern) -> int {
+            static bool carved = false;
+            if (!carved) {
+                DS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
+                carved = true;
+            }
+            kern<<<nchunks, SD2_THREADS, 0, stream>>>(brow, bcol, order, chunk_row, Kval, Mblk, X, ldx, YK, ldyk, YM, ldym);
+            DS_LAUNCH_CHECK();
+            return DS_OK;
+        };
+        return cpl == 1 ? go(k_spmm_dual_v2<1>) : (cpl == 2 ? go(k_spmm_dual_v2<2>) : go(k_spmm_dual_v2<3>));
+    }
     DS_DISPATCH_CPL(cpl, (k_spmm_dual<CPL><<<g, 256, 0, stream>>>(brow, bcol, n_nodes, Kval, Mblk, X, ldx, YK, ldyk, YM,
                                                                   ldym)));
     DS_LAUNCH_CHECK();
