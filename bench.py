@@ -293,7 +293,7 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     if stats and "cheb_step" in prof and stats.get("cheb_steps"):
-        # One fine-level FP32 SpMM launch (k_spmm32) streams one 40-byte record per 3x3 block (9 fp32 K
+        # One fine-level FP32 SpMM launch (k_spmm32v) streams one 40-byte record per 3x3 block (9 fp32 K
         # values + bcol), brow (4 B) and the 3x3 block-Jacobi inverse (36 B) per node, reads the gathered
         # block Z once plus R and Zprev, and writes Znew: 4 x n x c x 4 B (3 for the residual launch of a
         # V-cycle, which has no Zprev).
@@ -303,10 +303,20 @@ def main():
         streams = 4.0 - n_resid / steps_total
         per_launch_bytes = nnzb * 40 + n_nodes * (4 + 36) + streams * n * c_avg * 4
         t_avg = prof["cheb_step"]["ms"] / prof["cheb_step"]["count"] * 1e-3     # seconds per launch
-        roof = {"bound": "hbm", "kernel": "k_spmm32 (FP32 block-CSR SpMM on TMA-staged 40 B records, fused Chebyshev "
-                                          "update; the fine-level smoother of the eigensolver's preconditioner)",
+        # DRAM traffic of the same kernel from the committed ncu --set full capture (per launch at the captured
+        # column count), scaled to this run's average column count by the algorithmic-byte ratio
+        traffic = None
+        try:
+            cap = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["k_spmm32v"]
+            cap_alg = nnzb * 40 + n_nodes * (4 + 36) + 4.0 * n * cap["ncols"] * 4
+            traffic = cap["dram_bytes_per_launch"] * per_launch_bytes / cap_alg
+        except Exception:
+            pass
+        roof = {"bound": "hbm", "kernel": "k_spmm32v (FP32 block-CSR SpMM on 40 B records, L1-resident gather in a Morton "
+                                          "node numbering, packed FFMA2, fused Chebyshev update; the fine-level smoother "
+                                          "of the eigensolver's preconditioner)",
                 "achieved": per_launch_bytes / t_avg / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": per_launch_bytes / t_avg / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                "frac": per_launch_bytes / t_avg / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
                 "launches_per_step": steps_total, "avg_launch_ms": t_avg * 1e3, "avg_cols": c_avg,
                 "bytes_per_launch": per_launch_bytes, "share_of_step": prof["cheb_step"]["ms"] / ms}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

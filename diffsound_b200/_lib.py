@@ -65,7 +65,6 @@ SIGNATURES = {
     "ds_k32_pack": (cint, [i32p, i32p, i64, i64, f64p, f64p, dbl, ptr, f32p, ptr]),
     "ds_unique_rows3_count": (cint, [ptr, f32p, i64, C.POINTER(C.c_int64), ptr]),
     "ds_unique_rows3_fill": (cint, [ptr, ptr, ptr, ptr]),
-    "ds_set_spmm32_variant": (None, [cint]),
     "ds_spmm32": (cint, [cint, i32p, ptr, i64, cint, f32p, f32p, f32p, f32p, f32p, dbl, dbl, i32p, ptr]),
     "ds_spmm32_chunk_count": (cint, [i64]),
     "ds_spmm32_chunks": (cint, [i32p, i64, i32p, ptr]),

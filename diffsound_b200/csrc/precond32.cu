@@ -1,5 +1,5 @@
-// FP32 preconditioner kernels of the eigensolver: block-CSR SpMM on 40-byte block records
-// streamed through shared memory by the TMA unit, fused with the Chebyshev / residual epilogue.
+// FP32 preconditioner kernels of the eigensolver: block-CSR SpMM on 40-byte block records with an
+// L1-resident gather, fused with the Chebyshev / residual epilogue.
 //
 // Reference behaviour replaced: none one-to-one -- the reference factorises K - sigma M on the CPU
 // (SciPy SuperLU inside eigsh, /root/reference/src/diffelastic/diff_model.py:356-358) and its own
@@ -8,17 +8,18 @@
 // FP32 (LOBPCG only needs an approximate SPD operator; the eigenpairs themselves stay FP64).
 //
 // Layout: one record per 3x3 block, 10 x 4 bytes = {k00 k01 k02 k10 k11 k12 k20 k21 k22 | bcol},
-// in block-CSR order, so the records of consecutive node rows are ONE contiguous byte range:
-// a tile of S32_ROWS node rows is fetched by a single cp.async.bulk (1-D TMA) into a 2-stage
-// shared-memory ring while the previous tile is being multiplied.  Dense blocks are row-major
-// fp32 (n x c), c in {16, 32, 48, 64}; the 3 rows of a node are contiguous (3c floats), so a
-// gathered neighbour is one 192..768-byte run.
+// in block-CSR order of the level's own node numbering (a Morton curve through the node coordinates
+// when the caller supplies them: consecutive rows then gather overlapping sets of X rows).  Dense
+// blocks are row-major fp32 (n x c), c in {16, 32, 48, 64}; the 3 rows of a node are contiguous
+// (3c floats), so a gathered neighbour is one 192..768-byte run.
 //
-// Mapping: a warp owns one node row at a time (rows of the tile are handed out through a
-// shared-memory ticket, so long and short rows balance); LPR lanes cover the c columns
-// (CPT contiguous columns each, 64/128-bit loads), the 32/LPR lane groups walk alternate
-// blocks of the row and are combined by a butterfly at the end.  Lane groups 0..2 then apply the
-// epilogue for component 0..2 of the node.
+// Mapping (k_spmm32v): one 1024-thread CTA per SM sweeps a contiguous chunk of node rows; a warp owns
+// one node row at a time (rows are handed out through a shared-memory ticket, so long and short
+// rows balance and the ~32 rows in flight are neighbours); LPR lanes cover the c columns (CPT
+// columns each, 64/128-bit loads), the 32/LPR lane groups walk alternate blocks of the row and are
+// combined by a butterfly at the end.  Lane groups 0..2 then apply the epilogue for component 0..2
+// of the node.  The gathered X rows live in the SM's L1 (no shared memory is used, all 256 KB are
+// L1); records, R and Zprev are streamed once with L1::no_allocate behind bulk L2 prefetches.
 #include "common.cuh"
 #include "../../include/diffsound_sm100.h"
 #include "kernels.cuh"
@@ -29,13 +30,7 @@
 
 namespace ds {
 
-constexpr int S32_ROWS = 8;                  // node rows per tile
-constexpr int S32_CAP = 384;                 // block records staged per tile (rest read from global)
-constexpr int S32_THREADS = 128;
 constexpr int S32_REC_BYTES = 40;
-constexpr int S32_STAGE_BYTES = (S32_CAP + 2) * S32_REC_BYTES;   // 15440: multiple of 16
-static_assert(S32_STAGE_BYTES % 16 == 0, "stage must keep 16-byte alignment");
-constexpr int S32_SMEM = 2 * S32_STAGE_BYTES + 64;
 
 enum { S32_PLAIN = S32_MODE_PLAIN, S32_RESID = S32_MODE_RESID, S32_CHEB = S32_MODE_CHEB };
 
@@ -104,203 +99,6 @@ template <bool PEER, int C>
 __device__ __forceinline__ const float* node_rows(const float* __restrict__ X, const PeerTable& tab, uint32_t j) {
     if constexpr (PEER) return tab.p[j >> 28] + (int64_t)(j & 0x0fffffffu) * (3 * C);
     else return X + (int64_t)(int)j * (3 * C);
-}
-
-// acc[c][t] += K[c][d] * X[3j+d][cols of this lane] for one block record
-template <int LPR, int CPT, bool PEER>
-__device__ __forceinline__ void block_fma(const uint2* __restrict__ r, const float* __restrict__ X,
-                                          const PeerTable& tab, int l, float (&acc)[3][CPT]) {
-    constexpr int C = LPR * CPT;
-    const uint2 a0 = r[0], a1 = r[1], a2 = r[2], a3 = r[3], a4 = r[4];
-    const float* xr = node_rows<PEER, C>(X, tab, a4.y);
-    float x[3][CPT];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) ld_row<LPR, CPT>(xr + d * C, l, x[d]);
-    const float k00 = __uint_as_float(a0.x), k01 = __uint_as_float(a0.y), k02 = __uint_as_float(a1.x);
-    const float k10 = __uint_as_float(a1.y), k11 = __uint_as_float(a2.x), k12 = __uint_as_float(a2.y);
-    const float k20 = __uint_as_float(a3.x), k21 = __uint_as_float(a3.y), k22 = __uint_as_float(a4.x);
-#pragma unroll
-    for (int t = 0; t < CPT; ++t) {
-        acc[0][t] = fmaf(k00, x[0][t], fmaf(k01, x[1][t], fmaf(k02, x[2][t], acc[0][t])));
-        acc[1][t] = fmaf(k10, x[0][t], fmaf(k11, x[1][t], fmaf(k12, x[2][t], acc[1][t])));
-        acc[2][t] = fmaf(k20, x[0][t], fmaf(k21, x[1][t], fmaf(k22, x[2][t], acc[2][t])));
-    }
-}
-
-// two independent blocks with all loads issued before the first FMA (memory-level parallelism)
-template <int LPR, int CPT, bool PEER>
-__device__ __forceinline__ void block_fma2(const uint2* __restrict__ ra, const uint2* __restrict__ rb,
-                                           const float* __restrict__ X, const PeerTable& tab, int l,
-                                           float (&acc)[3][CPT]) {
-    constexpr int C = LPR * CPT;
-    const uint2 a0 = ra[0], a1 = ra[1], a2 = ra[2], a3 = ra[3], a4 = ra[4];
-    const uint2 b0 = rb[0], b1 = rb[1], b2 = rb[2], b3 = rb[3], b4 = rb[4];
-    const float* xa = node_rows<PEER, C>(X, tab, a4.y);
-    const float* xb = node_rows<PEER, C>(X, tab, b4.y);
-    float x[3][CPT], y[3][CPT];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        ld_row<LPR, CPT>(xa + d * C, l, x[d]);
-        ld_row<LPR, CPT>(xb + d * C, l, y[d]);
-    }
-    {
-        const float k00 = __uint_as_float(a0.x), k01 = __uint_as_float(a0.y), k02 = __uint_as_float(a1.x);
-        const float k10 = __uint_as_float(a1.y), k11 = __uint_as_float(a2.x), k12 = __uint_as_float(a2.y);
-        const float k20 = __uint_as_float(a3.x), k21 = __uint_as_float(a3.y), k22 = __uint_as_float(a4.x);
-#pragma unroll
-        for (int t = 0; t < CPT; ++t) {
-            acc[0][t] = fmaf(k00, x[0][t], fmaf(k01, x[1][t], fmaf(k02, x[2][t], acc[0][t])));
-            acc[1][t] = fmaf(k10, x[0][t], fmaf(k11, x[1][t], fmaf(k12, x[2][t], acc[1][t])));
-            acc[2][t] = fmaf(k20, x[0][t], fmaf(k21, x[1][t], fmaf(k22, x[2][t], acc[2][t])));
-        }
-    }
-    {
-        const float k00 = __uint_as_float(b0.x), k01 = __uint_as_float(b0.y), k02 = __uint_as_float(b1.x);
-        const float k10 = __uint_as_float(b1.y), k11 = __uint_as_float(b2.x), k12 = __uint_as_float(b2.y);
-        const float k20 = __uint_as_float(b3.x), k21 = __uint_as_float(b3.y), k22 = __uint_as_float(b4.x);
-#pragma unroll
-        for (int t = 0; t < CPT; ++t) {
-            acc[0][t] = fmaf(k00, y[0][t], fmaf(k01, y[1][t], fmaf(k02, y[2][t], acc[0][t])));
-            acc[1][t] = fmaf(k10, y[0][t], fmaf(k11, y[1][t], fmaf(k12, y[2][t], acc[1][t])));
-            acc[2][t] = fmaf(k20, y[0][t], fmaf(k21, y[1][t], fmaf(k22, y[2][t], acc[2][t])));
-        }
-    }
-}
-
-// MODE PLAIN:  Out = A X
-//      RESID:  Out = R - A X
-//      CHEB:   Out = X + ab (X - Zprev) + cc invD (R - A X)      (Zprev may alias Out)
-// PEER: X is this rank's own slab (rows of the epilogue), the gather goes through `tab`.
-template <int LPR, int CPT, int MODE, bool PEER>
-__global__ void __launch_bounds__(S32_THREADS)
-k_spmm32(const int32_t* __restrict__ brow, const uint2* __restrict__ rec, int64_t n_nodes,
-         const float* __restrict__ X, const float* __restrict__ R, const float* __restrict__ invD,
-         const float* Zprev, float* Out, float ab, float cc, const __grid_constant__ PeerTable tab) {
-    constexpr int C = LPR * CPT;
-    constexpr int NG = 32 / LPR;
-    extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * S32_STAGE_BYTES);
-    int* ticket = reinterpret_cast<int*>(full + 2);        // [2]
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int g = lane / LPR, l = lane % LPR;
-    const int64_t n_tiles = (n_nodes + S32_ROWS - 1) / S32_ROWS;
-    if (tid == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
-        ticket[0] = 0;
-        ticket[1] = 0;
-        fence_barrier_init();
-    }
-    __syncthreads();
-    uint32_t phase = 0;     // bit s = parity to wait for on stage s
-
-    auto issue = [&](int s, int64_t lo, int64_t hi) {      // one thread; hi > lo
-        const int64_t al = lo & ~int64_t(1);                // 80-byte pairs keep the source 16-byte aligned
-        const uint32_t bytes = (uint32_t)(((hi - al) * S32_REC_BYTES + 15) & ~int64_t(15));
-        mbar_expect_tx(&full[s], bytes);
-        tma_load_1d(smem + s * S32_STAGE_BYTES, reinterpret_cast<const unsigned char*>(rec) + al * S32_REC_BYTES,
-                    bytes, &full[s]);
-    };
-    auto tile_range = [&](int64_t tile, int64_t& r0, int64_t& r1, int64_t& b0, int64_t& b1) {
-        r0 = tile * S32_ROWS;
-        r1 = min(r0 + (int64_t)S32_ROWS, n_nodes);
-        b0 = brow[r0];
-        b1 = brow[r1];
-    };
-
-    int64_t tile = blockIdx.x;
-    if (tid == 0 && tile < n_tiles) {
-        int64_t r0, r1, b0, b1;
-        tile_range(tile, r0, r1, b0, b1);
-        if (b1 > b0) issue(0, b0, min(b1, b0 + (int64_t)S32_CAP));
-    }
-    for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int s = it & 1;
-        int64_t r0, r1, tb0, tb1;
-        tile_range(tile, r0, r1, tb0, tb1);
-        if (tid == 0) {
-            ticket[s ^ 1] = 0;
-            const int64_t nt = tile + gridDim.x;
-            if (nt < n_tiles) {
-                int64_t nr0, nr1, nb0, nb1;
-                tile_range(nt, nr0, nr1, nb0, nb1);
-                if (nb1 > nb0) issue(s ^ 1, nb0, min(nb1, nb0 + (int64_t)S32_CAP));
-            }
-        }
-        const int64_t staged_hi = min(tb1, tb0 + (int64_t)S32_CAP);
-        if (tb1 > tb0) {
-            mbar_wait(&full[s], (phase >> s) & 1u);
-            phase ^= 1u << s;
-        }
-        // record p of the tile lives at stage + (p - (tb0 & ~1)) * 40
-        const unsigned char* stage = smem + s * S32_STAGE_BYTES;
-        const int64_t sb = tb0 & ~int64_t(1);
-        const unsigned char* gbase = reinterpret_cast<const unsigned char*>(rec);
-        for (;;) {
-            int rr = 0;
-            if (lane == 0) rr = atomicAdd(&ticket[s], 1);
-            rr = __shfl_sync(0xffffffffu, rr, 0);
-            const int64_t row = r0 + rr;
-            if (row >= r1) break;
-            const int64_t rb0 = brow[row], rb1 = brow[row + 1];
-            float acc[3][CPT];
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-#pragma unroll
-                for (int t = 0; t < CPT; ++t) acc[c][t] = 0.f;
-            const int64_t se = min(rb1, staged_hi);          // blocks [rb0, se) are in shared memory
-            int64_t p = rb0 + g;
-            for (; p + NG < se; p += 2 * NG)
-                block_fma2<LPR, CPT, PEER>(reinterpret_cast<const uint2*>(stage + (p - sb) * S32_REC_BYTES),
-                                           reinterpret_cast<const uint2*>(stage + (p + NG - sb) * S32_REC_BYTES), X, tab,
-                                           l, acc);
-            if (p < se) {
-                block_fma<LPR, CPT, PEER>(reinterpret_cast<const uint2*>(stage + (p - sb) * S32_REC_BYTES), X, tab, l, acc);
-                p += NG;
-            }
-            for (; p < rb1; p += NG)                         // overflow of an oversized tile: straight from global
-                block_fma<LPR, CPT, PEER>(reinterpret_cast<const uint2*>(gbase + p * S32_REC_BYTES), X, tab, l, acc);
-#pragma unroll
-            for (int off = LPR; off < 32; off <<= 1)
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-#pragma unroll
-                    for (int t = 0; t < CPT; ++t) acc[c][t] += __shfl_xor_sync(0xffffffffu, acc[c][t], off);
-            if (g < 3) {
-                const int64_t o = (3 * row + g) * C;          // output row of this lane group
-                float a[CPT];
-#pragma unroll
-                for (int t = 0; t < CPT; ++t) a[t] = g == 0 ? acc[0][t] : (g == 1 ? acc[1][t] : acc[2][t]);
-                float v[CPT];
-                if (MODE == S32_PLAIN) {
-#pragma unroll
-                    for (int t = 0; t < CPT; ++t) v[t] = a[t];
-                } else if (MODE == S32_RESID) {
-                    float rv[CPT];
-                    ld_row<LPR, CPT>(R + o, l, rv);
-#pragma unroll
-                    for (int t = 0; t < CPT; ++t) v[t] = rv[t] - a[t];
-                } else {
-                    const float d0 = __ldg(invD + 9 * row + 3 * g), d1 = __ldg(invD + 9 * row + 3 * g + 1),
-                                d2 = __ldg(invD + 9 * row + 3 * g + 2);
-                    float r0v[CPT], r1v[CPT], r2v[CPT], z[CPT], zp[CPT];
-                    const int64_t ob = 3 * row * C;
-                    ld_row<LPR, CPT>(R + ob, l, r0v);
-                    ld_row<LPR, CPT>(R + ob + C, l, r1v);
-                    ld_row<LPR, CPT>(R + ob + 2 * C, l, r2v);
-                    ld_row<LPR, CPT>(X + o, l, z);
-                    ld_row_plain<LPR, CPT>(Zprev + o, l, zp);
-#pragma unroll
-                    for (int t = 0; t < CPT; ++t) {
-                        const float dr = d0 * (r0v[t] - acc[0][t]) + d1 * (r1v[t] - acc[1][t]) + d2 * (r2v[t] - acc[2][t]);
-                        v[t] = z[t] + ab * (z[t] - zp[t]) + cc * dr;
-                    }
-                }
-                st_row<LPR, CPT>(Out + o, l, v);
-            }
-        }
-        __syncthreads();     // every warp is done with stage s (and ticket[s]) before it is refilled
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -458,7 +256,7 @@ template <int LPR, int CPT, int MODE, bool PEER>
 __global__ void __launch_bounds__(S32V_THREADS, 1)
 k_spmm32v(const int32_t* __restrict__ brow, const uint2* __restrict__ rec, const int32_t* __restrict__ chunk_row,
           const float* __restrict__ X, const float* __restrict__ R, const float* __restrict__ invD,
-          const float* Zprev, float* Out, float ab, float cc, const __grid_constant__ PeerTable tab) {
+          const float* Zprev, float* Out, float ab, float cc, int prefetch, const __grid_constant__ PeerTable tab) {
     constexpr int C = LPR * CPT;
     constexpr int NG = 32 / LPR;
     constexpr int NP = CPT / 2;
@@ -484,7 +282,7 @@ k_spmm32v(const int32_t* __restrict__ brow, const uint2* __restrict__ rec, const
         }
         if ((r & 15) == 0) prefetch_l2(brow + min(r + 2 * S32V_PF, r_hi));      // the row pointers themselves
     };
-    if (lane == 0) {
+    if (lane == 0 && prefetch) {
         if (r_lo + warp < r_hi) prefetch_row(r_lo + warp);
         if (r_lo + 32 + warp < r_hi) prefetch_row(r_lo + 32 + warp);
     }
@@ -496,7 +294,7 @@ k_spmm32v(const int32_t* __restrict__ brow, const uint2* __restrict__ rec, const
         rr = __shfl_sync(0xffffffffu, rr, 0);
         const int row = r_lo + rr;
         if (row >= r_hi) break;
-        if (lane == 0 && row + S32V_PF < r_hi) prefetch_row(row + S32V_PF);
+        if (lane == 0 && prefetch && row + S32V_PF < r_hi) prefetch_row(row + S32V_PF);
         const int rb0 = brow[row], rb1 = brow[row + 1];
         u64 acc[3][NP];
 #pragma unroll
@@ -864,23 +662,6 @@ int inject64(const int32_t* rptr, const int32_t* rlist, int64_t n_coarse, const 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static int s32_grid(int64_t n_nodes) {
-    static int ctas_per_sm = 0, sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_spmm32<8, 6, S32_CHEB, false>, S32_THREADS,
-                                                      S32_SMEM);
-        if (ctas_per_sm < 1) ctas_per_sm = 1;
-    }
-    const int64_t tiles = ceil_div(n_nodes, S32_ROWS);
-    const int64_t g = (int64_t)sms * ctas_per_sm;
-    return (int)(tiles < g ? tiles : g);
-}
-
-static int g_spmm32_variant = 2;      // 1: TMA-staged tiles (k_spmm32), 2: L1-resident gather (k_spmm32v)
-
 static int s32v_grid(int64_t n_nodes) {
     static int sms = 0;
     if (!sms) {
@@ -905,20 +686,6 @@ template <int LPR, int CPT, bool PEER>
 static int launch_spmm32(int mode, const int32_t* brow, const void* rec, int64_t n_nodes, const int32_t* chunk_row,
                          const float* X, const float* R, const float* invD, const float* Zprev, float* Out, float ab,
                          float cc, const PeerTable& tab, cudaStream_t st) {
-    if (g_spmm32_variant == 1) {
-        const int grid = s32_grid(n_nodes);
-        auto go = [&](auto kern) -> int {
-            kern<<<grid, S32_THREADS, S32_SMEM, st>>>(brow, reinterpret_cast<const uint2*>(rec), n_nodes, X, R, invD,
-                                                      Zprev, Out, ab, cc, tab);
-            DS_LAUNCH_CHECK();
-            return DS_OK;
-        };
-        switch (mode) {
-            case S32_PLAIN: return go(k_spmm32<LPR, CPT, S32_PLAIN, PEER>);
-            case S32_RESID: return go(k_spmm32<LPR, CPT, S32_RESID, PEER>);
-            default: return go(k_spmm32<LPR, CPT, S32_CHEB, PEER>);
-        }
-    }
     DS_REQUIRE(chunk_row != nullptr, "spmm32: missing row chunks");
     const int grid = s32v_grid(n_nodes);
     auto go = [&](auto kern) -> int {
@@ -927,8 +694,11 @@ static int launch_spmm32(int mode, const int32_t* brow, const void* rec, int64_t
             DS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
             carved = true;
         }
+        // a level whose records and four dense blocks fit in half of the 126 MB L2 stays resident between the
+        // launches of a Chebyshev sequence: the look-ahead prefetch would only add latency to every row
+        const int prefetch = (n_nodes * (int64_t)(30 * S32_REC_BYTES + 48 * LPR * CPT)) > ((int64_t)60 << 20);
         kern<<<grid, S32V_THREADS, 0, st>>>(brow, reinterpret_cast<const uint2*>(rec), chunk_row, X, R, invD, Zprev, Out,
-                                            ab, cc, tab);
+                                            ab, cc, prefetch, tab);
         DS_LAUNCH_CHECK();
         return DS_OK;
     };
@@ -958,7 +728,7 @@ struct ChunkTmp {
     cudaStream_t st;
     int get(const int32_t* brow, int64_t n_nodes, const int32_t* given, cudaStream_t s, const int32_t** out) {
         st = s;
-        if (given || g_spmm32_variant == 1) { *out = given; return DS_OK; }
+        if (given) { *out = given; return DS_OK; }
         DS_CUDA(cudaMallocAsync(&p, sizeof(int32_t) * (s32v_grid(n_nodes) + 1), s));
         DS_TRY(spmm32_chunks(brow, n_nodes, p, s));
         *out = p;
@@ -1191,8 +961,6 @@ int Level32::cheb(const float* r, int ncols, int degree, double ratio, bool from
 }  // namespace ds
 
 using namespace ds;
-
-extern "C" void ds_set_spmm32_variant(int v) { g_spmm32_variant = v == 1 ? 1 : 2; }
 
 extern "C" int64_t ds_k32_record_bytes(int64_t nnzb) { return nnzb * S32_REC_BYTES + 64; }
 

@@ -221,8 +221,7 @@ int ds_spmm32(int mode, const int32_t* brow, const void* rec, int64_t n_nodes, i
  * then builds the chunks into a stream-ordered temporary on every call. */
 int ds_spmm32_chunk_count(int64_t n_nodes);
 int ds_spmm32_chunks(const int32_t* brow, int64_t n_nodes, int32_t* chunk_row, void* stream);
-/* tuning hook: 1 = TMA-staged tile kernel (k_spmm32), 2 = L1-resident gather kernel (k_spmm32v, default) */
-void ds_set_spmm32_variant(int variant);
+
 /* Row-partitioned SpMM for one large mesh on several GPUs of a node: rank r owns
  * a contiguous slab of node rows; the records of its slab carry column ids packed as
  * owner << 28 | index inside the owner's slab (colmap), and the kernel gathers the dense block through

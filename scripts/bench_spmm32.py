@@ -1,8 +1,7 @@
 """Micro-benchmark of the fine-level FP32 SpMM (Chebyshev mode) on the bench mesh: CUDA-event time per launch
-and achieved algorithmic GB/s, for both kernel variants and for the reference (lexicographic) and a
-Morton node numbering.  Also the target of the ncu captures.
+and achieved algorithmic GB/s, for the reference (lexicographic) and a Morton node numbering.  Also the target of the ncu captures.
 
-usage: python scripts/bench_spmm32.py [cube N] [reps] [variants e.g. 12] [orders e.g. lm] [cols e.g. 48,16]"""
+usage: python scripts/bench_spmm32.py [cube N] [reps] [orders e.g. lm] [cols e.g. 48,16]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -13,9 +12,8 @@ from diffsound_b200.diffelastic.deform import Deform
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-variants = [int(c) for c in (sys.argv[3] if len(sys.argv) > 3 else "12")]
-orders = sys.argv[4] if len(sys.argv) > 4 else "lm"
-cols = [int(c) for c in (sys.argv[5] if len(sys.argv) > 5 else "48,32,16").split(",")]
+orders = sys.argv[3] if len(sys.argv) > 3 else "lm"
+cols = [int(c) for c in (sys.argv[4] if len(sys.argv) > 4 else "48,32,16").split(",")]
 dev = torch.device("cuda:0")
 lib = native._lib.load()
 
@@ -47,24 +45,16 @@ for order in orders:
         X = torch.randn(pat.n, c, device=dev)
         R = torch.randn(pat.n, c, device=dev)
         Zp = torch.randn(pat.n, c, device=dev)
-        outs = {}
-        for var in variants:
-            lib.ds_set_spmm32_variant(var)
-            out = torch.empty_like(X)
-            for _ in range(3):
-                native.spmm32(pat, rec, X, mode=2, R=R, invD=invD, Zprev=Zp, ab=0.3, cc=1e-12, out=out)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(reps):
-                native.spmm32(pat, rec, X, mode=2, R=R, invD=invD, Zprev=Zp, ab=0.3, cc=1e-12, out=out)
-            e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / reps
-            nbytes = pat.nnzb * 40 + pat.n_nodes * 40 + 4 * pat.n * c * 4
-            outs[var] = out
-            print(f"order={order} variant={var} c={c}: {ms * 1e3:.1f} us/launch  {nbytes / ms / 1e6:.0f} GB/s algorithmic "
-                  f"({nbytes / 1e6:.0f} MB)", flush=True)
-        if len(outs) == 2:
-            a, b = outs[1], outs[2]
-            print(f"   variants agree to {float((a - b).abs().max() / a.abs().max()):.2e} (relative to max)", flush=True)
-lib.ds_set_spmm32_variant(2)
+        out = torch.empty_like(X)
+        for _ in range(3):
+            native.spmm32(pat, rec, X, mode=2, R=R, invD=invD, Zprev=Zp, ab=0.3, cc=1e-12, out=out)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            native.spmm32(pat, rec, X, mode=2, R=R, invD=invD, Zprev=Zp, ab=0.3, cc=1e-12, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        nbytes = pat.nnzb * 40 + pat.n_nodes * 40 + 4 * pat.n * c * 4
+        print(f"order={order} c={c}: {ms * 1e3:.1f} us/launch  {nbytes / ms / 1e6:.0f} GB/s algorithmic "
+              f"({nbytes / 1e6:.0f} MB)", flush=True)

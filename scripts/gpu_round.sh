@@ -11,7 +11,7 @@ cat gpurun_out/${TAG}_bench.json
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python scripts/profile_step.py 32 1 > gpurun_out/${TAG}_launches.log 2>&1; echo "ncu list rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on \
-    -k regex:'k_spmm32|k_gram_sym|k_assemble_rows|k_eigval_grad_shape|k_block_gemm|k_spmm_dual|k_coarse|k_eigh' \
-    --launch-skip 40 --launch-count 24 -f -o gpurun_out/${TAG}_full python scripts/profile_step.py 32 1 > gpurun_out/${TAG}_full.log 2>&1; echo "ncu full rc=$?"
+    -k regex:'k_spmm32v|k_gram_sym|k_rr_update|k_spmm_dual|k_eigh|k_block_gemm' \
+    --launch-skip 420 --launch-count 30 -f -o gpurun_out/${TAG}_full python scripts/profile_step.py 32 1 > gpurun_out/${TAG}_full.log 2>&1; echo "ncu full rc=$?"
 ncu -i gpurun_out/${TAG}_full.ncu-rep --page raw --csv > gpurun_out/${TAG}_full_raw.csv 2>/dev/null
 ls -la gpurun_out
