@@ -24,7 +24,7 @@ struct ColIdx {
     short v[128];
 };
 enum { S32_MODE_PLAIN = 0, S32_MODE_RESID = 1, S32_MODE_CHEB = 2 };
-// Out = A X | R - A X | X + ab (X - Zprev) + cc invD (R - A X) on 40-byte block records; ncols in {16,32,48,64}
+// Out = A X | R - A X | X + ab (X - Zprev) + cc invD (R - A X) on 48-byte block records; ncols in {16,32,48,64}
 int spmm32(int mode, const int32_t* brow, const void* rec, int64_t n_nodes, int ncols, const float* X, const float* R,
            const float* invD, const float* Zprev, float* Out, float ab, float cc, int prof_cls, cudaStream_t st,
            const int32_t* chunk_row = nullptr);
@@ -34,7 +34,7 @@ int pack_k32(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, const do
              double shift, void* rec, float* invD, cudaStream_t st, const uint32_t* colmap = nullptr,
              int64_t row_offset = 0, const int32_t* perm = nullptr, const int32_t* inv = nullptr,
              const int32_t* brow_out = nullptr);
-int jacobi32(const float* invD, const float* R, int64_t n_nodes, int ncols, float cc, float* Out, cudaStream_t st);
+int jacobi32(const float* invD, const float* R, int64_t n_nodes, int ncols, float cc, float* Out, cudaStream_t st);   // timed as PROF_JACOBI
 // perm_* / inv_*: node renumberings of the levels' private (Morton) orderings, NULL = identity
 int restrict32(const int32_t* rptr, const int32_t* rlist, int64_t n_coarse, const float* res, int ncols, float* rc,
                cudaStream_t st, const int32_t* perm_c = nullptr, const int32_t* inv_f = nullptr);

@@ -68,7 +68,7 @@ static void drain() {
 
 static const char* kNames[PROF_NCLASS] = {"pattern", "geometry", "assemble", "spmm", "cheb_step", "gram", "block_gemm",
                                           "eigh", "residual", "copy", "grad_shape", "quadforms", "synth", "other",
-                                          "coarse_step", "transfer"};
+                                          "coarse_step", "transfer", "jacobi_scale"};
 
 }  // namespace ds
 

@@ -203,8 +203,8 @@ int ds_unique_rows3_fill(ds_workspace* ws, int64_t* inverse, int64_t* first, voi
 
 /* ---- FP32 preconditioner pieces (exported for tests and for callers that build their own cycle) ---
  * No reference counterpart: the reference factorises K - sigma M with SuperLU on the CPU
- * (diff_model.py:356-358).  rec: ds_k32_record_bytes(nnzb) bytes, 16-byte aligned, one 40-byte
- * record {k00..k22 (fp32), bcol} per block of K + shift*M; invD: fp32 [9*n_nodes] inverses of the
+ * (diff_model.py:356-358).  rec: ds_k32_record_bytes(nnzb) bytes, 16-byte aligned, one 48-byte
+ * record {k00..k22 (fp32), bcol, 8 bytes of padding} per block of K + shift*M; invD: fp32 [9*n_nodes] inverses of the
  * diagonal blocks.  ds_spmm32 modes: 0: Out = A X; 1: Out = R - A X; 2 (one Chebyshev step):
  * Out = X + ab (X - Zprev) + cc invD (R - A X), Zprev may alias Out, X must not.  Dense blocks are
  * fp32 row-major [3*n_nodes x ncols] with ld = ncols in {16, 32, 48, 64}. */
