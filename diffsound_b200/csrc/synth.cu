@@ -38,12 +38,16 @@ __device__ __forceinline__ void anchor(float d, float f, int64_t t, double inv_s
     im = dec * s;
 }
 
+// one-sample rotor w = exp((-d + 2 pi i f) / sr).  FP32 transcendental on an argument formed in fp64: the
+// recurrence is re-anchored from an fp64 phase every SY_SEG samples, so the rotor's 1e-7 relative error grows to at
+// most ~2e-6 before it is discarded (audio tolerance 1e-4), and the fp64 sincospi / exp it replaces cost as much
+// as a third of the contraction in the forward kernel.
 __device__ __forceinline__ void rotor(float d, float f, double inv_sr, float& wr, float& wi) {
-    double s, c;
-    sincospi(2.0 * (double)f * inv_sr, &s, &c);
-    double dec = exp(-(double)d * inv_sr);
-    wr = (float)(dec * c);
-    wi = (float)(dec * s);
+    float s, c;
+    sincospif((float)(2.0 * (double)f * inv_sr), &s, &c);
+    const float dec = expf(-(float)((double)d * inv_sr));
+    wr = dec * c;
+    wi = dec * s;
 }
 
 // Fill S[mk][t] (and optionally C[mk][t]) for modes m0..m0+MK, times t0..t0+BT.
@@ -72,196 +76,274 @@ __device__ __forceinline__ void fill_basis(const float* __restrict__ damp, const
 }
 
 // ---------------------------------------------------------------------------
-// forward: grid (ceil(T/BT), ceil(B/BB))
+// forward: grid (ceil(T/BT), ceil(B/SF_BB)).  y tile = 128 batch rows x 128 samples per CTA, 8 x 8 per thread
+// (rows 4 ty + {0..3} and 64 + 4 ty + {0..3}, samples 4 tx + {0..3} and 64 + 4 tx + {0..3}: every shared-memory
+// read is one conflict-free 128-bit load).  Per mode a thread does 4 LDS.128 and 32 packed FFMA2
+// (fma.rn.f32x2 with the amplitude broadcast) = 64 FMAs: the FP32 pipe, not shared-memory bandwidth, is
+// the limit (the 4 x 8 tile with scalar FFMA ran at 96 % of the shared-memory pipe and 41 % of the FMA pipe).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(SY_THREADS)
+constexpr int SF_BB = 128;   // batch rows per forward tile
+
+__device__ __forceinline__ void ffma2_bcast(unsigned long long& acc, float a, unsigned long long s2) {
+    unsigned long long aa;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(aa), "l"(s2));
+}
+
+__global__ void __launch_bounds__(SY_THREADS, 2)
 k_synth_fwd(const float* __restrict__ amp, const float* __restrict__ damp, const float* __restrict__ freq, int64_t B,
             int k, int64_t T, double inv_sr, float* __restrict__ y) {
     __shared__ __align__(16) float S[SY_MK][SY_BT + 4];
-    __shared__ __align__(16) float A[SY_MK][SY_BB + 4];
+    __shared__ __align__(16) float A[SY_MK][SF_BB + 4];
     const int64_t t0 = (int64_t)blockIdx.x * SY_BT;
-    const int64_t b0 = (int64_t)blockIdx.y * SY_BB;
-    const int tx = threadIdx.x & 15;   // 16 x 8 time samples
-    const int ty = threadIdx.x >> 4;   // 16 x 4 batch rows
-    float acc[4][8];
+    const int64_t b0 = (int64_t)blockIdx.y * SF_BB;
+    const int tx = threadIdx.x & 15;   // samples 4 tx + {0..3}, 64 + 4 tx + {0..3}
+    const int ty = threadIdx.x >> 4;   // rows    4 ty + {0..3}, 64 + 4 ty + {0..3}
+    unsigned long long acc[8][4];      // [row][sample pair]
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0ull;
     for (int m0 = 0; m0 < k; m0 += SY_MK) {
         __syncthreads();
         fill_basis<false>(damp, freq, k, m0, t0, inv_sr, S, nullptr);
-        for (int idx = threadIdx.x; idx < SY_MK * SY_BB; idx += SY_THREADS) {
+        for (int idx = threadIdx.x; idx < SY_MK * SF_BB; idx += SY_THREADS) {
             int bb = idx / SY_MK, mk = idx - bb * SY_MK;   // consecutive threads read consecutive modes
             int64_t b = b0 + bb;
             int m = m0 + mk;
             A[mk][bb] = (b < B && m < k) ? __ldg(amp + b * k + m) : 0.f;
         }
         __syncthreads();
-#pragma unroll 8
+#pragma unroll 4
         for (int mk = 0; mk < SY_MK; ++mk) {
-            float4 a4 = *reinterpret_cast<const float4*>(&A[mk][ty * 4]);
-            float4 s0 = *reinterpret_cast<const float4*>(&S[mk][tx * 8]);
-            float4 s1 = *reinterpret_cast<const float4*>(&S[mk][tx * 8 + 4]);
-            float a[4] = {a4.x, a4.y, a4.z, a4.w};
-            float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            const float4 a0 = *reinterpret_cast<const float4*>(&A[mk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&A[mk][64 + ty * 4]);
+            const ulonglong2 s0 = *reinterpret_cast<const ulonglong2*>(&S[mk][tx * 4]);
+            const ulonglong2 s1 = *reinterpret_cast<const ulonglong2*>(&S[mk][64 + tx * 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], s[j], acc[i][j]);
+            for (int i = 0; i < 8; ++i) {
+                ffma2_bcast(acc[i][0], a[i], s0.x);
+                ffma2_bcast(acc[i][1], a[i], s0.y);
+                ffma2_bcast(acc[i][2], a[i], s1.x);
+                ffma2_bcast(acc[i][3], a[i], s1.y);
+            }
         }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        int64_t b = b0 + ty * 4 + i;
+    for (int i = 0; i < 8; ++i) {
+        const int64_t b = b0 + (i < 4 ? 4 * ty + i : 64 + 4 * ty + (i - 4));
         if (b >= B) continue;
-        int64_t t = t0 + tx * 8;
-        float* yp = y + b * T + t;
-        if (t + 8 <= T && ((reinterpret_cast<uintptr_t>(yp) & 15) == 0)) {
-            *reinterpret_cast<float4*>(yp) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-            *reinterpret_cast<float4*>(yp + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
-        } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (t + j < T) yp[j] = acc[i][j];
+        for (int h = 0; h < 2; ++h) {
+            const int64_t t = t0 + 64 * h + 4 * tx;
+            float v[4];
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(v[0]), "=f"(v[1]) : "l"(acc[i][2 * h]));
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(v[2]), "=f"(v[3]) : "l"(acc[i][2 * h + 1]));
+            float* yp = y + b * T + t;
+            if (t + 4 <= T && ((reinterpret_cast<uintptr_t>(yp) & 15) == 0)) {
+                *reinterpret_cast<float4*>(yp) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (t + j < T) yp[j] = v[j];
+            }
         }
     }
 }
 
 // ---------------------------------------------------------------------------
-// backward 1: gamp partials.  grid (n_chunks over T, ceil(B/BB), ceil(k/MK)); each CTA owns a
-// 64 x 32 (batch x mode) output tile and a contiguous run of time tiles.
+// backward 1: gamp[b,m] = sum_t gy[b,t] s_m(t), partial sums per time chunk.
+// grid (n_chunks over T, ceil(B/128), ceil(k/128)); each CTA owns a 128 x 128 (batch x mode) output tile and a
+// contiguous run of 32-sample slabs; 8 x 8 outputs per thread (rows 4 ty + {0..3}, 64 + 4 ty + {0..3}; modes
+// 4 tx + {0..3}, 64 + 4 tx + {0..3}).  Both operands are staged TRANSPOSED (sample-major), so per sample a thread
+// does 4 conflict-free LDS.128 and 32 FFMA2 -- the same FP32-pipe-bound inner loop as the forward kernel.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(SY_THREADS)
+constexpr int SB_TT = 32;    // samples per staged slab
+constexpr int SB_W = 128;    // tile width (batch rows, modes or samples)
+
+__global__ void __launch_bounds__(SY_THREADS, 2)
 k_synth_bwd_amp(const float* __restrict__ damp, const float* __restrict__ freq, const float* __restrict__ gy,
-                int64_t B, int k, int64_t T, double inv_sr, int tiles_per_chunk, float* __restrict__ partial) {
-    __shared__ __align__(16) float S[SY_MK][SY_BT + 4];
-    constexpr int HT = SY_BT / 2;   // gy is staged half a time tile at a time (48 KB static limit)
-    __shared__ __align__(16) float Gy[SY_BB][HT + 4];
-    const int64_t b0 = (int64_t)blockIdx.y * SY_BB;
-    const int m0 = blockIdx.z * SY_MK;
-    const int tx = threadIdx.x & 7;    // 8 x 4 modes
-    const int ty = threadIdx.x >> 3;   // 32 x 2 batch rows
-    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-    const int64_t n_tiles = (T + SY_BT - 1) / SY_BT;
-    const int64_t tile_lo = (int64_t)blockIdx.x * tiles_per_chunk;
-    const int64_t tile_hi = min(n_tiles, tile_lo + tiles_per_chunk);
-    for (int64_t tile = tile_lo; tile < tile_hi; ++tile) {
-        const int64_t t0 = tile * SY_BT;
-        __syncthreads();
-        fill_basis<false>(damp, freq, k, m0, t0, inv_sr, S, nullptr);
-        for (int h = 0; h < 2; ++h) {
-            if (h) __syncthreads();
-            for (int idx = threadIdx.x; idx < SY_BB * HT; idx += SY_THREADS) {
-                int bb = idx / HT, tt = idx - bb * HT;
-                int64_t b = b0 + bb, t = t0 + h * HT + tt;
-                Gy[bb][tt] = (b < B && t < T) ? __ldg(gy + b * T + t) : 0.f;
-            }
-            __syncthreads();
-#pragma unroll 4
-            for (int tt = 0; tt < HT; tt += 4) {
-                float4 g0 = *reinterpret_cast<const float4*>(&Gy[ty * 2][tt]);
-                float4 g1 = *reinterpret_cast<const float4*>(&Gy[ty * 2 + 1][tt]);
+                int64_t B, int k, int64_t T, double inv_sr, int slabs_per_chunk, float* __restrict__ partial) {
+    __shared__ __align__(16) float ST[SB_TT][SB_W + 4];    // [sample][mode]
+    __shared__ __align__(16) float GT[SB_TT][SB_W + 4];    // [sample][batch row]
+    const int64_t b0 = (int64_t)blockIdx.y * SB_W;
+    const int m0 = blockIdx.z * SB_W;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    unsigned long long acc[8][4];      // [row][mode pair]
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float4 s = *reinterpret_cast<const float4*>(&S[tx * 4 + j][h * HT + tt]);
-                    acc[0][j] = fmaf(g0.x, s.x, fmaf(g0.y, s.y, fmaf(g0.z, s.z, fmaf(g0.w, s.w, acc[0][j]))));
-                    acc[1][j] = fmaf(g1.x, s.x, fmaf(g1.y, s.y, fmaf(g1.z, s.z, fmaf(g1.w, s.w, acc[1][j]))));
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0ull;
+    const int64_t n_slabs = (T + SB_TT - 1) / SB_TT;
+    const int64_t slab_lo = (int64_t)blockIdx.x * slabs_per_chunk;
+    const int64_t slab_hi = min(n_slabs, slab_lo + slabs_per_chunk);
+    // basis generator of this thread: one mode, one 16-sample segment of every slab
+    const int gm = threadIdx.x & (SB_W - 1), gseg = threadIdx.x >> 7;
+    float gd = 0.f, gf = 0.f, wr = 0.f, wi = 0.f;
+    const bool gvalid = m0 + gm < k;
+    if (gvalid) {
+        gd = __ldg(damp + m0 + gm);
+        gf = __ldg(freq + m0 + gm);
+        rotor(gd, gf, inv_sr, wr, wi);
+    }
+    for (int64_t slab = slab_lo; slab < slab_hi; ++slab) {
+        const int64_t t0 = slab * SB_TT;
+        __syncthreads();
+        {
+            float re = 0.f, im = 0.f;
+            if (gvalid) anchor(gd, gf, t0 + gseg * SY_SEG, inv_sr, re, im);
+#pragma unroll
+            for (int j = 0; j < SY_SEG; ++j) {
+                ST[gseg * SY_SEG + j][gm] = im;
+                const float nr = re * wr - im * wi;
+                im = re * wi + im * wr;
+                re = nr;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < (SB_W * SB_TT / 4) / SY_THREADS; ++r) {
+            const int idx = threadIdx.x + r * SY_THREADS;
+            const int bb = idx & (SB_W - 1), q = idx >> 7;          // 4 samples 4 q .. 4 q + 3 of row bb
+            const int64_t b = b0 + bb, t = t0 + 4 * q;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (b < B) {
+                const float* gp = gy + b * T + t;
+                if (t + 4 <= T && (reinterpret_cast<uintptr_t>(gp) & 15) == 0) {
+                    const float4 w = __ldg(reinterpret_cast<const float4*>(gp));
+                    v[0] = w.x; v[1] = w.y; v[2] = w.z; v[3] = w.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (t + e < T) v[e] = __ldg(gp + e);
                 }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) GT[4 * q + e][bb] = v[e];
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int tt = 0; tt < SB_TT; ++tt) {
+            const float4 g0 = *reinterpret_cast<const float4*>(&GT[tt][ty * 4]);
+            const float4 g1 = *reinterpret_cast<const float4*>(&GT[tt][64 + ty * 4]);
+            const ulonglong2 s0 = *reinterpret_cast<const ulonglong2*>(&ST[tt][tx * 4]);
+            const ulonglong2 s1 = *reinterpret_cast<const ulonglong2*>(&ST[tt][64 + tx * 4]);
+            const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                ffma2_bcast(acc[i][0], g[i], s0.x);
+                ffma2_bcast(acc[i][1], g[i], s0.y);
+                ffma2_bcast(acc[i][2], g[i], s1.x);
+                ffma2_bcast(acc[i][3], g[i], s1.y);
             }
         }
     }
     // partial[chunk][b][m]
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        int64_t b = b0 + ty * 2 + i;
+    for (int i = 0; i < 8; ++i) {
+        const int64_t b = b0 + (i < 4 ? 4 * ty + i : 64 + 4 * ty + (i - 4));
         if (b >= B) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int m = m0 + tx * 4 + j;
-            if (m < k) partial[((int64_t)blockIdx.x * B + b) * k + m] = acc[i][j];
+        for (int h = 0; h < 2; ++h) {
+            const int m = m0 + 64 * h + 4 * tx;
+            float v[4];
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(v[0]), "=f"(v[1]) : "l"(acc[i][2 * h]));
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(v[2]), "=f"(v[3]) : "l"(acc[i][2 * h + 1]));
+            float* pp = partial + ((int64_t)blockIdx.x * B + b) * k + m;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (m + e < k) pp[e] = v[e];
         }
     }
 }
 
 // ---------------------------------------------------------------------------
-// backward 2: z = A^T gy per (mode chunk, time tile), contracted at once with -tau s and 2 pi tau c.
-// grid (ceil(T/BT), ceil(k/MK)); partial[tile][2][k]
+// backward 2: z[m,t] = sum_b a[b,m] gy[b,t] per (128 modes x 128 samples) tile, 8 x 8 per thread with the same
+// FFMA2 inner loop (reduction over the batch in slabs of 32 rows), contracted in registers with -tau s_m(t) and
+// 2 pi tau c_m(t) (basis regenerated per thread from fp64 anchors), reduced over the 16 sample lanes by shuffles.
+// grid (ceil(T/128), ceil(k/128)); partial[tile][2][k]
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(SY_THREADS)
+__global__ void __launch_bounds__(SY_THREADS, 2)
 k_synth_bwd_df(const float* __restrict__ amp, const float* __restrict__ damp, const float* __restrict__ freq,
                const float* __restrict__ gy, int64_t B, int k, int64_t T, double inv_sr,
                float* __restrict__ partial) {
-    // the (A, Gy) staging tiles of the batch loop and the (S, C) basis tiles of the epilogue share storage
-    __shared__ __align__(16) float raw[2 * SY_MK * (SY_BT + 4)];
-    __shared__ float red[2][SY_MK][17];
-    float (*S)[SY_BT + 4] = reinterpret_cast<float (*)[SY_BT + 4]>(raw);
-    float (*Cc)[SY_BT + 4] = reinterpret_cast<float (*)[SY_BT + 4]>(raw + SY_MK * (SY_BT + 4));
-    float (*Gy)[SY_BT + 4] = reinterpret_cast<float (*)[SY_BT + 4]>(raw);                               // [bb][t]
-    float (*A)[SY_MK + 4] = reinterpret_cast<float (*)[SY_MK + 4]>(raw + SY_MK * (SY_BT + 4));          // [bb][mk]
-    const int64_t t0 = (int64_t)blockIdx.x * SY_BT;
-    const int m0 = blockIdx.y * SY_MK;
-    const int tx = threadIdx.x & 15;   // 16 x 8 time samples
-    const int ty = threadIdx.x >> 4;   // 16 x 2 modes
-    float z[2][8];
+    __shared__ __align__(16) float A[SB_TT][SB_W + 4];     // [batch row][mode]
+    __shared__ __align__(16) float G[SB_TT][SB_W + 4];     // [batch row][sample]
+    const int64_t t0 = (int64_t)blockIdx.x * SB_W;
+    const int m0 = blockIdx.y * SB_W;
+    const int tx = threadIdx.x & 15;   // samples 4 tx + {0..3}, 64 + 4 tx + {0..3}
+    const int ty = threadIdx.x >> 4;   // modes   4 ty + {0..3}, 64 + 4 ty + {0..3}
+    unsigned long long z[8][4];        // [mode][sample pair]
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) z[i][j] = 0.f;
-    for (int64_t b0 = 0; b0 < B; b0 += SY_MK) {
+        for (int j = 0; j < 4; ++j) z[i][j] = 0ull;
+    for (int64_t b0 = 0; b0 < B; b0 += SB_TT) {
         __syncthreads();
-        for (int idx = threadIdx.x; idx < SY_MK * SY_MK; idx += SY_THREADS) {
-            int bb = idx / SY_MK, mk = idx - bb * SY_MK;
-            int64_t b = b0 + bb;
-            int m = m0 + mk;
-            A[bb][mk] = (b < B && m < k) ? __ldg(amp + b * k + m) : 0.f;
-        }
-        for (int idx = threadIdx.x; idx < SY_MK * SY_BT; idx += SY_THREADS) {
-            int bb = idx / SY_BT, tt = idx - bb * SY_BT;
-            int64_t b = b0 + bb, t = t0 + tt;
-            Gy[bb][tt] = (b < B && t < T) ? __ldg(gy + b * T + t) : 0.f;
+#pragma unroll
+        for (int r = 0; r < (SB_W * SB_TT) / SY_THREADS; ++r) {
+            const int idx = threadIdx.x + r * SY_THREADS;
+            const int c = idx & (SB_W - 1), bb = idx >> 7;
+            const int64_t b = b0 + bb;
+            A[bb][c] = (b < B && m0 + c < k) ? __ldg(amp + b * k + m0 + c) : 0.f;
+            G[bb][c] = (b < B && t0 + c < T) ? __ldg(gy + b * T + t0 + c) : 0.f;
         }
         __syncthreads();
-#pragma unroll 8
-        for (int bb = 0; bb < SY_MK; ++bb) {
-            float a0 = A[bb][ty * 2], a1 = A[bb][ty * 2 + 1];
-            float4 g0 = *reinterpret_cast<const float4*>(&Gy[bb][tx * 8]);
-            float4 g1 = *reinterpret_cast<const float4*>(&Gy[bb][tx * 8 + 4]);
-            float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll 4
+        for (int bb = 0; bb < SB_TT; ++bb) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&A[bb][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&A[bb][64 + ty * 4]);
+            const ulonglong2 g0 = *reinterpret_cast<const ulonglong2*>(&G[bb][tx * 4]);
+            const ulonglong2 g1 = *reinterpret_cast<const ulonglong2*>(&G[bb][64 + tx * 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                z[0][j] = fmaf(a0, g[j], z[0][j]);
-                z[1][j] = fmaf(a1, g[j], z[1][j]);
+            for (int i = 0; i < 8; ++i) {
+                ffma2_bcast(z[i][0], a[i], g0.x);
+                ffma2_bcast(z[i][1], a[i], g0.y);
+                ffma2_bcast(z[i][2], a[i], g1.x);
+                ffma2_bcast(z[i][3], a[i], g1.y);
             }
         }
     }
-    __syncthreads();
-    fill_basis<true>(damp, freq, k, m0, t0, inv_sr, S, Cc);
-    __syncthreads();
-    // contract over this thread's 8 samples, then over the 16 tx lanes
     const float two_pi = 6.283185307179586f;
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        int mk = ty * 2 + i;
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + (i < 4 ? 4 * ty + i : 64 + 4 * ty + (i - 4));
         float gd = 0.f, gf = 0.f;
+        if (m < k) {
+            const float d = __ldg(damp + m), f = __ldg(freq + m);
+            float wr, wi;
+            rotor(d, f, inv_sr, wr, wi);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            int tt = tx * 8 + j;
-            float tau = (float)((double)(t0 + tt + 1) * inv_sr);
-            gd = fmaf(-tau * S[mk][tt], z[i][j], gd);
-            gf = fmaf(two_pi * tau * Cc[mk][tt], z[i][j], gf);
+            for (int h = 0; h < 2; ++h) {
+                const int64_t t = t0 + 64 * h + 4 * tx;
+                float re, im;
+                anchor(d, f, t, inv_sr, re, im);
+                float zz[4];
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(zz[0]), "=f"(zz[1]) : "l"(z[i][2 * h]));
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(zz[2]), "=f"(zz[3]) : "l"(z[i][2 * h + 1]));
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (t + e < T) {
+                        const float tau = (float)((double)(t + e + 1) * inv_sr);
+                        gd = fmaf(-tau * im, zz[e], gd);
+                        gf = fmaf(two_pi * tau * re, zz[e], gf);
+                    }
+                    const float nr = re * wr - im * wi;
+                    im = re * wi + im * wr;
+                    re = nr;
+                }
+            }
         }
-        red[0][mk][tx] = gd;
-        red[1][mk][tx] = gf;
-    }
-    __syncthreads();
-    if (threadIdx.x < 2 * SY_MK) {
-        int which = threadIdx.x / SY_MK, mk = threadIdx.x - which * SY_MK;
-        float s = 0.f;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) s += red[which][mk][q];
-        int m = m0 + mk;
-        if (m < k) partial[((int64_t)blockIdx.x * 2 + which) * k + m] = s;
+        for (int o = 8; o > 0; o >>= 1) {
+            gd += __shfl_xor_sync(0xffffffffu, gd, o);
+            gf += __shfl_xor_sync(0xffffffffu, gf, o);
+        }
+        if (tx == 0 && m < k) {
+            partial[((int64_t)blockIdx.x * 2 + 0) * k + m] = gd;
+            partial[((int64_t)blockIdx.x * 2 + 1) * k + m] = gf;
+        }
     }
 }
 
@@ -277,8 +359,8 @@ __global__ void k_synth_reduce(const float* __restrict__ partial, int64_t nparts
 }
 
 static int amp_chunks(int64_t T) {
-    int64_t n_tiles = ceil_div(T, SY_BT);
-    int64_t chunks = ceil_div(n_tiles, 32);   // up to 32 time tiles (4096 samples) per CTA
+    int64_t n_slabs = ceil_div(T, SB_TT);
+    int64_t chunks = ceil_div(n_slabs, 75);   // up to 75 slabs (2400 samples) per CTA: 37 chunks at T = 88 200
     return (int)(chunks < 1 ? 1 : chunks);
 }
 
@@ -288,7 +370,7 @@ using namespace ds;
 
 extern "C" int64_t ds_synth_scratch_elems(int64_t B, int k, int64_t T) {
     int64_t a = (int64_t)amp_chunks(T) * B * k;
-    int64_t d = ceil_div(T, SY_BT) * 2 * k;
+    int64_t d = ceil_div(T, SB_W) * 2 * k;
     return a > d ? a : d;
 }
 
@@ -299,7 +381,7 @@ extern "C" int ds_modal_synth_fwd(const float* amp, const float* damp, const flo
     DS_REQUIRE(amp && damp && freq && y, "ds_modal_synth_fwd: null argument");
     DS_REQUIRE(B > 0 && k > 0 && T > 0 && sr > 0, "ds_modal_synth_fwd: bad sizes (B=%lld k=%d T=%lld)", (long long)B, k,
                (long long)T);
-    dim3 grid((unsigned)ceil_div(T, SY_BT), (unsigned)ceil_div(B, SY_BB));
+    dim3 grid((unsigned)ceil_div(T, SY_BT), (unsigned)ceil_div(B, SF_BB));
     ProfScope prof(PROF_SYNTH, stream);
     DS_REQUIRE(grid.y <= 65535, "ds_modal_synth_fwd: batch too large");
     k_synth_fwd<<<grid, SY_THREADS, 0, stream>>>(amp, damp, freq, B, k, T, 1.0 / sr, y);
@@ -315,15 +397,15 @@ extern "C" int ds_modal_synth_bwd(const float* amp, const float* damp, const flo
     DS_REQUIRE(B > 0 && k > 0 && T > 0 && sr > 0, "ds_modal_synth_bwd: bad sizes");
     const int chunks = amp_chunks(T);
     ProfScope prof(PROF_SYNTH, stream);
-    const int64_t n_tiles = ceil_div(T, SY_BT);
-    const int tiles_per_chunk = (int)ceil_div(n_tiles, chunks);
-    dim3 g1((unsigned)chunks, (unsigned)ceil_div(B, SY_BB), (unsigned)ceil_div(k, SY_MK));
+    const int64_t n_tiles = ceil_div(T, SB_W);
+    const int slabs_per_chunk = (int)ceil_div(ceil_div(T, SB_TT), chunks);
+    dim3 g1((unsigned)chunks, (unsigned)ceil_div(B, SB_W), (unsigned)ceil_div(k, SB_W));
     DS_REQUIRE(g1.y <= 65535 && g1.z <= 65535, "ds_modal_synth_bwd: batch or mode count too large");
-    k_synth_bwd_amp<<<g1, SY_THREADS, 0, stream>>>(damp, freq, gy, B, k, T, 1.0 / sr, tiles_per_chunk, scratch);
+    k_synth_bwd_amp<<<g1, SY_THREADS, 0, stream>>>(damp, freq, gy, B, k, T, 1.0 / sr, slabs_per_chunk, scratch);
     DS_LAUNCH_CHECK();
     k_synth_reduce<<<(unsigned)ceil_div(B * k, 256), 256, 0, stream>>>(scratch, chunks, B * k, gamp, B * k, nullptr);
     DS_LAUNCH_CHECK();
-    dim3 g2((unsigned)n_tiles, (unsigned)ceil_div(k, SY_MK));
+    dim3 g2((unsigned)n_tiles, (unsigned)ceil_div(k, SB_W));
     k_synth_bwd_df<<<g2, SY_THREADS, 0, stream>>>(amp, damp, freq, gy, B, k, T, 1.0 / sr, scratch);
     DS_LAUNCH_CHECK();
     k_synth_reduce<<<(unsigned)ceil_div(2 * (int64_t)k, 256), 256, 0, stream>>>(scratch, n_tiles, 2 * (int64_t)k, gdamp, k,
