@@ -258,6 +258,14 @@ __device__ __forceinline__ void st_cluster_f64(uint32_t addr, double v) {
 __device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared::cluster.u32 [%0], %1;\n" ::"r"(addr), "r"(v) : "memory");
 }
+// mailbox hand-shake between neighbouring warps of the cluster: the row travels as asynchronous DSMEM stores that
+// complete transaction bytes on an mbarrier in the RECEIVER's shared memory (st.async ... complete_tx); the
+// receiver arms the barrier with the expected byte count and waits on its phase -- no fences, no cluster barrier
+__device__ __forceinline__ void st_async_f64(uint32_t addr, double v, uint32_t mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];\n" ::"r"(addr),
+                 "l"(__double_as_longlong(v)), "r"(mbar)
+                 : "memory");
+}
 __device__ __forceinline__ uint32_t ld_cluster_u32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared::cluster.u32 %0, [%1];\n" : "=r"(v) : "r"(addr) : "memory");
@@ -270,6 +278,7 @@ k_eigh_jacobi(int N, double* __restrict__ scratch, int* __restrict__ info) {
     __shared__ __align__(16) double slotE[JC_GPC][JC_SLOT];   // even steps: position 2g arriving at group g
     __shared__ __align__(16) double park[JC_SLOT];            // position 0 rests here during odd steps
     __shared__ uint32_t s_again;                              // used in CTA 0 of the cluster
+    __shared__ __align__(8) uint64_t barO[JC_GPC], barE[JC_GPC];   // transaction barriers of slotO / slotE
     double* Yg = scratch + eig_off_Y(N);
     if (scratch[eig_off_meta(N) + 1] != 0.0) return;          // factorisation failed (every CTA sees the same flag)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -290,6 +299,15 @@ k_eigh_jacobi(int N, double* __restrict__ scratch, int* __restrict__ info) {
     const uint32_t dstO = g >= 1 ? map_to_cta(&slotO[(g - 1) % JC_GPC][0], (uint32_t)((g - 1) / JC_GPC)) : 0u;
     const uint32_t dstE = g + 1 < G ? map_to_cta(&slotE[(g + 1) % JC_GPC][0], (uint32_t)((g + 1) / JC_GPC)) : 0u;
     const uint32_t again_addr = map_to_cta(&s_again, 0u);
+    const uint32_t fdstO = g >= 1 ? map_to_cta(&barO[(g - 1) % JC_GPC], (uint32_t)((g - 1) / JC_GPC)) : 0u;
+    const uint32_t fdstE = g + 1 < G ? map_to_cta(&barE[(g + 1) % JC_GPC], (uint32_t)((g + 1) / JC_GPC)) : 0u;
+    if (lane == 0) {
+        mbar_init(&barO[warp], 1);
+        mbar_init(&barE[warp], 1);
+        fence_barrier_init();
+    }
+    uint32_t phO = 0u, phE = 0u;                              // parity of the next phase of this warp's barriers
+    constexpr uint32_t ROW_BYTES = (JC_LD + 1) * 8u;          // elements + |row|^2
 
     // rotate x (|x|^2 = nx) against y; returns 1 if a rotation was applied (all lanes of the warp call it)
     auto rotate = [&](bool enable, double (&x)[JC_E], double& nx, double (&y)[JC_E], double& ny) -> int {
@@ -316,10 +334,18 @@ k_eigh_jacobi(int N, double* __restrict__ scratch, int* __restrict__ info) {
         ny += t * ga;
         return 1;
     };
-    auto send = [&](uint32_t dst, const double (&x)[JC_E], double nx) {
+    // Rows travel between neighbouring warps without a cluster-wide barrier.  A mailbox is never overwritten
+    // early: the sender's next store into it is ordered after a row it receives from that same neighbour, which the
+    // neighbour sends only after it has emptied the mailbox.
+    auto send = [&](uint32_t dst, uint32_t bar, const double (&x)[JC_E], double nx) {
 #pragma unroll
-        for (int i = 0; i < JC_E; ++i) st_cluster_f64(dst + (uint32_t)(lane + 32 * i) * 8u, x[i]);
-        if (lane == 0) st_cluster_f64(dst + (uint32_t)JC_LD * 8u, nx);
+        for (int i = 0; i < JC_E; ++i) st_async_f64(dst + (uint32_t)(lane + 32 * i) * 8u, x[i], bar);
+        if (lane == 0) st_async_f64(dst + (uint32_t)JC_LD * 8u, nx, bar);
+    };
+    auto wait_row = [&](uint64_t* bar, uint32_t& parity) {
+        if (lane == 0) mbar_expect_tx(bar, ROW_BYTES);
+        mbar_wait(bar, parity);
+        parity ^= 1u;
     };
     auto recv = [&](const double* src, double (&x)[JC_E], double& nx) {
 #pragma unroll
@@ -349,13 +375,12 @@ k_eigh_jacobi(int N, double* __restrict__ scratch, int* __restrict__ info) {
 #pragma unroll
                     for (int i = 0; i < JC_E; ++i) park[lane + 32 * i] = rb[i];
                     if (lane == 0) park[JC_LD] = nb;
+                    __syncwarp();
                 } else {
-                    send(dstO, rb, nb);
+                    send(dstO, fdstO, rb, nb);
                 }
-            }
-            cluster_sync_all();
-            if (active) {
                 if (g < G - 1) {
+                    wait_row(&barO[warp], phO);
                     recv(&slotO[warp][0], rb, nb);
                 } else {                                       // beyond the end of the line: a zero row
 #pragma unroll
@@ -372,11 +397,14 @@ k_eigh_jacobi(int N, double* __restrict__ scratch, int* __restrict__ info) {
                 const double tv = na; na = nb; nb = tv;
             }
             // next even step: position 2g+2 (ra) goes to the right neighbour; position 2g arrives in ra
-            if (active && g + 1 < G) send(dstE, ra, na);
-            cluster_sync_all();
             if (active) {
-                if (g == 0) recv(park, ra, na);
-                else recv(&slotE[warp][0], ra, na);
+                if (g + 1 < G) send(dstE, fdstE, ra, na);
+                if (g == 0) {
+                    recv(park, ra, na);
+                } else {
+                    wait_row(&barE[warp], phE);
+                    recv(&slotE[warp][0], ra, na);
+                }
             }
         }
         if (__any_sync(0xffffffffu, rotated) && lane == 0) st_cluster_u32(again_addr, 1u);

@@ -541,29 +541,41 @@ __global__ void k_jacobi32(const float* __restrict__ invD, const float* __restri
 }
 
 // dst32[:, s] = (float) src64[:, idx[s]] for s < count, 0 for count <= s < width; with perm, dof row 3 r + c of
-// dst is dof row 3 perm[r] + c of src (the preconditioner's own node numbering)
+// dst is dof row 3 perm[r] + c of src (the preconditioner's own node numbering).  One thread per (row, 4 columns).
 __global__ void k_gather_cols_f32(const double* __restrict__ src, int64_t lds, const __grid_constant__ ColIdx idx,
                                   int count, int width, int64_t n, float* __restrict__ dst,
                                   const int32_t* __restrict__ perm) {
+    const int w4 = width >> 2;
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= n * width) return;
-    const int64_t row = t / width;
-    const int s = (int)(t - row * width);
+    if (t >= n * w4) return;
+    const int64_t row = t / w4;
+    const int s = (int)(t - row * w4) * 4;
     int64_t srow = row;
     if (perm) { const int64_t node = row / 3; srow = 3 * (int64_t)perm[node] + (row - 3 * node); }
-    dst[t] = s < count ? (float)src[srow * lds + idx.v[s]] : 0.f;
+    const double* sp = src + srow * lds;
+    float4 v;
+    v.x = s + 0 < count ? (float)__ldg(sp + idx.v[s + 0]) : 0.f;
+    v.y = s + 1 < count ? (float)__ldg(sp + idx.v[s + 1]) : 0.f;
+    v.z = s + 2 < count ? (float)__ldg(sp + idx.v[s + 2]) : 0.f;
+    v.w = s + 3 < count ? (float)__ldg(sp + idx.v[s + 3]) : 0.f;
+    reinterpret_cast<float4*>(dst + row * width)[s >> 2] = v;
 }
 
-// dst64[:, :width] (ld) = (double) src32 (n x width); with perm, dof row 3 perm[r] + c of dst from row 3 r + c of src
+// dst64[:, :width] (ld) = (double) src32 (n x width); with perm, dof row 3 perm[r] + c of dst from row 3 r + c of src.
+// One thread per (row, 4 columns); dst rows must be 16-byte aligned (even ld, aligned base).
 __global__ void k_widen_f32(const float* __restrict__ src, int width, int64_t n, double* __restrict__ dst, int64_t ldd,
                             const int32_t* __restrict__ perm) {
+    const int w4 = width >> 2;
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= n * width) return;
-    const int64_t row = t / width;
-    const int s = (int)(t - row * width);
+    if (t >= n * w4) return;
+    const int64_t row = t / w4;
+    const int q = (int)(t - row * w4);
     int64_t drow = row;
     if (perm) { const int64_t node = row / 3; drow = 3 * (int64_t)perm[node] + (row - 3 * node); }
-    dst[drow * ldd + s] = (double)src[t];
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + row * width) + q);
+    double2* dp = reinterpret_cast<double2*>(dst + drow * ldd + 4 * q);
+    dp[0] = make_double2((double)v.x, (double)v.y);
+    dp[1] = make_double2((double)v.z, (double)v.w);
 }
 
 // per-column sum of squares of an fp32 block (n x w), fp64 accumulation; partial[cta][w]
@@ -828,14 +840,16 @@ int prolong64(const int32_t* par, int64_t n_fine, const double* xc, int64_t ldc,
 int gather_cols_f32(const double* src, int64_t lds, const ColIdx& idx, int count, int width, int64_t n, float* dst,
                     cudaStream_t st, const int32_t* perm) {
     ProfScope prof(PROF_COPY, st);
-    k_gather_cols_f32<<<(unsigned)ceil_div(n * width, 256), 256, 0, st>>>(src, lds, idx, count, width, n, dst, perm);
+    DS_REQUIRE(width % 4 == 0, "gather_cols_f32: width must be a multiple of 4");
+    k_gather_cols_f32<<<(unsigned)ceil_div(n * (width / 4), 256), 256, 0, st>>>(src, lds, idx, count, width, n, dst, perm);
     DS_LAUNCH_CHECK();
     return DS_OK;
 }
 
 int widen_f32(const float* src, int width, int64_t n, double* dst, int64_t ldd, cudaStream_t st, const int32_t* perm) {
     ProfScope prof(PROF_COPY, st);
-    k_widen_f32<<<(unsigned)ceil_div(n * width, 256), 256, 0, st>>>(src, width, n, dst, ldd, perm);
+    DS_REQUIRE(width % 4 == 0 && ldd % 2 == 0 && ((uintptr_t)dst & 15) == 0, "widen_f32: width % 4, even ld and 16-byte aligned dst");
+    k_widen_f32<<<(unsigned)ceil_div(n * (width / 4), 256), 256, 0, st>>>(src, width, n, dst, ldd, perm);
     DS_LAUNCH_CHECK();
     return DS_OK;
 }
