@@ -67,6 +67,7 @@ SIGNATURES = {
     "ds_unique_rows3_fill": (cint, [ptr, ptr, ptr, ptr]),
     "ds_spmm32": (cint, [cint, i32p, ptr, i64, cint, f32p, f32p, f32p, f32p, f32p, dbl, dbl, i32p, ptr]),
     "ds_spmm32_chunk_count": (cint, [i64]),
+    "ds_cheb32_solve": (cint, [i32p, ptr, f32p, i64, i64, f32p, cint, cint, dbl, dbl, cint, f32p, f32p, C.POINTER(cint), ptr]),
     "ds_spmm32_chunks": (cint, [i32p, i64, i32p, ptr]),
     "ds_k32_pack_slab": (cint, [i32p, i32p, i64, i64, i64, f64p, f64p, dbl, ptr, ptr, f32p, ptr]),
     "ds_spmm32_rowpart": (cint, [cint, i32p, ptr, i64, cint, C.POINTER(C.c_void_p), cint, cint, f32p, f32p, f32p, f32p,

@@ -59,6 +59,8 @@ struct Level32 {
     unsigned char* rec = nullptr;
     float* invD = nullptr;
     int32_t* chunk_row = nullptr;
+    unsigned* gbar = nullptr;                // [0] grid-barrier counter, [1] error flag of the persistent Chebyshev kernel
+    bool persistent = false;                 // cooperative launches available
     double lmax = 0.0;
     int prof_cls = PROF_CHEB;
     int64_t launches = 0, cols = 0;          // SpMM launches and the sum of their column counts

@@ -479,7 +479,14 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
     DS_CUDA(cudaMemcpy2DAsync(X, m * 8, Xb(cur), ld * 8, m * 8, n, cudaMemcpyDeviceToDevice, st));
     DS_CUDA(cudaMemcpyAsync(lambda_out, lam_d, m * sizeof(double), cudaMemcpyDeviceToDevice, st));
     DS_CUDA(cudaMemcpyAsync(resid_out, rel.data(), m * sizeof(double), cudaMemcpyHostToDevice, st));
+    unsigned gb_f[2] = {0, 0}, gb_c[2] = {0, 0};      // [1]: grid-barrier timeout flag of the persistent Chebyshev kernel
+    DS_CUDA(cudaMemcpyAsync(gb_f, fine.gbar, sizeof(gb_f), cudaMemcpyDeviceToHost, st));
+    if (cl) DS_CUDA(cudaMemcpyAsync(gb_c, coarse.gbar, sizeof(gb_c), cudaMemcpyDeviceToHost, st));
     DS_CUDA(cudaStreamSynchronize(st));
+    if (gb_f[1] || gb_c[1]) {
+        set_error("ds_lobpcg: grid barrier of the persistent Chebyshev kernel timed out (device shared with other work?)");
+        return DS_ERR_CUDA;
+    }
     stats[0] = it;
     stats[1] = nconv;
     stats[3] = status;

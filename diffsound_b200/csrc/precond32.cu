@@ -26,6 +26,7 @@
 #include "../../include/diffsound_sm100.h"
 #include "kernels.cuh"
 #include "ptx.cuh"
+#include <algorithm>
 #include <utility>
 #include <cstring>
 #include <cub/cub.cuh>
@@ -134,6 +135,9 @@ __device__ __forceinline__ u64 ldg_u64(const float* p) {
 }
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -346,6 +350,173 @@ k_spmm32v(const int32_t* __restrict__ brow, const uint4* __restrict__ rec, const
             }
             st_row_stream<LPR, CPT>(Out + o, l, v);
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent Chebyshev solve for a level that fits on chip (the P1 coarse operator: ~25 MB of records):
+// ALL `degree` steps of z = p(invD A) invD r run in ONE cooperative launch, one 1024-thread CTA per SM.
+// Every CTA copies the block records of its row chunk into shared memory once (~170 KB) and reuses them
+// in every step; the steps are separated by a grid barrier (one atomic per CTA on a global counter + an
+// acquire fence that also drops the stale L1 lines of the iterate).  Per step the only traffic left is the
+// gather of the iterate from L2.  Replaces `degree` launches of k_spmm32v whose time at this size (~40 us
+// each) was launch + dependent-latency, not bandwidth.
+// ---------------------------------------------------------------------------------------------
+constexpr int CHP_MAX_DEGREE = 64;
+struct ChebCoef {
+    float cc0;                       // z_1 = cc0 invD r
+    float ab[CHP_MAX_DEGREE];        // step k = 1 .. degree-1
+    float cc[CHP_MAX_DEGREE];
+    int degree;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// coherent (L1-cacheable within a step, invalidated by the fence of the grid barrier) loads of the iterate
+__device__ __forceinline__ void ld_v2u64_coh(const float* p, u64& a, u64& b) {
+    asm volatile("ld.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ u64 ld_u64_coh(const float* p) {
+    u64 a;
+    asm volatile("ld.global.u64 %0, [%1];" : "=l"(a) : "l"(p) : "memory");
+    return a;
+}
+template <int LPR, int CPT>
+__device__ __forceinline__ void ld_row2_coh(const float* row, int l, u64* out) {
+    ld_v2u64_coh(row + 4 * l, out[0], out[1]);
+    if constexpr (CPT == 6) out[2] = ld_u64_coh(row + 4 * LPR + 2 * l);
+    if constexpr (CPT == 8) ld_v2u64_coh(row + 4 * LPR + 4 * l, out[2], out[3]);
+}
+
+// all CTAs of the (cooperative) grid; `target` = barriers passed so far * gridDim.x.  A CTA that waits longer
+// than ~1 s raises *err and leaves (the results are then garbage, but the device does not hang).
+__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned target, int* err, int* ticket) {
+    __syncthreads();                 // every warp of this CTA has left the row loop of the step
+    if (threadIdx.x == 0) {
+        *ticket = 0;                 // only now may the row ticket be rewound
+        __threadfence();             // release: this CTA's rows of the new iterate (cumulative over the bar.sync)
+        atomicAdd(ctr, 1u);
+        const long long t0 = clock64();
+        while (ld_acquire_gpu_u32(ctr) < target) {
+            if (*(volatile int*)err || clock64() - t0 > (2ll << 30)) { *err = 1; break; }
+        }
+        __threadfence();             // acquire; the gpu-scope fence also invalidates this SM's L1 (CCTL.IVALL), so the
+                                     // stale lines of the buffer that now holds the new iterate are dropped
+    }
+    __syncthreads();
+}
+
+template <int LPR, int CPT>
+__global__ void __launch_bounds__(S32V_THREADS, 1)
+k_cheb32_persistent(const int32_t* __restrict__ brow, const uint4* __restrict__ rec, const int32_t* __restrict__ chunk_row,
+                    const float* __restrict__ R, const float* __restrict__ invD, float* Za, float* Zb,
+                    const __grid_constant__ ChebCoef coef, int smem_records, unsigned* gbar, int* err) {
+    constexpr int C = LPR * CPT;
+    constexpr int NG = 32 / LPR;
+    constexpr int NP = CPT / 2;
+    extern __shared__ __align__(16) uint4 srec[];           // records of this chunk (first smem_records of them)
+    __shared__ int s_ticket;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int g = lane / LPR, l = lane % LPR;
+    const int r_lo = chunk_row[blockIdx.x], r_hi = chunk_row[blockIdx.x + 1];
+    const int rec_lo = brow[r_lo], rec_hi = brow[r_hi];
+    const int n_s = min(rec_hi - rec_lo, smem_records);
+    for (int i = tid; i < 3 * n_s; i += S32V_THREADS) srec[i] = __ldg(rec + (int64_t)3 * rec_lo + i);
+    const int s_hi = rec_lo + n_s;                           // records [rec_lo, s_hi) are in shared memory
+    // ---- step 0: z_1 = cc0 invD r on the own rows -> Za
+    for (int idx = tid; idx < (r_hi - r_lo) * (C / 4); idx += S32V_THREADS) {
+        const int row = r_lo + idx / (C / 4), q = idx % (C / 4);
+        const float4 r0 = __ldg(reinterpret_cast<const float4*>(R + (int64_t)3 * row * C) + q);
+        const float4 r1 = __ldg(reinterpret_cast<const float4*>(R + ((int64_t)3 * row + 1) * C) + q);
+        const float4 r2 = __ldg(reinterpret_cast<const float4*>(R + ((int64_t)3 * row + 2) * C) + q);
+        const float* d = invD + 9 * (int64_t)row;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float d0 = coef.cc0 * __ldg(d + 3 * c), d1 = coef.cc0 * __ldg(d + 3 * c + 1), d2 = coef.cc0 * __ldg(d + 3 * c + 2);
+            float4 v;
+            v.x = d0 * r0.x + d1 * r1.x + d2 * r2.x;
+            v.y = d0 * r0.y + d1 * r1.y + d2 * r2.y;
+            v.z = d0 * r0.z + d1 * r1.z + d2 * r2.z;
+            v.w = d0 * r0.w + d1 * r1.w + d2 * r2.w;
+            reinterpret_cast<float4*>(Za + ((int64_t)3 * row + c) * C)[q] = v;
+        }
+    }
+    float* X = Za;      // z_k
+    float* Zp = Zb;     // z_{k-1}, overwritten by z_{k+1}
+    unsigned passed = 0;
+    for (int k = 1; k < coef.degree; ++k) {
+        grid_barrier(gbar, (++passed) * gridDim.x, err, &s_ticket);
+        const float ab = coef.ab[k], cc = coef.cc[k];
+        const bool have_prev = k > 1;                        // z_0 = 0
+        for (;;) {
+            int rr = 0;
+            if (lane == 0) rr = atomicAdd(&s_ticket, 1);
+            rr = __shfl_sync(0xffffffffu, rr, 0);
+            const int row = r_lo + rr;
+            if (row >= r_hi) break;
+            const int rb0 = brow[row], rb1 = brow[row + 1];
+            u64 acc[3][NP];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int t = 0; t < NP; ++t) acc[c][t] = 0ull;
+            for (int p = rb0 + g; p < rb1; p += NG) {
+                uint4 a0, a1, a2;
+                if (p < s_hi) {
+                    const uint4* rp = srec + 3 * (p - rec_lo);
+                    a0 = rp[0]; a1 = rp[1]; a2 = rp[2];
+                } else {
+                    const uint4* rp = rec + (int64_t)3 * p;
+                    a0 = ldg_na_u4(rp); a1 = ldg_na_u4(rp + 1); a2 = ldg_na_u4(rp + 2);
+                }
+                const float* xr = X + (int64_t)(int)a2.y * (3 * C);
+                u64 x[3][NP];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) ld_row2_coh<LPR, CPT>(xr + d * C, l, x[d]);
+                const float kv[9] = {__uint_as_float(a0.x), __uint_as_float(a0.y), __uint_as_float(a0.z),
+                                     __uint_as_float(a0.w), __uint_as_float(a1.x), __uint_as_float(a1.y),
+                                     __uint_as_float(a1.z), __uint_as_float(a1.w), __uint_as_float(a2.x)};
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int d = 0; d < 3; ++d)
+#pragma unroll
+                        for (int t = 0; t < NP; ++t) ffma2(acc[c][t], kv[3 * c + d], x[d][t]);
+            }
+#pragma unroll
+            for (int off = LPR; off < 32; off <<= 1)
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int t = 0; t < NP; ++t) acc[c][t] = fadd2(acc[c][t], __shfl_xor_sync(0xffffffffu, acc[c][t], off));
+            if (g < 3) {
+                const int64_t o = ((int64_t)3 * row + g) * C;
+                float a[3][CPT];
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int t = 0; t < NP; ++t) unpack2(acc[c][t], a[c][2 * t], a[c][2 * t + 1]);
+                const float d0 = __ldg(invD + 9 * (int64_t)row + 3 * g), d1 = __ldg(invD + 9 * (int64_t)row + 3 * g + 1),
+                            d2 = __ldg(invD + 9 * (int64_t)row + 3 * g + 2);
+                float r0v[CPT], r1v[CPT], r2v[CPT], z[CPT], zp[CPT], v[CPT];
+                const int64_t ob = (int64_t)3 * row * C;
+                ld_row<LPR, CPT>(R + ob, l, r0v);
+                ld_row<LPR, CPT>(R + ob + C, l, r1v);
+                ld_row<LPR, CPT>(R + ob + 2 * C, l, r2v);
+                ld_row_plain<LPR, CPT>(X + o, l, z);
+                if (have_prev) ld_row_plain<LPR, CPT>(Zp + o, l, zp);
+#pragma unroll
+                for (int t = 0; t < CPT; ++t) {
+                    const float dr = d0 * (r0v[t] - a[0][t]) + d1 * (r1v[t] - a[1][t]) + d2 * (r2v[t] - a[2][t]);
+                    v[t] = z[t] + ab * (z[t] - (have_prev ? zp[t] : 0.f)) + cc * dr;
+                }
+                st_row<LPR, CPT>(Zp + o, l, v);
+            }
+        }
+        float* tsw = X; X = Zp; Zp = tsw;
     }
 }
 
@@ -889,7 +1060,7 @@ static size_t morton_sort_temp(int64_t n_nodes) {
 size_t Level32::bytes(int64_t n_nodes, int64_t nnzb) {
     auto al = [](size_t b) { return ((b + 255) & ~size_t(255)) + 256; };
     return al((size_t)nnzb * S32_REC_BYTES + 64) + al((size_t)n_nodes * 9 * sizeof(float)) + al(1024 * sizeof(int32_t)) +
-           6 * al((size_t)(n_nodes + 1) * sizeof(int32_t)) + al(morton_sort_temp(n_nodes)) + al(64);
+           6 * al((size_t)(n_nodes + 1) * sizeof(int32_t)) + al(morton_sort_temp(n_nodes)) + 2 * al(64);
 }
 
 // coords (optional, fp32 [n_nodes x 3]): the operator is stored with its rows and columns renumbered along a
@@ -903,7 +1074,15 @@ int Level32::setup(Arena& a, const int32_t* brow_, const int32_t* bcol, int64_t 
     rec = a.take<unsigned char>((size_t)nnzb * S32_REC_BYTES + 64);
     invD = a.take<float>((size_t)n_nodes * 9);
     chunk_row = a.take<int32_t>(1024);
-    DS_REQUIRE(rec && invD && chunk_row, "Level32: workspace arena exhausted");
+    gbar = a.take<unsigned>(16);
+    DS_REQUIRE(rec && invD && chunk_row && gbar, "Level32: workspace arena exhausted");
+    DS_CUDA(cudaMemsetAsync(gbar, 0, 16 * sizeof(unsigned), st));
+    {
+        int dev = 0, coop = 0;
+        DS_CUDA(cudaGetDevice(&dev));
+        DS_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+        persistent = coop != 0;
+    }
     DS_REQUIRE(s32v_grid(n_nodes) < 1024, "Level32: more than 1023 SMs");
     DS_CUDA(cudaMemsetAsync(rec + (size_t)nnzb * S32_REC_BYTES, 0, 64, st));    // bulk prefetches read up to 8 bytes past the end
     perm = inv = nullptr;
@@ -945,12 +1124,66 @@ int Level32::setup(Arena& a, const int32_t* brow_, const int32_t* bcol, int64_t 
 // z = p(invD A) invD r by `degree` Chebyshev steps on [lmax/ratio, lmax].
 //   from_zero: z0 = 0 (first step is a pure Jacobi scaling); else z0 = contents of *zc.
 // zc / zp: ping-pong buffers; on return *zc holds the result.
+template <int LPR, int CPT>
+static int launch_cheb_persistent(const Level32& L, const float* r, const ChebCoef& coef, float* Za, float* Zb,
+                                  int smem_records, size_t smem_bytes, cudaStream_t st) {
+    auto kern = k_cheb32_persistent<LPR, CPT>;
+    static bool attr = false;
+    if (!attr) {
+        DS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr = true;
+    }
+    const int32_t* brow = L.brow;
+    const uint4* rec = reinterpret_cast<const uint4*>(L.rec);
+    const int32_t* chunk_row = L.chunk_row;
+    const float* invD = L.invD;
+    unsigned* gbar = L.gbar;
+    int* err = reinterpret_cast<int*>(L.gbar + 1);
+    void* args[] = {(void*)&brow, (void*)&rec, (void*)&chunk_row, (void*)&r, (void*)&invD, (void*)&Za, (void*)&Zb,
+                    (void*)&coef, (void*)&smem_records, (void*)&gbar, (void*)&err};
+    DS_CUDA(cudaMemsetAsync(L.gbar, 0, sizeof(unsigned), st));
+    DS_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(spmm32_chunk_count(L.n_nodes)), dim3(S32V_THREADS), args,
+                                        smem_bytes, st));
+    count_launch();
+    return DS_OK;
+}
+
 int Level32::cheb(const float* r, int ncols, int degree, double ratio, bool from_zero, float** zc, float** zp,
                   cudaStream_t st) {
     const double lmin = lmax / ratio;
     const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sig = theta / delta;
     double rho = 1.0 / sig;
     int k = 0;
+    // a level whose records fit into the SMs' shared memory runs all its steps in one cooperative launch
+    const int nchunks = spmm32_chunk_count(n_nodes);
+    const size_t avg_rec_bytes = (size_t)nnzb * S32_REC_BYTES / (size_t)nchunks;
+    if (from_zero && persistent && degree >= 3 && degree <= CHP_MAX_DEGREE && nchunks >= 8 && avg_rec_bytes <= 190 * 1024 &&
+        (ncols == 16 || ncols == 32 || ncols == 48)) {
+        ChebCoef coef;
+        coef.cc0 = (float)(1.0 / theta);
+        coef.degree = degree;
+        for (k = 1; k < degree; ++k) {
+            const double rho_new = 1.0 / (2.0 * sig - rho);
+            coef.ab[k] = (float)(rho_new * rho);
+            coef.cc[k] = (float)(2.0 * rho_new / delta);
+            rho = rho_new;
+        }
+        // shared memory: the average chunk + 12 % (chunks are balanced by blocks + rows); a longer chunk reads its
+        // tail from global memory
+        size_t smem_bytes = std::min<size_t>(avg_rec_bytes + avg_rec_bytes / 8 + 4096, 216 * 1024);
+        smem_bytes &= ~size_t(15);
+        const int smem_records = (int)(smem_bytes / S32_REC_BYTES);
+        ProfScope prof(prof_cls, st);
+        switch (ncols) {
+            case 16: DS_TRY((launch_cheb_persistent<4, 4>(*this, r, coef, *zc, *zp, smem_records, smem_bytes, st))); break;
+            case 32: DS_TRY((launch_cheb_persistent<8, 4>(*this, r, coef, *zc, *zp, smem_records, smem_bytes, st))); break;
+            default: DS_TRY((launch_cheb_persistent<8, 6>(*this, r, coef, *zc, *zp, smem_records, smem_bytes, st))); break;
+        }
+        if ((degree - 1) & 1) std::swap(*zc, *zp);      // z_1 in zc; every further step swaps the roles
+        launches += degree - 1;
+        cols += (int64_t)(degree - 1) * ncols;
+        return DS_OK;
+    }
     if (from_zero) {
         DS_TRY(jacobi32(invD, r, n_nodes, ncols, (float)(1.0 / theta), *zc, st));
     } else {
@@ -998,6 +1231,42 @@ extern "C" int ds_spmm32(int mode, const int32_t* brow, const void* rec, int64_t
 }
 
 extern "C" int ds_spmm32_chunk_count(int64_t n_nodes) { return s32v_grid(n_nodes); }
+
+/* z = p(invD A) invD R by `degree` Chebyshev steps on [lmax / ratio, lmax] from a zero initial guess (the coarse solve
+ * and the one-level preconditioner of the eigensolver).  persistent != 0: all steps in one cooperative launch with the
+ * records in shared memory (levels that fit); 0: one k_spmm32v launch per step.  Za, Zb: ping-pong buffers
+ * [3*n_nodes x ncols]; *which_host = 0 / 1: the result is in Za / Zb. */
+extern "C" int ds_cheb32_solve(const int32_t* brow, const void* rec, const float* invD, int64_t n_nodes, int64_t nnzb,
+                               const float* R, int ncols, int degree, double lmax, double ratio, int persistent,
+                               float* Za, float* Zb, int* which_host, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    DS_REQUIRE(brow && rec && invD && R && Za && Zb && which_host && degree >= 1 && lmax > 0 && ratio > 1,
+               "ds_cheb32_solve: bad argument");
+    Level32 L;
+    L.brow = brow;
+    L.n_nodes = n_nodes;
+    L.nnzb = nnzb;
+    L.rec = const_cast<unsigned char*>(reinterpret_cast<const unsigned char*>(rec));
+    L.invD = const_cast<float*>(invD);
+    L.lmax = lmax;
+    int32_t* tmp = nullptr;
+    DS_CUDA(cudaMallocAsync(&tmp, sizeof(int32_t) * (1024 + 16), st));
+    L.chunk_row = tmp;
+    L.gbar = reinterpret_cast<unsigned*>(tmp + 1024);
+    DS_CUDA(cudaMemsetAsync(L.gbar, 0, 16 * sizeof(unsigned), st));
+    L.persistent = persistent != 0;
+    int rc = spmm32_chunks(brow, n_nodes, L.chunk_row, st);
+    float *zc = Za, *zp = Zb;
+    if (rc == DS_OK) rc = L.cheb(R, ncols, degree, ratio, true, &zc, &zp, st);
+    unsigned flags[2] = {0, 0};
+    if (rc == DS_OK && cudaMemcpyAsync(flags, L.gbar, sizeof(flags), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = DS_ERR_CUDA;
+    cudaFreeAsync(tmp, st);
+    DS_CUDA(cudaStreamSynchronize(st));
+    DS_TRY(rc);
+    DS_REQUIRE(flags[1] == 0, "ds_cheb32_solve: grid barrier timed out");
+    *which_host = zc == Za ? 0 : 1;
+    return DS_OK;
+}
 
 extern "C" int ds_spmm32_chunks(const int32_t* brow, int64_t n_nodes, int32_t* chunk_row, void* stream) {
     DS_REQUIRE(brow && chunk_row && n_nodes > 0, "ds_spmm32_chunks: bad argument");

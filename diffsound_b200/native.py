@@ -365,6 +365,19 @@ def spmm32(pattern, rec, X, mode=0, R=None, invD=None, Zprev=None, ab=0.0, cc=0.
     return out
 
 
+def cheb32_solve(pattern, rec, invD, R, degree, lmax, ratio, persistent=True):
+    """`degree` block-Jacobi Chebyshev steps towards A^-1 R from zero (ds_cheb32_solve); fp32 (n, ncols)."""
+    lib = _lib.load()
+    assert R.dtype == torch.float32 and R.is_contiguous()
+    Za, Zb = torch.empty_like(R), torch.empty_like(R)
+    which = C.c_int(0)
+    with torch.cuda.device(R.device):
+        _lib.check(lib.ds_cheb32_solve(_p(pattern.brow), _p(rec), _p(invD), pattern.n_nodes, pattern.nnzb, _p(R), R.shape[1],
+                                       int(degree), float(lmax), float(ratio), int(bool(persistent)), _p(Za), _p(Zb),
+                                       C.byref(which), _stream()), "ds_cheb32_solve")
+    return Zb if which.value else Za
+
+
 def pmg_restrict32(coarse, res):
     lib = _lib.load()
     rc = torch.empty(3 * coarse.n_nodes, res.shape[1], dtype=torch.float32, device=res.device)

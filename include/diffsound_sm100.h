@@ -220,6 +220,14 @@ int ds_spmm32(int mode, const int32_t* brow, const void* rec, int64_t n_nodes, i
  * holds the first row of every chunk, balanced by blocks + rows.  ds_spmm32 accepts chunk_row = NULL and
  * then builds the chunks into a stream-ordered temporary on every call. */
 int ds_spmm32_chunk_count(int64_t n_nodes);
+/* z = p(invD A) invD R: `degree` block-Jacobi Chebyshev steps on [lmax / ratio, lmax] from a zero initial guess (the
+ * coarse solve of the V-cycle and the one-level preconditioner of the nested eigen-solve).  persistent != 0: all
+ * steps in ONE cooperative launch, one CTA per SM, the block records of each CTA's row chunk held in shared memory
+ * and the steps separated by a grid barrier (levels whose records fit on chip); 0: one SpMM launch per step.
+ * Za, Zb: fp32 ping-pong buffers [3*n_nodes x ncols]; *which_host = 0 / 1: result in Za / Zb.  Synchronises. */
+int ds_cheb32_solve(const int32_t* brow, const void* rec, const float* invD, int64_t n_nodes, int64_t nnzb,
+                    const float* R, int ncols, int degree, double lmax, double ratio, int persistent,
+                    float* Za, float* Zb, int* which_host, void* stream);
 int ds_spmm32_chunks(const int32_t* brow, int64_t n_nodes, int32_t* chunk_row, void* stream);
 
 /* Row-partitioned SpMM for one large mesh on several GPUs of a node: rank r owns
