@@ -1142,8 +1142,12 @@ static int launch_cheb_persistent(const Level32& L, const float* r, const ChebCo
     void* args[] = {(void*)&brow, (void*)&rec, (void*)&chunk_row, (void*)&r, (void*)&invD, (void*)&Za, (void*)&Zb,
                     (void*)&coef, (void*)&smem_records, (void*)&gbar, (void*)&err};
     DS_CUDA(cudaMemsetAsync(L.gbar, 0, sizeof(unsigned), st));
-    DS_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(spmm32_chunk_count(L.n_nodes)), dim3(S32V_THREADS), args,
-                                        smem_bytes, st));
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void*)kern, dim3(spmm32_chunk_count(L.n_nodes)),
+                                                      dim3(S32V_THREADS), args, smem_bytes, st);
+    if (e != cudaSuccess) {          // e.g. the device cannot co-schedule the grid right now: the caller steps instead
+        cudaGetLastError();
+        return 1;
+    }
     count_launch();
     return DS_OK;
 }
@@ -1173,16 +1177,24 @@ int Level32::cheb(const float* r, int ncols, int degree, double ratio, bool from
         size_t smem_bytes = std::min<size_t>(avg_rec_bytes + avg_rec_bytes / 8 + 4096, 216 * 1024);
         smem_bytes &= ~size_t(15);
         const int smem_records = (int)(smem_bytes / S32_REC_BYTES);
-        ProfScope prof(prof_cls, st);
-        switch (ncols) {
-            case 16: DS_TRY((launch_cheb_persistent<4, 4>(*this, r, coef, *zc, *zp, smem_records, smem_bytes, st))); break;
-            case 32: DS_TRY((launch_cheb_persistent<8, 4>(*this, r, coef, *zc, *zp, smem_records, smem_bytes, st))); break;
-            default: DS_TRY((launch_cheb_persistent<8, 6>(*this, r, coef, *zc, *zp, smem_records, smem_bytes, st))); break;
+        int rc;
+        {
+            ProfScope prof(prof_cls, st);
+            switch (ncols) {
+                case 16: rc = launch_cheb_persistent<4, 4>(*this, r, coef, *zc, *zp, smem_records, smem_bytes, st); break;
+                case 32: rc = launch_cheb_persistent<8, 4>(*this, r, coef, *zc, *zp, smem_records, smem_bytes, st); break;
+                default: rc = launch_cheb_persistent<8, 6>(*this, r, coef, *zc, *zp, smem_records, smem_bytes, st); break;
+            }
         }
-        if ((degree - 1) & 1) std::swap(*zc, *zp);      // z_1 in zc; every further step swaps the roles
-        launches += degree - 1;
-        cols += (int64_t)(degree - 1) * ncols;
-        return DS_OK;
+        if (rc < 0) return rc;
+        if (rc == DS_OK) {
+            if ((degree - 1) & 1) std::swap(*zc, *zp);      // z_1 in zc; every further step swaps the roles
+            launches += degree - 1;
+            cols += (int64_t)(degree - 1) * ncols;
+            return DS_OK;
+        }
+        persistent = false;          // cooperative launch refused: one launch per step from now on
+        rho = 1.0 / sig;
     }
     if (from_zero) {
         DS_TRY(jacobi32(invD, r, n_nodes, ncols, (float)(1.0 / theta), *zc, st));
