@@ -14,9 +14,11 @@ timeout 900 ncu --set full --clock-control none --import-source on \
     -k regex:'k_spmm32v|k_gram_sym|k_rr_update|k_spmm_dual|k_eigh|k_block_gemm|k_cheb32_persistent|k_assemble_rows|k_eigval_grad' \
     --launch-skip 100 --launch-count 40 -f -o gpurun_out/${TAG}_full python scripts/profile_step.py 32 1 > gpurun_out/${TAG}_full.log 2>&1; echo "ncu full rc=$?"
 ncu -i gpurun_out/${TAG}_full.ncu-rep --page raw --csv > gpurun_out/${TAG}_full_raw.csv 2>/dev/null
+rm -f gpurun_out/${TAG}_full.ncu-rep      # gpurun_out/ travels back only below 64 MiB: keep the CSV export
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_synth -c 5 -f -o gpurun_out/${TAG}_synth \
     python scripts/bench_synth.py 1024 256 88200 1 > /dev/null 2>&1; echo "ncu synth rc=$?"
 ncu -i gpurun_out/${TAG}_synth.ncu-rep --page raw --csv > gpurun_out/${TAG}_synth_raw.csv 2>/dev/null
+rm -f gpurun_out/${TAG}_synth.ncu-rep
 timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/${TAG}_bench_reference.json 2>/dev/null; echo "reference arm rc=$?"
 timeout 300 python scripts/bench_synth.py > gpurun_out/${TAG}_synth.json 2>/dev/null
 timeout 300 python scripts/bench_material.py > gpurun_out/${TAG}_material.json 2>/dev/null
