@@ -121,6 +121,15 @@ class PMG:
         return self.sm.spmm + 0  # fine spmm so far (excluding the residual ones, added by caller)
 
 
+class PMGTwice(PMG):
+    """two V-cycles per application: z = V r + V (r - A V r)  (symmetric: 2V - V A V)"""
+
+    def __call__(self, r):
+        r = r.astype(self.dtype)
+        z = PMG.__call__(self, r)
+        return z + PMG.__call__(self, r - self.A @ z)
+
+
 class PMGDeflated(PMG):
     """V-cycle whose coarse solve is deflated by the lowest coarse eigenvectors Q (from the nested P1
     eigen-solve): zc = Q Th^-1 Q^T rc + Cheb(rc - Mc Q Q^T rc) -- the polynomial then only has to cover the
@@ -237,7 +246,7 @@ def main():
             dt = np.float32 if "f32" in parts else np.float64
             P, corners = prolongation(pt, pv.shape[0])
             defl = [q for q in parts if q.startswith("defl")]
-            pre = (PMGDeflated if defl else PMG)(K, P, nu, smr, cdeg, cr, dt)
+            pre = (PMGDeflated if defl else (PMGTwice if "twice" in parts else PMG))(K, P, nu, smr, cdeg, cr, dt)
             t0 = time.time()
             Xs = X0.copy()
             if "nested" in parts:
