@@ -35,6 +35,32 @@ def test_library_exports_every_declared_symbol():
     assert isinstance(_lib.last_error(), str)
 
 
+def test_cabi_rejects_bad_arguments_with_a_message():
+    """Argument validation happens before any device work: null pointers, empty meshes and unsupported shapes
+    come back as DS_ERR_ARG (-2) with a message in ds_last_error(), never as a crash (reference debug build:
+    std::runtime_error -> RuntimeError, include/macro.h:109-124)."""
+    from diffsound_b200 import _lib
+    lib = _lib.load()
+    N = None
+    cases = [
+        lambda: lib.ds_assemble_km(N, N, 0, 2, 0, 1.0, 1.0, N, N, N, N, N, N, 0, N, N, N, N),
+        lambda: lib.ds_assemble_mass_coo(N, N, 4, 7, N, 1.0, N, N, N, N),                  # order 7
+        lambda: lib.ds_spmm32(0, N, N, 10, 48, N, N, N, N, N, 0.0, 0.0, N, N),
+        lambda: lib.ds_spmm32(5, N, N, 10, 48, N, N, N, N, N, 0.0, 0.0, N, N),             # unknown mode
+        lambda: lib.ds_lobpcg(N, N, N, 10, N, N, N, N, 48, N, N, N, N, N),
+        lambda: lib.ds_modal_synth_fwd(N, N, N, 0, 0, 0, 44100.0, N, N, N),
+        lambda: lib.ds_unique_rows3_count(N, N, 0, N, N),
+        lambda: lib.ds_rr_update_f64(N, N, N, 144, 144, 40, N, N, 48, 144, 10, N, N, N, 144, N),   # m = 40
+        lambda: lib.ds_cheb32_solve(N, N, N, 10, 10, N, 48, 0, 1.0, 2.0, 1, N, N, N, N),
+        lambda: lib.ds_gram_f64(N, 8, 12, N, 8, 8, 10, N, 8, N, N),                        # p not a multiple of 8
+    ]
+    for i, call in enumerate(cases):
+        rc = call()
+        assert rc == -2, (i, rc)
+        msg = _lib.last_error()
+        assert isinstance(msg, str) and len(msg) > 8, (i, msg)
+
+
 def test_no_compute_without_gpu_and_no_cpu_fallback():
     if torch.cuda.is_available():
         pytest.skip("GPU present")
