@@ -12,12 +12,6 @@ int spmm_dual(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, const d
               const double* X, int64_t ldx, int ncols, double* YK, int64_t ldyk, double* YM, int64_t ldym,
               cudaStream_t stream, const int32_t* order = nullptr, const int32_t* chunk_row = nullptr, int nchunks = 0);
 int spmm32_chunk_count(int64_t n_nodes);
-int block_jacobi(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, const double* Kval, const double* Mblk,
-                 double shift, double* invD, cudaStream_t stream);
-// `degree` block-Jacobi Chebyshev steps on K + shift*M applied to R; result points at Z0 or Z1.
-int cheb_precond(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, const double* Kval, const double* Mblk,
-                 double shift, const double* invD, double lmin, double lmax, int degree, const double* R, int64_t ldr,
-                 int ncols, double* Z0, double* Z1, int64_t ldz, double** result, cudaStream_t stream);
 
 // precond32.cu -- FP32 preconditioner pieces
 struct ColIdx {

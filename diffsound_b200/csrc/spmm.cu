@@ -143,16 +143,6 @@ k_spmm_dual(const int32_t* __restrict__ brow, const int32_t* __restrict__ bcol, 
 constexpr int SD2_THREADS = 768;
 constexpr int SD2_AHEAD = 96;
 
-__device__ __forceinline__ double ldg_na_f64(const double* p) {
-    double v;
-    asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ int ldg_na_s32(const int32_t* p) {
-    int v;
-    asm("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
 __device__ __forceinline__ void st_na_f64(double* p, double v) {
     asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
@@ -219,7 +209,8 @@ k_spmm_dual_v2(const int32_t* __restrict__ brow, const int32_t* __restrict__ bco
 #pragma unroll
             for (int c = 0; c < 3; ++c)
 #pragma unroll
-                for (int d = 0; d < 3; ++d) k[c][d] = __ldg(kp + c * rs + d);      // line reuse across p: keep in L1
+                for (int d = 0; d < 3; ++d) k[c][d] = __ldg(kp + c * rs + d);      // line reuse across p: normal L1 policy
+                                                                                     // (no_allocate and evict_first both measured slower)
             const double m = __ldg(Mblk + b0 + p);
 #pragma unroll
             for (int c = 0; c < 3; ++c)
@@ -249,94 +240,6 @@ k_spmm_dual_v2(const int32_t* __restrict__ brow, const int32_t* __restrict__ bco
                 else st_na_f64(YM + (3 * row + c) * ldym + col, accm[c][t]);
             }
     }
-}
-
-// One Chebyshev step on A = K + shift*M with block-Jacobi scaling:
-//   z_new = z + ab (z - z_prev) + cc * invD (R - A z)      (z_prev buffer is overwritten by z_new)
-// first == true:  z_new = cc * invD R   (z = 0)
-template <int CPL>
-__global__ void __launch_bounds__(256)
-k_cheb_step(const int32_t* __restrict__ brow, const int32_t* __restrict__ bcol, int64_t n_nodes,
-            const double* __restrict__ Kval, const double* __restrict__ Mblk, double shift,
-            const double* __restrict__ invD, const double* __restrict__ R, int64_t ldr,
-            const double* __restrict__ Z, double* __restrict__ Zprev_new, int64_t ldz, double ab, double cc,
-            int first) {
-    int lane = threadIdx.x & 31, half = lane >> 4, cl = lane & 15;
-    int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    if (row >= n_nodes) return;
-    int64_t b0 = brow[row];
-    int deg = (int)(brow[row + 1] - b0);
-    double acc[3][CPL], accm[3][CPL];
-    if (!first) {
-        row_product<CPL, true, true, false>(bcol, Kval, Mblk, shift, Z, ldz, b0, deg, half, cl, acc, accm);
-    } else {
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-#pragma unroll
-            for (int t = 0; t < CPL; ++t) acc[c][t] = 0.0;
-    }
-    double di[9];
-#pragma unroll
-    for (int q = 0; q < 9; ++q) di[q] = __ldg(invD + 9 * row + q);
-#pragma unroll
-    for (int t = 0; t < CPL; ++t) {
-        if ((t & 1) != half) continue;
-        int64_t col = cl + 16 * t;
-        double r0 = R[(3 * row + 0) * ldr + col] - acc[0][t];
-        double r1 = R[(3 * row + 1) * ldr + col] - acc[1][t];
-        double r2 = R[(3 * row + 2) * ldr + col] - acc[2][t];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            double dr = di[3 * c] * r0 + di[3 * c + 1] * r1 + di[3 * c + 2] * r2;
-            int64_t o = (3 * row + c) * ldz + col;
-            double v;
-            if (first) {
-                v = cc * dr;
-            } else {
-                double z = Z[o], zp = Zprev_new[o];
-                v = z + ab * (z - zp) + cc * dr;
-            }
-            Zprev_new[o] = v;
-        }
-    }
-}
-
-// invD[node] = inverse of the 3x3 diagonal block of K + shift*M
-__global__ void k_block_jacobi(const int32_t* __restrict__ brow, const int32_t* __restrict__ bcol, int64_t n_nodes,
-                               const double* __restrict__ Kval, const double* __restrict__ Mblk, double shift,
-                               double* __restrict__ invD) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= n_nodes) return;
-    int64_t b0 = brow[i];
-    int deg = (int)(brow[i + 1] - b0);
-    int lo = 0, hi = deg - 1, p = -1;
-    while (lo <= hi) {
-        int mid = (lo + hi) >> 1;
-        int32_t j = bcol[b0 + mid];
-        if (j == i) { p = mid; break; }
-        if (j < i) lo = mid + 1; else hi = mid - 1;
-    }
-    double A[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-    if (p >= 0) {
-        double m = Mblk ? Mblk[b0 + p] : 0.0;
-        for (int c = 0; c < 3; ++c)
-            for (int d = 0; d < 3; ++d)
-                A[c][d] = Kval[9 * b0 + (int64_t)c * 3 * deg + 3 * p + d] + (c == d ? shift * m : 0.0);
-    }
-    double c00 = A[1][1] * A[2][2] - A[1][2] * A[2][1];
-    double c01 = A[1][2] * A[2][0] - A[1][0] * A[2][2];
-    double c02 = A[1][0] * A[2][1] - A[1][1] * A[2][0];
-    double id = 1.0 / (A[0][0] * c00 + A[0][1] * c01 + A[0][2] * c02);
-    double* o = invD + 9 * i;
-    o[0] = c00 * id;
-    o[1] = (A[0][2] * A[2][1] - A[0][1] * A[2][2]) * id;
-    o[2] = (A[0][1] * A[1][2] - A[0][2] * A[1][1]) * id;
-    o[3] = c01 * id;
-    o[4] = (A[0][0] * A[2][2] - A[0][2] * A[2][0]) * id;
-    o[5] = (A[0][2] * A[1][0] - A[0][0] * A[1][2]) * id;
-    o[6] = c02 * id;
-    o[7] = (A[0][1] * A[2][0] - A[0][0] * A[2][1]) * id;
-    o[8] = (A[0][0] * A[1][1] - A[0][1] * A[1][0]) * id;
 }
 
 static inline unsigned row_blocks(int64_t n_nodes) { return (unsigned)ceil_div(n_nodes * 32, 256); }
@@ -404,57 +307,6 @@ int spmm_dual(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, const d
     }
     DS_DISPATCH_CPL(cpl, (k_spmm_dual<CPL><<<g, 256, 0, stream>>>(brow, bcol, n_nodes, Kval, Mblk, X, ldx, YK, ldyk, YM,
                                                                   ldym)));
-    DS_LAUNCH_CHECK();
-    return DS_OK;
-}
-
-int block_jacobi(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, const double* Kval, const double* Mblk,
-                 double shift, double* invD, cudaStream_t stream) {
-    k_block_jacobi<<<(unsigned)ceil_div(n_nodes, 128), 128, 0, stream>>>(brow, bcol, n_nodes, Kval, Mblk, shift, invD);
-    DS_LAUNCH_CHECK();
-    return DS_OK;
-}
-
-int cheb_precond(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, const double* Kval, const double* Mblk,
-                 double shift, const double* invD, double lmin, double lmax, int degree, const double* R, int64_t ldr,
-                 int ncols, double* Z0, double* Z1, int64_t ldz, double** result, cudaStream_t stream) {
-    DS_REQUIRE(ncols > 0 && ncols % 16 == 0 && ncols <= 128, "cheb: ncols=%d must be a multiple of 16 <= 128", ncols);
-    DS_REQUIRE(degree >= 1, "cheb: degree must be >= 1");
-    unsigned g = row_blocks(n_nodes);
-    int cpl = ncols / 16;
-    double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sig = theta / delta;
-    double rho = 1.0 / sig;
-    ProfScope prof(PROF_CHEB, stream);
-    // z1 = (1/theta) invD R  -> Z0
-    DS_DISPATCH_CPL(cpl, (k_cheb_step<CPL><<<g, 256, 0, stream>>>(brow, bcol, n_nodes, Kval, Mblk, shift, invD, R, ldr,
-                                                                  Z0, Z0, ldz, 0.0, 1.0 / theta, 1)));
-    DS_LAUNCH_CHECK();
-    double* zc = Z0;   // z_k
-    double* zp = Z1;   // z_{k-1} (z_0 = 0 for the first real step)
-    for (int k = 1; k < degree; ++k) {
-        double rho_new = 1.0 / (2.0 * sig - rho);
-        double ab = rho_new * rho;
-        double cc = 2.0 * rho_new / delta;
-        if (k == 1) DS_CUDA(cudaMemsetAsync(zp, 0, sizeof(double) * 3 * n_nodes * ldz, stream));
-        DS_DISPATCH_CPL(cpl, (k_cheb_step<CPL><<<g, 256, 0, stream>>>(brow, bcol, n_nodes, Kval, Mblk, shift, invD, R,
-                                                                      ldr, zc, zp, ldz, ab, cc, 0)));
-        DS_LAUNCH_CHECK();
-        double* t = zc; zc = zp; zp = t;
-        rho = rho_new;
-    }
-    *result = zc;
-    return DS_OK;
-}
-
-int cheb_single_step(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, const double* Kval, const double* Mblk,
-                     double shift, const double* invD, const double* R, int64_t ldr, int ncols, const double* Z,
-                     double* Zprev_new, int64_t ldz, double ab, double cc, cudaStream_t stream) {
-    DS_REQUIRE(ncols > 0 && ncols % 16 == 0 && ncols <= 128, "cheb: ncols=%d must be a multiple of 16 <= 128", ncols);
-    unsigned g = row_blocks(n_nodes);
-    int cpl = ncols / 16;
-    ProfScope prof(PROF_CHEB, stream);
-    DS_DISPATCH_CPL(cpl, (k_cheb_step<CPL><<<g, 256, 0, stream>>>(brow, bcol, n_nodes, Kval, Mblk, shift, invD, R, ldr, Z,
-                                                                  Zprev_new, ldz, ab, cc, 0)));
     DS_LAUNCH_CHECK();
     return DS_OK;
 }

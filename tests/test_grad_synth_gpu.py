@@ -122,7 +122,7 @@ def _rand_modes(k, seed=0):
 
 
 @pytest.mark.parametrize("B,k,T,sr", [(1, 16, 8000, 32000), (3, 40, 5000, 44100), (4, 256, 88200, 44100),
-                                       (70, 33, 1001, 44100)])
+                                       (70, 33, 1001, 44100), (1, 1, 1, 44100), (2, 3, 5, 8000), (130, 130, 261, 44100)])
 def test_synth_forward_vs_closed_form(B, k, T, sr):
     from diffsound_b200 import native
     d, fd = _rand_modes(k, seed=k)
@@ -136,7 +136,8 @@ def test_synth_forward_vs_closed_form(B, k, T, sr):
     assert err <= 5e-6, err   # the kernel itself is far inside the budget
 
 
-@pytest.mark.parametrize("B,k,T,sr", [(2, 16, 4000, 32000), (5, 40, 9000, 44100), (66, 33, 700, 44100)])
+@pytest.mark.parametrize("B,k,T,sr", [(2, 16, 4000, 32000), (5, 40, 9000, 44100), (66, 33, 700, 44100), (1, 1, 2, 44100),
+                                       (130, 131, 259, 44100), (3, 300, 4100, 44100)])
 def test_synth_backward_vs_autograd(B, k, T, sr):
     from diffsound_b200 import native
     d, fd = _rand_modes(k, seed=3)
