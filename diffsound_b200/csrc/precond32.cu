@@ -125,6 +125,11 @@ __device__ __forceinline__ uint4 ldg_na_u4(const uint4* p) {
     asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
+__device__ __forceinline__ uint32_t ldg_na_u32(const uint32_t* p) {
+    uint32_t v;
+    asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ void ldg_v2u64(const float* p, u64& a, u64& b) {
     asm("ld.global.nc.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
 }
@@ -199,11 +204,11 @@ __device__ __forceinline__ void st_row_stream(float* row, int l, const float* v)
 
 // acc[c][:] += K[c][:] . X[3j..3j+2][cols of this lane] for one block record read from global
 template <int LPR, int CPT, bool PEER>
-__device__ __forceinline__ void block_fma_v(const uint4* __restrict__ r, const float* __restrict__ X,
+__device__ __forceinline__ void block_fma_v(const uint4* __restrict__ r, uint32_t ja, const float* __restrict__ X,
                                             const PeerTable& tab, int l, u64 (&acc)[3][CPT / 2]) {
     constexpr int C = LPR * CPT, NP = CPT / 2;
+    const float* xr = node_rows<PEER, C>(X, tab, ja);
     const uint4 a2 = ldg_na_u4(r + 2), a0 = ldg_na_u4(r), a1 = ldg_na_u4(r + 1);
-    const float* xr = node_rows<PEER, C>(X, tab, a2.y);
     u64 x[3][NP];
 #pragma unroll
     for (int d = 0; d < 3; ++d) ld_row2<LPR, CPT>(xr + d * C, l, x[d]);
@@ -219,15 +224,17 @@ __device__ __forceinline__ void block_fma_v(const uint4* __restrict__ r, const f
 }
 
 template <int LPR, int CPT, bool PEER>
-__device__ __forceinline__ void block_fma2_v(const uint4* __restrict__ ra, const uint4* __restrict__ rb,
-                                             const float* __restrict__ X, const PeerTable& tab, int l,
+__device__ __forceinline__ void block_fma2_v(const uint4* __restrict__ ra, const uint4* __restrict__ rb, uint32_t ja,
+                                             uint32_t jb, const float* __restrict__ X, const PeerTable& tab, int l,
                                              u64 (&acc)[3][CPT / 2]) {
     constexpr int C = LPR * CPT, NP = CPT / 2;
+    // the column ids arrive from the previous iteration (software pipelining): the X loads go out together with the
+    // loads of the K values instead of one L2 round trip behind them
+    const float* xa = node_rows<PEER, C>(X, tab, ja);
+    const float* xb = node_rows<PEER, C>(X, tab, jb);
     const uint4 a2 = ldg_na_u4(ra + 2), b2 = ldg_na_u4(rb + 2);
     const uint4 a0 = ldg_na_u4(ra), a1 = ldg_na_u4(ra + 1);
     const uint4 b0 = ldg_na_u4(rb), b1 = ldg_na_u4(rb + 1);
-    const float* xa = node_rows<PEER, C>(X, tab, a2.y);
-    const float* xb = node_rows<PEER, C>(X, tab, b2.y);
     u64 x[3][NP], y[3][NP];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -307,9 +314,17 @@ k_spmm32v(const int32_t* __restrict__ brow, const uint4* __restrict__ rec, const
 #pragma unroll
             for (int t = 0; t < NP; ++t) acc[c][t] = 0ull;
         int p = rb0 + g;
-        for (; p + NG < rb1; p += 2 * NG)
-            block_fma2_v<LPR, CPT, PEER>(rec + (int64_t)3 * p, rec + (int64_t)3 * (p + NG), X, tab, l, acc);
-        if (p < rb1) block_fma_v<LPR, CPT, PEER>(rec + (int64_t)3 * p, X, tab, l, acc);
+        const uint32_t* colw = reinterpret_cast<const uint32_t*>(rec) + 9;         // word 9 of a record = column id
+        uint32_t ja = p < rb1 ? ldg_na_u32(colw + (int64_t)S32_REC_WORDS * p) : 0u;
+        uint32_t jb = p + NG < rb1 ? ldg_na_u32(colw + (int64_t)S32_REC_WORDS * (p + NG)) : 0u;
+        for (; p + NG < rb1; p += 2 * NG) {
+            const uint32_t jan = p + 2 * NG < rb1 ? ldg_na_u32(colw + (int64_t)S32_REC_WORDS * (p + 2 * NG)) : 0u;
+            const uint32_t jbn = p + 3 * NG < rb1 ? ldg_na_u32(colw + (int64_t)S32_REC_WORDS * (p + 3 * NG)) : 0u;
+            block_fma2_v<LPR, CPT, PEER>(rec + (int64_t)3 * p, rec + (int64_t)3 * (p + NG), ja, jb, X, tab, l, acc);
+            ja = jan;
+            jb = jbn;
+        }
+        if (p < rb1) block_fma_v<LPR, CPT, PEER>(rec + (int64_t)3 * p, ja, X, tab, l, acc);
 #pragma unroll
         for (int off = LPR; off < 32; off <<= 1)
 #pragma unroll

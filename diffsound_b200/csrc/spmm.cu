@@ -196,8 +196,10 @@ k_spmm_dual_v2(const int32_t* __restrict__ brow, const int32_t* __restrict__ bco
             for (int t = 0; t < CPL; ++t) acc[c][t] = accm[c][t] = 0.0;
         const double* kbase = Kval + 9 * b0;
         const int64_t rs = 3 * (int64_t)deg;
+        int jn = half < deg ? __ldg(bcol + b0 + half) : 0;        // column id one block ahead (software pipelining)
         for (int p = half; p < deg; p += 2) {
-            const int64_t j = __ldg(bcol + b0 + p);
+            const int64_t j = jn;
+            if (p + 2 < deg) jn = __ldg(bcol + b0 + p + 2);
             const double* xr = X + 3 * j * ldx + cl;
             double x[3][CPL];
 #pragma unroll
