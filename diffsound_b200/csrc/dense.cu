@@ -275,6 +275,9 @@ __global__ void __launch_bounds__(BG_THREADS)
 k_rr_update(const __grid_constant__ RRUpdateArgs g) {
     extern __shared__ __align__(16) double Cs[];  // C1s [prow][qs1] | C2s [prow - m][qs2]
     constexpr int q1 = 8 * QT1, q2 = 8 * QT2;
+    constexpr int NS = 2;                          // row strips per warp: every B fragment read from shared memory
+                                                   // feeds NS DMMAs (the one-strip version ran at 96 % of the
+                                                   // shared-memory pipe and 74 % of the FP64 tensor pipe)
     const int qs1 = pad8mod16(q1), qs2 = QT2 ? pad8mod16(q2) : 0;
     double* C1s = Cs;
     double* C2s = Cs + (size_t)g.prow * qs1;
@@ -294,48 +297,73 @@ k_rr_update(const __grid_constant__ RRUpdateArgs g) {
     const int kk = lane & 3, mm = lane >> 2;
     const int64_t n_strips = (g.n + 7) / 8;
     const int p = g.prow, m = g.m;
-    for (int64_t strip = blockIdx.x * 8 + warp; strip < n_strips; strip += (int64_t)gridDim.x * 8) {
-        const int64_t row = strip * 8 + mm;
-        const bool ok = row < g.n;
-        const double* ap = A + (ok ? row : 0) * g.lda + kk;
-        double acc1[QT1][2], acc2[QT2 ? QT2 : 1][2];
+    for (int64_t strip = ((int64_t)blockIdx.x * 8 + warp) * NS; strip < n_strips; strip += (int64_t)gridDim.x * 8 * NS) {
+        bool ok[NS];
+        const double* ap[NS];
 #pragma unroll
-        for (int t = 0; t < QT1; ++t) acc1[t][0] = acc1[t][1] = 0.0;
+        for (int s = 0; s < NS; ++s) {
+            const int64_t row = (strip + s) * 8 + mm;
+            ok[s] = row < g.n;
+            ap[s] = A + (ok[s] ? row : 0) * g.lda + kk;
+        }
+        double acc1[NS][QT1][2], acc2[NS][QT2 ? QT2 : 1][2];
 #pragma unroll
-        for (int t = 0; t < (QT2 ? QT2 : 1); ++t) acc2[t][0] = acc2[t][1] = 0.0;
-        double a[4], an[4];
+        for (int s = 0; s < NS; ++s) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) a[u] = (ok && 4 * u < p) ? __ldg(ap + 4 * u) : 0.0;
+            for (int t = 0; t < QT1; ++t) acc1[s][t][0] = acc1[s][t][1] = 0.0;
+#pragma unroll
+            for (int t = 0; t < (QT2 ? QT2 : 1); ++t) acc2[s][t][0] = acc2[s][t][1] = 0.0;
+        }
+        double a[NS][4], an[NS][4];
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) a[s][u] = (ok[s] && 4 * u < p) ? __ldg(ap[s] + 4 * u) : 0.0;
         for (int k0 = 0; k0 < p; k0 += 16) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) an[u] = (ok && (k0 + 16 + 4 * u) < p) ? __ldg(ap + k0 + 16 + 4 * u) : 0.0;
+            for (int s = 0; s < NS; ++s)
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    an[s][u] = (ok[s] && (k0 + 16 + 4 * u) < p) ? __ldg(ap[s] + k0 + 16 + 4 * u) : 0.0;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int k = k0 + 4 * u;
                 if (k < p) {
                     const double* bp = C1s + (k + kk) * qs1 + mm;
 #pragma unroll
-                    for (int t = 0; t < QT1; ++t) dmma_m8n8k4(acc1[t][0], acc1[t][1], a[u], bp[8 * t]);
+                    for (int t = 0; t < QT1; ++t) {
+                        const double b = bp[8 * t];
+#pragma unroll
+                        for (int s = 0; s < NS; ++s) dmma_m8n8k4(acc1[s][t][0], acc1[s][t][1], a[s][u], b);
+                    }
                     if (QT2 && k >= m) {
                         const double* cp = C2s + (k - m + kk) * qs2 + mm;
 #pragma unroll
-                        for (int t = 0; t < QT2; ++t) dmma_m8n8k4(acc2[t][0], acc2[t][1], a[u], cp[8 * t]);
+                        for (int t = 0; t < QT2; ++t) {
+                            const double b = cp[8 * t];
+#pragma unroll
+                            for (int s = 0; s < NS; ++s) dmma_m8n8k4(acc2[s][t][0], acc2[s][t][1], a[s][u], b);
+                        }
                     }
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) a[u] = an[u];
+            for (int s = 0; s < NS; ++s)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) a[s][u] = an[s][u];
         }
-        if (ok) {
-            double* yp = Y + row * g.ldy + 2 * kk;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            if (!ok[s]) continue;
+            double* yp = Y + ((strip + s) * 8 + mm) * g.ldy + 2 * kk;
 #pragma unroll
             for (int t = 0; t < QT1; ++t)
-                *reinterpret_cast<double2*>(yp + 8 * t) = make_double2(acc1[t][0], acc1[t][1]);
+                *reinterpret_cast<double2*>(yp + 8 * t) = make_double2(acc1[s][t][0], acc1[s][t][1]);
             if (QT2) {
                 double* zp = yp + 2 * m;
 #pragma unroll
                 for (int t = 0; t < QT2; ++t)
-                    *reinterpret_cast<double2*>(zp + 8 * t) = make_double2(acc2[t][0], acc2[t][1]);
+                    *reinterpret_cast<double2*>(zp + 8 * t) = make_double2(acc2[s][t][0], acc2[s][t][1]);
             }
         }
     }
@@ -359,7 +387,7 @@ int rr_update_f64(const double* const A[3], int64_t lda, int prow, int m, const 
     ProfScope prof(PROF_GEMM, stream);
     const size_t smem = ((size_t)prow * pad8mod16(m) + (q2 ? (size_t)(prow - m) * pad8mod16(q2) : 0)) * sizeof(double);
     const int64_t strips = (n + 7) / 8;
-    const int per_buf = (int)std::min<int64_t>((strips + 7) / 8, 148 * 2);
+    const int per_buf = (int)std::min<int64_t>((strips + 15) / 16, 148 * 2);
     auto launch = [&](auto kern) -> int {
         DS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<dim3(per_buf, 3), BG_THREADS, smem, stream>>>(g);

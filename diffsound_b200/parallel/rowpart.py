@@ -3,7 +3,7 @@
 Rank r owns the contiguous slab of node rows [bounds[r], bounds[r+1]) of the block CSR (the node
 numbering is lexicographic in the coordinates, so a slab is a geometric slab and couples only to its
 two neighbours).  Every rank keeps its slab of each dense block in peer-visible memory (cudaMalloc +
-CUDA IPC); the SpMM kernel (csrc/precond32.cu, PEER variant of k_spmm32) reads the halo rows straight
+CUDA IPC); the SpMM kernel (csrc/precond32.cu, PEER variant of k_spmm32v) reads the halo rows straight
 from the neighbours' memory over NVLink -- there is no all-gather and no staging copy.  The only
 cross-rank ordering needed is a barrier between the step that writes a block and the step that gathers
 it, which the caller issues on the stream (torch.distributed).

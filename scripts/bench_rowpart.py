@@ -1,4 +1,4 @@
-"""Strong scaling of the row-partitioned FP32 SpMM (Chebyshev step, k_spmm32 PEER variant) on the
+"""Strong scaling of the row-partitioned FP32 SpMM (Chebyshev step, k_spmm32v PEER variant) on the
 bench mesh (BASELINE configs[2]: 'row-partitioned SpMM at 1/2/4/8 GPUs').  Launch with
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 scripts/bench_rowpart.py
 Every rank assembles the full matrix (replicated) and keeps only its slab of FP32 records; a step is
@@ -52,7 +52,7 @@ if world > 1:
 nbytes = pat.nnzb * 40 + pat.n_nodes * 40 + 4 * pat.n * ncols * 4
 halo = 0
 if rank == 0:
-    print(json.dumps({"what": "row-partitioned k_spmm32 Chebyshev step, strong scaling", "n_gpus": world, "ncols": ncols,
+    print(json.dumps({"what": "row-partitioned k_spmm32v Chebyshev step, strong scaling", "n_gpus": world, "ncols": ncols,
                       "ms_per_step": float(ms), "algorithmic_GB_per_step": nbytes / 1e9,
                       "aggregate_GB_per_s": nbytes / float(ms) / 1e6, "n": pat.n, "nnz": 9 * pat.nnzb,
                       "slab_rows": [b - a for a, b in zip(part.bounds[:-1], part.bounds[1:])]}), flush=True)

@@ -1,4 +1,4 @@
-"""Row-partitioned FP32 SpMM (PEER variant of k_spmm32) against the single-GPU kernel: identical
+"""Row-partitioned FP32 SpMM (PEER variant of k_spmm32v) against the single-GPU kernel: identical
 accumulation order per row, so the slabs must be BIT-EXACT.  world = 1 runs in the normal GPU suite;
 world = 2 needs two GPUs (gpurun --gpus 2) and is skipped otherwise."""
 import os
