@@ -14,10 +14,11 @@
 //   S_ab = sum_{l,m} ctab[a][b][l][m] G_l G_m^T
 //   K_ab[c][d] = |det A| ( mu (delta_cd tr S_ab + S_ab[d][c]) + lam S_ab[c][d] )
 //   M_ab = mtab[a][b] |det6V| I3.
-// Owner-computes: lane p of the warp that owns node row i sums all element
-// contributions of block (i, bcol[brow[i]+p]) in ascending element order.
+// Owner-computes: the warp that owns node row i sums all element contributions of its blocks
+// (i, bcol[brow[i]+p]) in ascending element order, the work split evenly over its lanes (k_assemble_rows).
 #include "common.cuh"
 #include "../../include/diffsound_sm100.h"
+#include <algorithm>
 
 namespace ds {
 
@@ -100,8 +101,65 @@ __global__ void k_tet_geometry(const float* __restrict__ verts, const int32_t* _
     g[13] = fabs(__dadd_rn(__dadd_rn(t1, t2), t3));
 }
 
+// one element contribution (tet e, local nodes a, b) added to a 3x3 accumulator and the mass scalar
 template <int ORDER>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void add_contribution(int pair, const double* __restrict__ geom, const double* s_ctab,
+                                                 const double* s_mtab, double mu, double lam, double (&acc)[3][3],
+                                                 double& macc) {
+    constexpr int NPE = ORDER == 1 ? 4 : 10;
+    constexpr int NPE2 = NPE * NPE;
+    const int e = pair / NPE2;
+    const int ab = pair - e * NPE2;
+    const int a = ab / NPE, b = ab - a * NPE;
+    const double* g = geom + (int64_t)e * GEOM_STRIDE;
+    double S[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    int na, nb, la[2], lb[2];
+    if (ORDER == 1) {
+        na = nb = 1;
+        la[0] = a; lb[0] = b; la[1] = lb[1] = 0;
+    } else {
+        na = c_nsup2[a]; nb = c_nsup2[b];
+        la[0] = c_sup2[a][0]; la[1] = c_sup2[a][1];
+        lb[0] = c_sup2[b][0]; lb[1] = c_sup2[b][1];
+    }
+    const double* ct = s_ctab + ab * 16;
+    for (int li = 0; li < na; ++li) {
+        const int l = la[li];
+        const double gl0 = g[3 * l], gl1 = g[3 * l + 1], gl2 = g[3 * l + 2];
+        for (int mi = 0; mi < nb; ++mi) {
+            const int m = lb[mi];
+            const double c = ct[l * 4 + m];
+            const double gm0 = g[3 * m], gm1 = g[3 * m + 1], gm2 = g[3 * m + 2];
+            const double a0 = c * gl0, a1 = c * gl1, a2 = c * gl2;
+            S[0][0] += a0 * gm0; S[0][1] += a0 * gm1; S[0][2] += a0 * gm2;
+            S[1][0] += a1 * gm0; S[1][1] += a1 * gm1; S[1][2] += a1 * gm2;
+            S[2][0] += a2 * gm0; S[2][1] += a2 * gm1; S[2][2] += a2 * gm2;
+        }
+    }
+    const double detK = g[12], detM = g[13];
+    const double tr = mu * (S[0][0] + S[1][1] + S[2][2]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            double v = mu * S[d][c] + lam * S[c][d];
+            if (c == d) v += tr;
+            acc[c][d] += detK * v;
+        }
+    macc += s_mtab[ab] * detM;
+}
+
+// Owner-computes with BALANCED lanes.  A warp owns one node row; the element contributions of all its block slots
+// form one contiguous, slot-sorted run [Q0, Q1) of the contributor list (1 .. 24+ per slot: the diagonal slot of a
+// corner node collects every tet around it, most slots one or two).  The run is cut into 32 equal chunks, one per
+// lane; a lane sums its chunk slot by slot in list order.  A slot that lies inside one chunk is written directly;
+// a slot that is cut by chunk borders leaves partial sums in shared memory (at most a head and a tail partial per
+// lane), which the lane holding the slot's first contribution adds up in lane order -- a fixed order, no atomics.
+// (The lane-per-slot version spent 7x the instructions of a balanced warp waiting for the longest slot.)
+constexpr int AS_WARPS = 4;
+
+template <int ORDER>
+__global__ void __launch_bounds__(32 * AS_WARPS)
 k_assemble_rows(const double* __restrict__ geom, const double* __restrict__ ctab_g,
                 const double* __restrict__ mtab_g, const int32_t* __restrict__ brow,
                 const int32_t* __restrict__ contrib_ptr, const int32_t* __restrict__ contrib,
@@ -110,67 +168,98 @@ k_assemble_rows(const double* __restrict__ geom, const double* __restrict__ ctab
     constexpr int NPE2 = NPE * NPE;
     __shared__ double s_ctab[NPE2 * 16];
     __shared__ double s_mtab[NPE2];
+    __shared__ double s_part[AS_WARPS][32][2][10];     // [lane][head / tail][9 stiffness entries + mass]
+    __shared__ int s_head[AS_WARPS][32];               // slot of the lane's head partial, -1: none
     for (int t = threadIdx.x; t < NPE2 * 16; t += blockDim.x) s_ctab[t] = ctab_g[t];
     for (int t = threadIdx.x; t < NPE2; t += blockDim.x) s_mtab[t] = mtab_g[t];
     __syncthreads();
-    int lane = threadIdx.x & 31;
-    int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    if (row >= n_nodes) return;
-    int64_t b0 = brow[row];
-    int deg = (int)(brow[row + 1] - b0);
-    for (int p = lane; p < deg; p += 32) {
-        int64_t s = b0 + p;
-        double acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-        double macc = 0.0;
-        int q0 = contrib_ptr[s], q1 = contrib_ptr[s + 1];
-        for (int q = q0; q < q1; ++q) {
-            int pair = contrib[q];
-            int e = pair / NPE2;
-            int ab = pair - e * NPE2;
-            int a = ab / NPE, b = ab - a * NPE;
-            const double* g = geom + (int64_t)e * GEOM_STRIDE;
-            double S[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-            int na, nb, la[2], lb[2];
-            if (ORDER == 1) {
-                na = nb = 1;
-                la[0] = a; lb[0] = b; la[1] = lb[1] = 0;
-            } else {
-                na = c_nsup2[a]; nb = c_nsup2[b];
-                la[0] = c_sup2[a][0]; la[1] = c_sup2[a][1];
-                lb[0] = c_sup2[b][0]; lb[1] = c_sup2[b][1];
-            }
-            const double* ct = s_ctab + ab * 16;
-            for (int li = 0; li < na; ++li) {
-                int l = la[li];
-                double gl0 = g[3 * l], gl1 = g[3 * l + 1], gl2 = g[3 * l + 2];
-                for (int mi = 0; mi < nb; ++mi) {
-                    int m = lb[mi];
-                    double c = ct[l * 4 + m];
-                    double gm0 = g[3 * m], gm1 = g[3 * m + 1], gm2 = g[3 * m + 2];
-                    double a0 = c * gl0, a1 = c * gl1, a2 = c * gl2;
-                    S[0][0] += a0 * gm0; S[0][1] += a0 * gm1; S[0][2] += a0 * gm2;
-                    S[1][0] += a1 * gm0; S[1][1] += a1 * gm1; S[1][2] += a1 * gm2;
-                    S[2][0] += a2 * gm0; S[2][1] += a2 * gm1; S[2][2] += a2 * gm2;
-                }
-            }
-            double detK = g[12], detM = g[13];
-            double tr = mu * (S[0][0] + S[1][1] + S[2][2]);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double (*part)[2][10] = s_part[warp];
+    int* head = s_head[warp];
+    for (int64_t row = (int64_t)blockIdx.x * AS_WARPS + warp; row < n_nodes; row += (int64_t)gridDim.x * AS_WARPS) {
+        const int b0 = brow[row];
+        const int deg = brow[row + 1] - b0;
+        const int Q0 = contrib_ptr[b0], Q1 = contrib_ptr[b0 + deg];
+        const int chunk = (Q1 - Q0 + 31) >> 5;
+        const int qa = min(Q0 + lane * chunk, Q1), qb = min(qa + chunk, Q1);
+        double* krow = Kval + 9 * (int64_t)b0;
+        const int rs = 3 * deg;
+        auto write_slot = [&](int s, const double (&acc)[3][3], double macc) {
+            double* out = krow + 3 * (s - b0);
 #pragma unroll
             for (int c = 0; c < 3; ++c)
 #pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    double v = mu * S[d][c] + lam * S[c][d];
-                    if (c == d) v += tr;
-                    acc[c][d] += detK * v;
+                for (int d = 0; d < 3; ++d) out[c * rs + d] = acc[c][d];
+            Mblk[s] = macc;
+        };
+        int head_slot = -1, tail_slot = -1;
+        if (qa < qb) {
+            // slot of the first contribution: last s in [b0, b0 + deg) with contrib_ptr[s] <= qa
+            int lo = b0, hi = b0 + deg - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (contrib_ptr[mid] <= qa) lo = mid; else hi = mid - 1;
+            }
+            int cur = lo;
+            int s_begin = contrib_ptr[cur], s_end = contrib_ptr[cur + 1];
+            double acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+            double macc = 0.0;
+            for (int q = qa; q < qb; ++q) {
+                if (q == s_end) {                    // slot `cur` ended inside this chunk
+                    if (s_begin >= qa) {
+                        write_slot(cur, acc, macc);
+                    } else {                         // it began in an earlier lane: head partial
+                        head_slot = cur;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+#pragma unroll
+                            for (int d = 0; d < 3; ++d) part[lane][0][3 * c + d] = acc[c][d];
+                        part[lane][0][9] = macc;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) acc[c][d] = 0.0;
+                    macc = 0.0;
+                    ++cur;
+                    s_begin = s_end;
+                    s_end = contrib_ptr[cur + 1];
                 }
-            macc += s_mtab[ab] * detM;
+                add_contribution<ORDER>(contrib[q], geom, s_ctab, s_mtab, mu, lam, acc, macc);
+            }
+            // the slot in progress at the end of the chunk
+            const bool began_here = s_begin >= qa, ends_here = s_end == qb;
+            if (began_here && ends_here) {
+                write_slot(cur, acc, macc);
+            } else {
+                const int side = began_here ? 1 : 0;      // began here and continues: tail partial (this lane owns the slot)
+                if (side) tail_slot = cur; else head_slot = cur;
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) part[lane][side][3 * c + d] = acc[c][d];
+                part[lane][side][9] = macc;
+            }
         }
-        double* out = Kval + 9 * b0 + 3 * p;
+        head[lane] = head_slot;
+        __syncwarp();
+        if (tail_slot >= 0) {                        // owner: own tail + the head partials of the following lanes
+            double acc[3][3];
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
+            for (int c = 0; c < 3; ++c)
 #pragma unroll
-            for (int d = 0; d < 3; ++d) out[(int64_t)c * 3 * deg + d] = acc[c][d];
-        Mblk[s] = macc;
+                for (int d = 0; d < 3; ++d) acc[c][d] = part[lane][1][3 * c + d];
+            double macc = part[lane][1][9];
+            for (int l2 = lane + 1; l2 < 32 && head[l2] == tail_slot; ++l2) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) acc[c][d] += part[l2][0][3 * c + d];
+                macc += part[l2][0][9];
+            }
+            write_slot(tail_slot, acc, macc);
+        }
+        __syncwarp();                                // partials are free for the next row
     }
 }
 
@@ -242,13 +331,14 @@ extern "C" int ds_assemble_km(const float* verts, const int32_t* tets, int64_t T
     ProfScope prof(PROF_ASSEMBLE, stream);
     k_tet_geometry<<<(unsigned)ceil_div(T, 128), 128, 0, stream>>>(verts, tets, T, npe, order, geom);
     DS_LAUNCH_CHECK();
-    unsigned blocks = (unsigned)ceil_div(n_nodes * 32, 256);
+    // grid-stride over rows: the per-order tables are staged into shared memory once per CTA
+    unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(n_nodes, AS_WARPS), 148 * 12);
     if (order == 1)
-        k_assemble_rows<1><<<blocks, 256, 0, stream>>>(geom, ctab, mtab, brow, contrib_ptr, contrib, n_nodes, mu,
-                                                       lam, Kval, Mblk);
+        k_assemble_rows<1><<<blocks, 32 * AS_WARPS, 0, stream>>>(geom, ctab, mtab, brow, contrib_ptr, contrib, n_nodes,
+                                                                 mu, lam, Kval, Mblk);
     else
-        k_assemble_rows<2><<<blocks, 256, 0, stream>>>(geom, ctab, mtab, brow, contrib_ptr, contrib, n_nodes, mu,
-                                                       lam, Kval, Mblk);
+        k_assemble_rows<2><<<blocks, 32 * AS_WARPS, 0, stream>>>(geom, ctab, mtab, brow, contrib_ptr, contrib, n_nodes,
+                                                                 mu, lam, Kval, Mblk);
     DS_LAUNCH_CHECK();
     return DS_OK;
 }
