@@ -8,8 +8,15 @@ from diffsound_b200.diffelastic.deform import Deform
 
 N = 32
 dev = torch.device("cuda:0")
-v, t = bench.kuhn_cube(N)
-obj = DiffSoundObj(torch.from_numpy(v).to(dev), torch.from_numpy(t).to(dev), mode_num=32, order=2, mat=bench.STEEL)
+MESH = os.environ.get("MESH", "")          # "" = the bench cube; "bowl" / "grid16": fixtures of tests/golden/meshes.npz
+MODES = int(os.environ.get("MODES", "32"))
+if MESH:
+    import numpy as np
+    d = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "meshes.npz"))
+    v, t = d[f"{MESH}_verts"], d[f"{MESH}_tets"].astype(np.int64)
+else:
+    v, t = bench.kuhn_cube(N)
+obj = DiffSoundObj(torch.from_numpy(v).to(dev), torch.from_numpy(t).to(dev), mode_num=MODES, order=2, mat=bench.STEEL)
 leaf = obj.tetmesh.vertices.detach().clone().requires_grad_(True)
 obj.tetmesh.vertices = leaf
 
