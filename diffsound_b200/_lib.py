@@ -87,6 +87,7 @@ SIGNATURES = {
     "ds_eigval_quadforms_material": (cint, [f32p, i32p, i64, cint, f64p, dbl, f64p, i64, cint, f64p, f64p, ptr]),
     "ds_synth_scratch_elems": (i64, [i64, cint, i64]),
     "ds_modal_synth_fwd": (cint, [f32p, f32p, f32p, i64, cint, i64, dbl, f32p, f32p, ptr]),
+    "ds_force_fir": (cint, [f32p, f32p, i64, i64, cint, cint, f32p, ptr]),
     "ds_prof_enable": (cint, [cint]),
     "ds_prof_enable_classes": (cint, [C.c_uint32]),
     "ds_prof_reset": (cint, []),

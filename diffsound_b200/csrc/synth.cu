@@ -347,6 +347,56 @@ k_synth_bwd_df(const float* __restrict__ amp, const float* __restrict__ damp, co
     }
 }
 
+// ---------------------------------------------------------------------------
+// Causal force FIR applied to the rendered audio (oscillator.py:305-309: conv1d with the flipped force, groups =
+// audio_num, padding F-1, cropped to T):   out[b,t] = sum_{i<F} force[b,i] x[b,t-i]      (reverse = 0)
+// and its adjoint w.r.t. x (backward):      out[b,t] = sum_{i<F} force[b,i] x[b,t+i]      (reverse = 1).
+// One CTA per (1024-sample tile, audio): the force and the tile (+ F-1 halo samples) are staged in shared memory,
+// each thread produces 4 consecutive samples.
+// ---------------------------------------------------------------------------
+constexpr int FIR_TILE = 1024;
+constexpr int FIR_MAXF = 2048;
+
+__global__ void __launch_bounds__(256)
+k_force_fir(const float* __restrict__ x, const float* __restrict__ force, int64_t T, int F, int reverse,
+            float* __restrict__ out) {
+    extern __shared__ float fir_sh[];          // fs[F] | xs[FIR_TILE + F - 1]
+    float* fs = fir_sh;
+    float* xs = fir_sh + F;
+    const int64_t b = blockIdx.y;
+    const int64_t t0 = (int64_t)blockIdx.x * FIR_TILE;
+    const float* xb = x + b * T;
+    for (int i = threadIdx.x; i < F; i += blockDim.x) fs[i] = __ldg(force + b * F + i);
+    // forward needs x[t0 - (F-1) .. t0 + TILE), reverse x[t0 .. t0 + TILE + F - 1)
+    const int64_t base = reverse ? t0 : t0 - (F - 1);
+    for (int i = threadIdx.x; i < FIR_TILE + F - 1; i += blockDim.x) {
+        const int64_t t = base + i;
+        xs[i] = (t >= 0 && t < T) ? __ldg(xb + t) : 0.f;
+    }
+    __syncthreads();
+    const int l = threadIdx.x * 4;             // local sample of this thread's first output
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!reverse) {
+        // out[t0 + l + e] = sum_i fs[i] xs[(l + e) + (F-1) - i]
+        for (int i = 0; i < F; ++i) {
+            const float f = fs[i];
+            const float* xp = xs + l + (F - 1) - i;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[e] = fmaf(f, xp[e], acc[e]);
+        }
+    } else {
+        for (int i = 0; i < F; ++i) {
+            const float f = fs[i];
+            const float* xp = xs + l + i;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[e] = fmaf(f, xp[e], acc[e]);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+        if (t0 + l + e < T) out[b * T + t0 + l + e] = acc[e];
+}
+
 // out[i] = sum_p partial[p][i]   (double accumulation, fixed order)
 __global__ void k_synth_reduce(const float* __restrict__ partial, int64_t nparts, int64_t width,
                                float* __restrict__ out0, int64_t split, float* __restrict__ out1) {
@@ -410,6 +460,22 @@ extern "C" int ds_modal_synth_bwd(const float* amp, const float* damp, const flo
     DS_LAUNCH_CHECK();
     k_synth_reduce<<<(unsigned)ceil_div(2 * (int64_t)k, 256), 256, 0, stream>>>(scratch, n_tiles, 2 * (int64_t)k, gdamp, k,
                                                                                 gfreq);
+    DS_LAUNCH_CHECK();
+    return DS_OK;
+}
+
+extern "C" int ds_force_fir(const float* x, const float* force, int64_t B, int64_t T, int F, int reverse, float* out,
+                            void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DS_REQUIRE(x && force && out, "ds_force_fir: null argument");
+    DS_REQUIRE(B > 0 && T > 0 && F >= 1 && F <= FIR_MAXF, "ds_force_fir: bad sizes (B=%lld T=%lld F=%d, F <= %d)",
+               (long long)B, (long long)T, F, FIR_MAXF);
+    DS_REQUIRE(B <= 65535, "ds_force_fir: batch too large");
+    DS_REQUIRE(x != out, "ds_force_fir: in-place operation is not supported");
+    ProfScope prof(PROF_SYNTH, stream);
+    dim3 grid((unsigned)ceil_div(T, FIR_TILE), (unsigned)B);
+    const size_t smem = (size_t)(2 * F + FIR_TILE) * sizeof(float);
+    k_force_fir<<<grid, 256, smem, stream>>>(x, force, T, F, reverse ? 1 : 0, out);
     DS_LAUNCH_CHECK();
     return DS_OK;
 }

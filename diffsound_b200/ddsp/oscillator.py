@@ -100,13 +100,26 @@ def modal_synth(amp, damp, freq, sample_num, sr):
     return ModalSynth.apply(amp, damp, freq, sample_num, sr)
 
 
-def _apply_force(signal, forces, audio_num, force_frame_num, sample_num):
-    """Causal FIR with the (already flipped) force, cropped to sample_num (oscillator.py:305-309).
-    A unit impulse -- what the shipped experiments use (material_sync_train.py:103-104) -- is the
-    identity and is skipped."""
-    signal = signal.unsqueeze(0)
-    signal = F.conv1d(signal, forces.to(signal.dtype), groups=audio_num, padding=force_frame_num - 1)
-    return signal.squeeze(0)[:, :sample_num]
+class ForceFIR(torch.autograd.Function):
+    """out[b,t] = sum_i force[b,i] signal[b,t-i]: the reference's conv1d with the flipped force, groups = audio_num,
+    padding F-1, cropped to sample_num (oscillator.py:305-309), as the native kernel ds_force_fir; the backward
+    pass w.r.t. the signal is its adjoint (the forces are recorded data, not parameters)."""
+
+    @staticmethod
+    def forward(ctx, signal, force):
+        ctx.save_for_backward(force)
+        return native.force_fir(signal.to(torch.float32).contiguous(), force)
+
+    @staticmethod
+    def backward(ctx, g):
+        (force,) = ctx.saved_tensors
+        return native.force_fir(g.to(torch.float32).contiguous(), force, reverse=True), None
+
+
+def _apply_force(signal, forces_natural):
+    """Causal FIR with the force.  A unit impulse -- what the shipped experiments use
+    (material_sync_train.py:103-104) -- is the identity and is skipped by the caller."""
+    return ForceFIR.apply(signal, forces_natural)
 
 
 def _is_unit_impulse(flipped_forces):
@@ -116,7 +129,8 @@ def _is_unit_impulse(flipped_forces):
 
 class _OscBase(nn.Module):
     def _setup_forces(self, forces, audio_num):
-        self.forces = torch.flip(forces.reshape(audio_num, 1, -1), [-1]).to(_device())
+        self.forces = torch.flip(forces.reshape(audio_num, 1, -1), [-1]).to(_device())      # reference attribute (flipped)
+        self._forces_natural = forces.reshape(audio_num, -1).to(_device()).to(torch.float32).contiguous()
         self.force_frame_num = forces.shape[-1]
         self._impulse = _is_unit_impulse(self.forces)
 
@@ -124,7 +138,7 @@ class _OscBase(nn.Module):
         y = modal_synth(amp, damp.reshape(-1), freq_d.reshape(-1), self.sample_num, self.sr)
         if self._impulse:
             return y
-        return _apply_force(y, self.forces, self.audio_num, self.force_frame_num, self.sample_num)
+        return _apply_force(y, self._forces_natural)
 
 
 def _rayleigh(freq_linear, alpha, beta):

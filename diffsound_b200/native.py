@@ -510,6 +510,19 @@ def modal_synth_bwd(amp, damp, freq, gy, sr):
     return gamp, gdamp, gfreq
 
 
+def force_fir(x, force, reverse=False):
+    """Causal FIR out[b,t] = sum_i force[b,i] x[b,t-i] (reverse: the adjoint sum_i force[b,i] x[b,t+i]); fp32 (B, T)."""
+    lib = _lib.load()
+    assert x.dtype == torch.float32 and force.dtype == torch.float32 and x.is_contiguous() and force.is_contiguous()
+    B, T = x.shape
+    assert force.shape[0] == B
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.ds_force_fir(_p(x), _p(force), B, T, force.shape[1], int(bool(reverse)), _p(out), _stream()),
+                   "ds_force_fir")
+    return out
+
+
 class prof:
     """Per-kernel-class device timing (ds_prof_*): `with native.prof() as p: ...; p.read()`.
     classes: names of the classes to time (None: all) -- a short list keeps the event overhead out of a

@@ -302,6 +302,13 @@ int ds_modal_synth_fwd(const float* amp, const float* damp, const float* freq, i
 int ds_modal_synth_bwd(const float* amp, const float* damp, const float* freq, const float* gy,
                        int64_t B, int k, int64_t T, double sr, float* gamp, float* gdamp,
                        float* gfreq, float* scratch, void* stream);
+/* Causal force FIR on the rendered audio, replacing F.conv1d(signal, flipped force, groups=audio_num,
+ * padding=F-1)[..., :T] of the oscillators (ddsp/oscillator.py:305-309, 139-141, 172-174, 239-241).
+ * x, out: fp32 [B x T]; force: fp32 [B x F] in natural (un-flipped) order, F <= 2048.
+ * reverse = 0: out[b,t] = sum_i force[b,i] x[b,t-i];  reverse = 1 (adjoint, the backward pass w.r.t. x):
+ * out[b,t] = sum_i force[b,i] x[b,t+i]. */
+int ds_force_fir(const float* x, const float* force, int64_t B, int64_t T, int F, int reverse, float* out,
+                 void* stream);
 
 /* ---- device-side timing per kernel class ---------------------------------------
  * Replaces the reference's opt-in torch.profiler hook of lobpcg (src/lobpcg/_lobpcg.py:357-369)

@@ -169,3 +169,42 @@ def test_synth_vs_reference_golden():
                                torch.tensor(fd.astype(np.float32), device=DEV), T, sr).cpu().numpy()
     ref = g["trad_audio_f64"]
     assert np.linalg.norm(y - ref) / np.linalg.norm(ref) <= 1e-4
+
+
+@pytest.mark.parametrize("B,T,F", [(1, 8000, 150), (3, 1000, 1), (2, 5000, 1024), (5, 1025, 7), (2, 300, 600)])
+def test_force_fir_matches_reference_conv1d(B, T, F):
+    """ds_force_fir against the reference's own expression, F.conv1d(signal, flipped force, groups, padding=F-1)[:, :T]
+    (oscillator.py:305-309), forward and backward w.r.t. the signal."""
+    import torch.nn.functional as Fn
+    from diffsound_b200.ddsp.oscillator import ForceFIR
+    g = torch.Generator().manual_seed(B * 1000 + F)
+    x = torch.randn(B, T, generator=g, dtype=torch.float64)
+    force = torch.randn(B, F, generator=g, dtype=torch.float64)
+    xr = x.clone().requires_grad_(True)
+    ref = Fn.conv1d(xr.unsqueeze(0), torch.flip(force.reshape(B, 1, F), [-1]), groups=B, padding=F - 1).squeeze(0)[:, :T]
+    w = torch.randn(B, T, generator=g, dtype=torch.float64)
+    (ref * w).sum().backward()
+    xd = x.float().to(DEV).requires_grad_(True)
+    out = ForceFIR.apply(xd, force.float().to(DEV).contiguous())
+    assert out.shape == (B, T) and out.dtype == torch.float32
+    (out * w.float().to(DEV)).sum().backward()
+    scale = float(ref.abs().max())
+    assert float((out.detach().cpu().double() - ref.detach()).abs().max()) <= 2e-5 * scale
+    gs = float(xr.grad.abs().max())
+    assert float((xd.grad.cpu().double() - xr.grad).abs().max()) <= 2e-5 * gs
+
+
+def test_oscillator_with_recorded_force_matches_fp64_reference_formula():
+    """TraditionalDampedOscillator with a non-impulse force: closed-form modal audio convolved with the force."""
+    from diffsound_b200.ddsp import oscillator as osc
+    from diffsound_b200.diffelastic.material_model import Material, MatSet
+    k, T, sr, F = 12, 4000, 32000, 150
+    rng = np.random.default_rng(5)
+    f = np.sort(rng.uniform(200, 9000, k))
+    force = rng.standard_normal((1, F)).astype(np.float32) * np.hanning(F).astype(np.float32)
+    o = osc.TraditionalDampedOscillator(torch.tensor(force), 1, k, T, sr, Material(MatSet.Ceramic))
+    y = o(torch.tensor(f.reshape(k, 1), dtype=torch.float32, device=DEV)).detach().cpu().numpy()
+    d, fd = mo.rayleigh_damping(f.astype(np.float32).astype(np.float64), 6.0, 1e-7)
+    dry = mo.synth_closed_form(np.ones((1, k)), d, fd, T, sr)[0]
+    ref = np.convolve(dry, force[0].astype(np.float64))[:T]
+    assert np.linalg.norm(y[0] - ref) / np.linalg.norm(ref) <= 1e-4
