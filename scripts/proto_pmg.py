@@ -101,7 +101,7 @@ class PMG:
         self.P = P.astype(dtype)
         Dinv = block_jacobi_inv(A)
         self.sm = Cheb(A, Dinv, nu, sm_ratio, dtype)
-        Ac = (P.T @ A @ P).tocsr()
+        Ac = (P.T @ A @ P).tocsr() if getattr(PMG, "coarse_matrix", None) is None else PMG.coarse_matrix
         self.nc = Ac.shape[0]
         self.coarse = Cheb(Ac, block_jacobi_inv(Ac), coarse_degree, coarse_ratio, dtype)
         self.dtype = dtype
@@ -207,15 +207,21 @@ def lobpcg(K, M, X, nev, precond, tol=1e-5, maxit=200, verbose=False):
 
 
 def main():
-    N = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     which = sys.argv[2:] or ["cheb", "pmg"]
-    v, t = mo.kuhn_cube(N)
+    if len(sys.argv) > 1 and not sys.argv[1].isdigit():        # a fixture of tests/golden/meshes.npz (bowl, grid16)
+        import torch
+        d = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "meshes.npz"))
+        N = sys.argv[1]
+        v, t = torch.tensor(d[f"{N}_verts"]), torch.tensor(d[f"{N}_tets"].astype(np.int64))
+    else:
+        N = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+        v, t = mo.kuhn_cube(N)
     pv, pt = mo.promote(v, t, 2)
     t0 = time.time()
     K, M = mo.assemble(pv, pt, 2, STEEL[1], STEEL[2], STEEL[0])
     n = K.shape[0]
     print(f"N={N} n={n} nnz={K.nnz} assemble {time.time() - t0:.1f}s")
-    m, nev = int(os.environ.get("PROTO_M", "48")), 38
+    m, nev = int(os.environ.get("PROTO_M", "48")), int(os.environ.get("PROTO_NEV", "38"))
     rng = np.random.default_rng(0)
     X0 = rng.standard_normal((n, m))
     p = pv.numpy().astype(np.float64); p = p - p.mean(0)
@@ -245,6 +251,13 @@ def main():
             cr = float(parts[4]) if len(parts) > 4 else 0.4 * cdeg * cdeg
             dt = np.float32 if "f32" in parts else np.float64
             P, corners = prolongation(pt, pv.shape[0])
+            PMG.coarse_matrix = None
+            if "p1" in parts:      # coarse operator = direct P1 assembly on the corner nodes (what the CUDA path does)
+                cmap = -np.ones(pv.shape[0], dtype=np.int64); cmap[corners] = np.arange(corners.size)
+                import torch as _t
+                ct = _t.tensor(cmap[pt.numpy()[:, [0, 2, 4, 9]]])
+                K1, _ = mo.assemble(pv[_t.tensor(corners)], ct, 1, STEEL[1], STEEL[2], STEEL[0])
+                PMG.coarse_matrix = sp.csr_matrix(K1)
             defl = [q for q in parts if q.startswith("defl")]
             pre = (PMGDeflated if defl else (PMGTwice if "twice" in parts else PMG))(K, P, nu, smr, cdeg, cr, dt)
             t0 = time.time()
