@@ -26,7 +26,7 @@ class LobpcgOpts(C.Structure):
                 ("sigma", C.c_double), ("cheb_ratio", C.c_double), ("n_rigid", C.c_int), ("verbose", C.c_int),
                 ("smooth_steps", C.c_int), ("coarse_degree", C.c_int), ("smooth_ratio", C.c_double),
                 ("coarse_ratio", C.c_double), ("nested", C.c_int), ("nested_tol", C.c_double),
-                ("nested_degree", C.c_int), ("coords", C.c_void_p)]
+                ("nested_degree", C.c_int), ("coords", C.c_void_p), ("locked", C.c_void_p), ("n_locked", C.c_int)]
 
 
 class PmgLevel(C.Structure):
@@ -88,6 +88,13 @@ SIGNATURES = {
     "ds_synth_scratch_elems": (i64, [i64, cint, i64]),
     "ds_modal_synth_fwd": (cint, [f32p, f32p, f32p, i64, cint, i64, dbl, f32p, f32p, ptr]),
     "ds_force_fir": (cint, [f32p, f32p, i64, i64, cint, cint, f32p, ptr]),
+    "ds_filtered_noise_fwd": (cint, [f32p, f32p, i64, cint, cint, cint, i64, dbl, f32p, ptr]),
+    "ds_filtered_noise_bwd": (cint, [f32p, f32p, f32p, i64, cint, cint, cint, i64, dbl, f32p, ptr]),
+    "ds_stft_frames": (cint, [i64, cint]),
+    "ds_stft_power": (cint, [f32p, i64, i64, cint, cint, f32p, ptr]),
+    "ds_mss_scratch_elems": (i64, [i64, i64, cint, cint]),
+    "ds_mss_loss_fwd": (cint, [f32p, f32p, i64, i64, cint, cint, cint, dbl, dbl, f32p, f64p, ptr]),
+    "ds_mss_loss_bwd": (cint, [f32p, f32p, i64, i64, cint, cint, cint, dbl, dbl, f64p, dbl, f32p, f32p, cint, ptr]),
     "ds_prof_enable": (cint, [cint]),
     "ds_prof_enable_classes": (cint, [C.c_uint32]),
     "ds_prof_reset": (cint, []),

@@ -18,7 +18,7 @@ LIB = os.path.join(HERE, "libdiffsound_sm100.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xptxas=-v",
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
 ]
 
 
@@ -27,6 +27,14 @@ def _nvcc():
         if cand and os.path.exists(cand):
             return cand
     raise RuntimeError("nvcc not found")
+
+
+def have_nvcc():
+    try:
+        _nvcc()
+        return True
+    except RuntimeError:
+        return False
 
 
 def _deps_mtime():

@@ -10,8 +10,9 @@ What differs underneath: the reference materialises (audio_num, mode_num,
 sample_num) tensors and runs cumsum/exp/sin/sum over them (oscillator.py:128-140,
 :230-242, :297-304).  Damping and damped frequency are per mode in all of these
 modules, so here the (mode_num,) vectors go to one CUDA kernel
-(`ds_modal_synth_fwd` / `_bwd`, csrc/synth.cu) through `ModalSynth`; the small
-reparameterisations and the force FIR stay in torch.  `damped_freq`, which the
+(`ds_modal_synth_fwd` / `_bwd`, csrc/synth.cu) through `ModalSynth`, the force FIR to
+`ds_force_fir` and the noise branch of `GTDampedOscillator` to `ds_filtered_noise_*`
+(csrc/noise.cu); only the small reparameterisations stay in torch.  `damped_freq`, which the
 reference exposes as a broadcast (B, k, T) tensor and the training scripts read
 as `damped_freq[:, :, 0]` (material_sync_train.py:156-159), is exposed as an
 expanded (stride-0) view of the (1, k, 1) values: same shape, no storage.
@@ -23,6 +24,7 @@ import torch.nn.functional as F
 
 from .. import native
 from ..diffelastic.material_model import Material, MatSet  # noqa: F401  (re-exported like the reference)
+from .filtered_noise import FilteredNoise
 from .utils import modifed_sigmoid
 
 
@@ -159,11 +161,12 @@ class DampedOscillator(_OscBase):
         self.mat = mat
         self.beta = WeightedSum([1, mode_num, 1], list(self.beta_list))
         self.amp = DirectValue([audio_num, mode_num, 1])
+        self.noise = FilteredNoise(audio_num, 8000)     # "not used, just for load" (oscillator.py:79): state-dict parity
         self._setup_forces(forces, audio_num)
 
     def forward(self, freq_linear, non_linear_rate=0.0, noise_rate=0.0):
-        if non_linear_rate != 0.0 or noise_rate != 0.0:
-            raise NotImplementedError("non_linear_rate / noise_rate are unused by the reference (oscillator.py:119,141)")
+        # both arguments are accepted and ignored, as in the reference: its only uses are commented out
+        # (oscillator.py:119,126,141)
         amp = self.amp().reshape(self.audio_num, self.mode_num)
         f = torch.reshape(freq_linear, (1, self.mode_num, 1))
         damp, fd = _rayleigh(f, self.alpha(), self.beta())
@@ -194,8 +197,9 @@ class GTDampedOscillator(_OscBase):
         super().__init__()
         self.audio_num, self.sr, self.sample_num, self.mode_num = audio_num, sr, sample_num, mode_num
         self.freq_linear = WeightedSum([1, mode_num, 1], f_range)
-        # the reference also allocates freq_nonlinear with dims (audio_num, mode_num, sample_num, bins)
-        # (oscillator.py:187-188); it only enters with non_linear_rate != 0, which no experiment uses.
+        # (audio_num, mode_num, sample_num, bins) parameters (oscillator.py:187-188): part of the reference's
+        # state dict and optimiser groups; they only enter the signal with non_linear_rate != 0
+        self.freq_nonlinear = WeightedSum([audio_num, mode_num, sample_num], f_range)
         bin_num = 64
         self.alpha_list = torch.exp(torch.linspace(np.log(mat.alpha / 10), np.log(mat.alpha * 100), bin_num))
         self.alpha = WeightedSum([1, mode_num, 1], list(self.alpha_list))
@@ -203,6 +207,7 @@ class GTDampedOscillator(_OscBase):
         self.mat = mat
         self.beta = WeightedSum([1, mode_num, 1], list(self.beta_list))
         self.amp = DirectValue([audio_num, mode_num, 1])
+        self.noise = FilteredNoise(audio_num, sample_num)
         self._setup_forces(forces, audio_num)
 
     def damping(self):
@@ -210,12 +215,14 @@ class GTDampedOscillator(_OscBase):
         return 0.5 * (self.alpha() + self.beta() * lbd_linear)
 
     def forward(self, non_linear_rate=0.0, noise_rate=0.0):
-        if non_linear_rate != 0.0 or noise_rate != 0.0:
-            raise NotImplementedError("non_linear_rate / noise_rate != 0 are not on the hot path")
+        if non_linear_rate != 0.0:
+            raise NotImplementedError("non_linear_rate != 0 (per-sample frequency offsets, oscillator.py:220) is not used by "
+                                      "any experiment of the reference and has no kernel here")
         amp = self.amp().reshape(self.audio_num, self.mode_num)
         damp, fd = _rayleigh(self.freq_linear(), self.alpha(), self.beta())
+        noise = self.noise()                     # drawn every call like the reference (oscillator.py:226)
         self.undamped_freq = ((2 * np.pi * fd) ** 2 + damp ** 2) ** 0.5 / (2 * np.pi)
-        return self._render(amp, damp, fd)
+        return self._render(amp, damp, fd) + noise * noise_rate
 
 
 class TraditionalDampedOscillator(_OscBase):

@@ -119,34 +119,88 @@ def build_model(mesh_dir, mode_num, order, mat, task, vertices=None, tets=None, 
     return model
 
 
+def _gram_diag(X, Y):
+    """diag(X^T Y) for (n, k) fp64 blocks, in chunks the Gram kernel accepts (<= 64 columns, multiples of 8)."""
+    k = X.shape[1]
+    out = []
+    for c0 in range(0, k, 48):
+        c1 = min(k, c0 + 48)
+        out.append(torch.diagonal(native.gram(X[:, c0:c1], Y[:, c0:c1])))
+    return torch.cat(out)
+
+
 class _EigvalShape(torch.autograd.Function):
     """get_vals(): value lambda + (u^T K u - lambda u^T M u), gradient u^T (dK - lambda dM) u w.r.t.
-    the (promoted) vertex positions."""
+    the (promoted) vertex positions.  Everything the backward pass needs is pinned in ctx at forward
+    time (eigenvectors, eigenvalues, geometry, material), as autograd does for the reference
+    (diff_model.py:390-399): a later eigen_decomposition() / update_*_matrix() on the same object
+    does not change the gradient of an earlier get_vals()."""
 
     @staticmethod
     def forward(ctx, vertices, obj):
-        ctx.obj = obj
-        X, lam = obj._X, obj.eigenvalues          # the whole eigensolver block (16 | 32 | 48 columns)
-        pat = obj.deform.pattern
+        X, lam = obj._Xpad, obj.eigenvalues          # all wanted columns, padded to a multiple of 16
+        d = obj.deform
+        pat = d.pattern
         KX, MX = native.spmm_k_and_m(pat, obj._Kval, obj._Mblk, X)
         lo, hi = 6, 6 + obj.mode_num
-        uku = torch.diagonal(native.gram(X, KX))[lo:hi]
-        umu = torch.diagonal(native.gram(X, MX))[lo:hi]
+        uku = _gram_diag(X, KX)[lo:hi]
+        umu = _gram_diag(X, MX)[lo:hi]
         predict = torch.zeros(obj.mode_num, dtype=torch.float32, device=X.device)
         predict += lam
         predict += uku - lam * umu
+        ctx.order = obj.tetmesh.order
+        ctx.lame = obj._lame_used
+        ctx.vdtype = obj.tetmesh.vertices.dtype
+        inc_ptr, inc = d.incidence
+        ctx.U = obj.U_hat                        # a view of storage that is never written again (see _start_block)
+        ctx.save_for_backward(obj._verts32, d.tets_i32, d.ctab, d.mtab(obj._density_used), lam, inc_ptr, inc)
         return predict.unsqueeze(1)
 
     @staticmethod
     def backward(ctx, g):
-        obj = ctx.obj
-        d = obj.deform
-        mu, lam_l = obj._lame_used
-        inc_ptr, inc = d.incidence
+        verts32, tets, ctab, mtab, lam, inc_ptr, inc = ctx.saved_tensors
+        mu, lam_l = ctx.lame
         gv = g.reshape(-1).to(torch.float64).contiguous()
-        grad = native.eigval_grad_shape(obj._verts32, d.tets_i32, obj.tetmesh.order, mu, lam_l, d.ctab,
-                                        d.mtab(obj._density_used), obj.U_hat, obj.eigenvalues, gv, inc_ptr, inc)
-        return grad.to(obj.tetmesh.vertices.dtype), None
+        grad = native.eigval_grad_shape(verts32, tets, ctx.order, mu, lam_l, ctab, mtab, ctx.U, lam, gv, inc_ptr, inc)
+        return grad.to(ctx.vdtype), None
+
+
+class _StiffFunc(torch.autograd.Function):
+    """y = (mu K_mu + lam K_lam) x with gradients to x (K is symmetric: K^T g) and to the two Lame
+    scalars (<g, K_mu x>, <g, K_lam x>) -- stiff_func of the reference is differentiable in both
+    (diff_model.py:314-328 through deform.py:70-165)."""
+
+    @staticmethod
+    def forward(ctx, x, mu, lam, obj):
+        Kmu, Kla = obj._unit_stiffness()
+        pat = obj.deform.pattern
+        cols = x.shape[1]
+        ys = []
+        for c0 in range(0, cols, 128):
+            c1 = min(cols, c0 + 128)
+            cp = (c1 - c0 + 15) // 16 * 16
+            xp = torch.zeros(x.shape[0], cp, dtype=torch.float64, device=x.device)
+            xp[:, :c1 - c0] = x[:, c0:c1]
+            ys.append((native.spmm(pat, Kmu, None, xp)[:, :c1 - c0], native.spmm(pat, Kla, None, xp)[:, :c1 - c0]))
+        ymu = torch.cat([a for a, _ in ys], dim=1)
+        yla = torch.cat([b for _, b in ys], dim=1)
+        ctx.obj = obj
+        ctx.save_for_backward(ymu, yla, mu, lam)
+        ctx.xdtype = x.dtype
+        return (mu.double() * ymu + lam.double() * yla).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        ymu, yla, mu, lam = ctx.saved_tensors
+        g64 = g.to(torch.float64)
+        gx = gmu = gla = None
+        if ctx.needs_input_grad[0]:
+            gx = _StiffFunc.apply(g.contiguous(), mu.detach(), lam.detach(), ctx.obj).to(ctx.xdtype)
+        if ctx.needs_input_grad[1]:
+            gmu = (g64 * ymu).sum().to(mu.dtype)
+        if ctx.needs_input_grad[2]:
+            gla = (g64 * yla).sum().to(lam.dtype)
+        return gx, gmu, gla, None
 
 
 class DiffSoundObj:
@@ -186,6 +240,8 @@ class DiffSoundObj:
         self._density_used = None
         self._lame_used = None
         self._X = None
+        self._Xpad = None
+        self._warm = []
         self._q = None
         self.eig_stats = None
 
@@ -258,20 +314,13 @@ class DiffSoundObj:
 
     # ------------------------------------------------------------------ operators
     def stiff_func(self, x_in: torch.Tensor):
-        """K(theta) x, differentiable in (E, nu): K = mu K_mu + lam K_lam (diff_model.py:314-328)."""
+        """K(theta) x, differentiable in (E, nu) and in x: K = mu K_mu + lam K_lam (diff_model.py:314-328).
+        Accepts (n,) or (n, k) like the reference, any number of columns."""
         x = x_in.unsqueeze(1) if x_in.dim() == 1 else x_in
-        Kmu, Kla = self._unit_stiffness()
-        cols = x.shape[1]
-        cp = (cols + 15) // 16 * 16
-        xp = torch.zeros(x.shape[0], cp, dtype=torch.float64, device=x.device)
-        xp[:, :cols] = x.detach()
-        pat = self.deform.pattern
-        ymu = native.spmm(pat, Kmu, None, xp)[:, :cols]
-        yla = native.spmm(pat, Kla, None, xp)[:, :cols]
         mu, lam = self.material_model.lame()
-        if torch.is_tensor(mu):
-            mu, lam = mu.to(x.device), lam.to(x.device)
-        force = (mu * ymu + lam * yla).to(x_in.dtype)
+        mu = torch.as_tensor(mu, dtype=torch.float32).to(x.device)
+        lam = torch.as_tensor(lam, dtype=torch.float32).to(x.device)
+        force = _StiffFunc.apply(x, mu, lam, self)
         return force.squeeze(1) if x_in.dim() == 1 else force
 
     def _unit_stiffness(self):
@@ -289,40 +338,51 @@ class DiffSoundObj:
         self._assemble(self.material_model.mat.density)
         self.eigen_decomposition_arpack()
 
-    def _start_block(self, m):
+    def _start_block(self, m, batch=0):
+        """Start block of batch `batch` (n, m): the previous decomposition's Ritz block of this mesh when there is
+        one (warm start; COPIED -- ds_lobpcg overwrites its block in place and earlier U_hat views / pending
+        backward passes keep the old storage), else the six analytic rigid-body modes + seeded random columns."""
         n = self.deform.pattern.n
         dev = self.deform.device
-        if self._X is not None and self._X.shape == (n, m):
-            return self._X              # warm start from the previous decomposition of this mesh
-        g = torch.Generator(device=dev).manual_seed(0)
+        prev = self._warm[batch] if batch < len(self._warm) else None
+        if prev is not None and prev.shape == (n, m):
+            return prev.clone(), True
+        g = torch.Generator(device=dev).manual_seed(batch)
         X = torch.randn(n, m, dtype=torch.float64, device=dev, generator=g)
-        p = self._verts32.double()
-        p = p - p.mean(0, keepdim=True)
-        X[:, :6] = 0
-        for c in range(3):
-            X[c::3, c] = 1
-        X[0::3, 3], X[1::3, 3] = -p[:, 1], p[:, 0]
-        X[1::3, 4], X[2::3, 4] = -p[:, 2], p[:, 1]
-        X[2::3, 5], X[0::3, 5] = -p[:, 0], p[:, 2]
-        return X
+        if batch == 0:
+            p = self._verts32.double()
+            p = p - p.mean(0, keepdim=True)
+            X[:, :6] = 0
+            for c in range(3):
+                X[c::3, c] = 1
+            X[0::3, 3], X[1::3, 3] = -p[:, 1], p[:, 0]
+            X[1::3, 4], X[2::3, 4] = -p[:, 2], p[:, 1]
+            X[2::3, 5], X[0::3, 5] = -p[:, 0], p[:, 2]
+        return X, False
+
+    #: pairs one eigensolver call has to converge at most (block 48 = 40 wanted + 8 guard columns); larger
+    #: requests (geometry_train.py:147: mode_num = 64) are solved in batches with the converged vectors locked
+    max_batch = 40
+
+    @staticmethod
+    def _block_for(need):
+        return next((c for c in (16, 32, 48) if c >= need + min(4, c // 8)), None)
 
     def eigen_decomposition_arpack(self):
         """Lowest mode_num + 6 eigenpairs of K u = lambda M u, rigid six dropped.  The name is the
         reference's (diff_model.py:335-369: SciPy ARPACK shift-invert on the CPU); the solver is the
-        device-resident LOBPCG of csrc/lobpcg.cu."""
+        device-resident LOBPCG of csrc/lobpcg.cu.  More pairs than one 48-column block holds are found in
+        batches: every batch runs M-orthogonal to the pairs already converged (ds_lobpcg_opts.locked) and
+        starts from the previous batch's guard columns."""
         k = self.mode_num
         need = k + 6
-        m = next((c for c in (16, 32, 48) if c >= need + min(4, c // 8)), None)
-        if m is None:
-            raise NotImplementedError(f"mode_num={k}: the eigensolver block is limited to 48 columns (mode_num <= 42)")
         pat = self.deform.pattern
-        if pat.n < 3 * m:
+        if pat.n < 3 * 16 or pat.n < need + 16:
             raise ValueError(f"mesh too small for {k} modes (n={pat.n})")
-        X = self._start_block(m)
         deg = int(min(40, max(8, round(pat.n ** (1.0 / 3.0) / 3.0))))
         kw = {}
         coarse = self.deform.coarse if self.two_level else None
-        if coarse is not None and 3 * coarse.n_nodes >= 3 * m:
+        if coarse is not None and 3 * coarse.n_nodes >= 3 * 48:
             # two-level p-multigrid preconditioner: P1 operator of the same mesh, same material
             mu, la = self._lame_used
             coarse.assemble(self._verts32, mu, la, coarse.ctab, self.deform.coarse_mtab(self._density_used))
@@ -330,19 +390,63 @@ class DiffSoundObj:
             cdeg = int(self.coarse_degree) or int(min(64, max(32, round((3 * coarse.n_nodes) ** (1.0 / 3.0) / 1.2))))
             cratio = float(self.coarse_ratio) or 0.4 * cdeg * cdeg
             kw = dict(coarse=coarse, smooth_steps=int(self.smooth_steps), smooth_ratio=float(self.smooth_ratio),
-                      coarse_degree=cdeg, coarse_ratio=cratio, nested=self.nested_start and self._X is not X,
-                      nested_tol=self.nested_tol, nested_degree=self.nested_degree)
-        lam, res, stats = native.lobpcg(pat, self._Kval, self._Mblk, X, nev=need, tol=self.eig_tol, maxit=self.eig_maxit,
-                                        cheb_degree=deg, cheb_ratio=0.4 * deg * deg, n_rigid=6,
-                                        coords=self._verts32 if self.morton else None, **kw)
-        if stats["status"] != 0:
-            raise RuntimeError(f"eigensolver did not converge: {stats}, max residual {float(res[:need].max()):.3e}")
-        self.eig_stats = stats
-        self._X = X
-        self.U_hat_full = X[:, :need]
-        self.eigenvalues = lam[6:need].clone()
-        self.ritz_values = lam          # all block columns (rigid six, wanted modes, guard columns)
-        self.U_hat = X[:, 6:need]
+                      coarse_degree=cdeg, coarse_ratio=cratio, nested_tol=self.nested_tol, nested_degree=self.nested_degree)
+        found_X, found_lam, warm, all_stats = [], [], [], []
+        done, batch, guard = 0, 0, None
+        while done < need:
+            want = min(need - done, self.max_batch)
+            m = self._block_for(want)
+            while pat.n < 3 * m and m > 16:
+                m -= 16
+            if m < want:
+                raise ValueError(f"mesh too small for {k} modes (n={pat.n})")
+            X, is_warm = self._start_block(m, batch)
+            if guard is not None and not is_warm:
+                gcols = min(guard.shape[1], m)
+                X[:, :gcols] = guard[:, :gcols]            # approximate next modes left over from the previous batch
+            locked = None
+            if done:
+                q = (done + 15) // 16 * 16
+                locked = torch.zeros(pat.n, q, dtype=torch.float64, device=X.device)
+                locked[:, :done] = torch.cat(found_X, dim=1)
+            if kw:
+                kw["nested"] = self.nested_start and not is_warm and batch == 0
+            lam, res, stats = native.lobpcg(pat, self._Kval, self._Mblk, X, nev=want, tol=self.eig_tol,
+                                            maxit=self.eig_maxit, cheb_degree=deg, cheb_ratio=0.4 * deg * deg,
+                                            n_rigid=6 if batch == 0 else 0,
+                                            coords=self._verts32 if self.morton else None, locked=locked, **kw)
+            if stats["status"] != 0:
+                raise RuntimeError(f"eigensolver did not converge (batch {batch}): {stats}, "
+                                   f"max residual {float(res[:want].max()):.3e}")
+            all_stats.append(stats)
+            warm.append(X)
+            found_X.append(X[:, :want])
+            found_lam.append(lam[:want])
+            guard = X[:, want:]
+            if batch == 0:
+                self.ritz_values = lam          # all block columns of the first batch (rigid six, modes, guard columns)
+            done += want
+            batch += 1
+        self._warm = warm
+        self.eig_stats = all_stats[0] if len(all_stats) == 1 else dict(
+            all_stats[0], batches=len(all_stats), iterations=sum(s["iterations"] for s in all_stats),
+            spmm=sum(s["spmm"] for s in all_stats), per_batch=all_stats)
+        if len(found_X) == 1:
+            self._X = warm[0]                    # (n, m): wanted columns + guard columns
+            self.U_hat_full = self._X[:, :need]
+            lam_all = found_lam[0]
+        else:
+            lam_all, order = torch.sort(torch.cat(found_lam))
+            self.U_hat_full = torch.cat(found_X, dim=1)[:, order].contiguous()
+            self._X = self.U_hat_full
+        self.eigenvalues = lam_all[6:need].clone()
+        self.U_hat = self.U_hat_full[:, 6:need]
+        # all wanted columns zero-padded to a multiple of 16 for the SpMM of get_vals()
+        if self._X.shape[1] % 16 == 0:
+            self._Xpad = self._X
+        else:
+            self._Xpad = torch.zeros(pat.n, (need + 15) // 16 * 16, dtype=torch.float64, device=self._X.device)
+            self._Xpad[:, :need] = self.U_hat_full
         self._q = None
 
     # ------------------------------------------------------------------ differentiable outputs

@@ -5,19 +5,24 @@ return convention: `E[:k]`, `X[:, :k]` [, rerr], ascending, B-orthonormal
 columns).  The worker is the device-resident LOBPCG of csrc/lobpcg.cu
 (`ds_lobpcg`), not a torch re-implementation.
 
-Differences that follow from running on the native solver (documented, not hidden):
+Two drivers sit behind the one signature:
 
-* the operators must have the FEM structure this library is built around:
-  A symmetric with dense 3x3 node blocks, B = (one scalar per block) (x) I3 on
-  (a subset of) the same block pattern.  The reference's K and M have exactly
-  this form ("nnz = 9 x node pairs").  Anything else
-  raises -- there is no generic or CPU fallback;
-* `largest=True` (the reference's default, never used for modal analysis:
-  src/utils/utils.py:82 passes largest=False) is not implemented;
-* computation is FP64 regardless of the input dtype (the reference's copy is
-  FP32-only because of its dtype table, SURVEY.md A.4); results are cast back;
-* `iK`, `method`, `ortho_*`, `tracker`, `profiler` are accepted for signature
-  compatibility; preconditioning is the solver's own block-Jacobi Chebyshev.
+* operators with the FEM structure this library is built around -- A symmetric with dense
+  3x3 node blocks, B = (one scalar per block) (x) I3 on (a subset of) the same block
+  pattern, which is exactly what the reference's K and M are (SURVEY.md section 8:
+  "nnz = 9 x node pairs") -- asked for their LOWEST pairs without a user preconditioner or
+  tracker go to the device-resident solver `ds_lobpcg` (its own FP32 Chebyshev / two-level
+  preconditioner);
+* everything else the reference's signature allows -- a callable `A` (the reason
+  `lobpcg_func` exists, _lobpcg.py:123-212), dense or unstructured sparse tensors,
+  `largest=True` (the reference's default), a preconditioner `iK` (tensor or callable,
+  _lobpcg.py:453,475), `tracker` / `profiler` hooks (_lobpcg.py:350-376) -- goes to the
+  operator-form worker `_generic.LOBPCG`, whose dense steps run on the library's FP64
+  Gram / eigh / block-GEMM kernels.
+
+Computation is FP64 regardless of the input dtype (the reference's copy is FP32-only because
+of its dtype table); results are cast back.  CPU tensors raise: there is no
+CPU path.  Blocks wider than 48 columns raise (Rayleigh-Ritz limit 3 x 48 = 144).
 """
 from typing import Optional
 
@@ -108,9 +113,49 @@ def _resolve(A, B):
     if callable(A) and owner is not None and hasattr(owner, "_Kval") and owner._Kval is not None:
         return BlockMatrices(owner.deform.pattern, owner._Kval, owner._Mblk)     # DiffSoundObj.stiff_func
     if callable(A) and not torch.is_tensor(A):
-        raise TypeError("lobpcg_func: a matrix-free callable cannot be handed to the CUDA solver; pass the sparse "
-                        "matrix, a BlockMatrices, or DiffSoundObj.stiff_func of an assembled model")
+        raise TypeError("matrix-free callable: operator-form driver")
+    if not torch.is_tensor(A) or A.layout == torch.strided or (B is not None and (not torch.is_tensor(B) or B.layout == torch.strided)):
+        raise TypeError("dense or non-tensor operator: operator-form driver")
     return from_torch_sparse(A, B)
+
+
+def _generic(A, k, B, X, E, n, iK, niter, tol, largest, method, tracker, ortho_iparams, ortho_fparams, ortho_bparams,
+             return_rerr, profiler):
+    """Operator-form driver: mirrors the parameter handling of _lobpcg.py:27-121 / :139-212."""
+    from ._generic import LOBPCG
+    ref = next((t for t in (X, B, A, iK) if torch.is_tensor(t)), None)
+    if ref is None:
+        raise TypeError("lobpcg: at least one of A, B, X, iK must be a tensor (to know the size and the device)")
+    if not ref.is_cuda:
+        raise RuntimeError("lobpcg: operators must be CUDA tensors (there is no CPU path)")
+    if torch.is_tensor(A):
+        assert A.shape[-2] == A.shape[-1], A.shape
+        if torch.is_tensor(B):
+            assert A.shape == B.shape, (A.shape, B.shape)
+    msize = (A if torch.is_tensor(A) else B if torch.is_tensor(B) else X).shape[-2]
+    dtype = X.dtype if X is not None else (ref.dtype if ref.dtype in (torch.float32, torch.float64) else torch.float32)
+    if tol is None:
+        tol = {torch.float32: 1.2e-07, torch.float64: 2.23e-16}[dtype] ** 0.5
+    k = (1 if X is None else X.shape[-1]) if k is None else k
+    n = (k if n is None else n) if X is None else X.shape[-1]
+    if msize < 3 * n:
+        raise ValueError("LPBPCG algorithm is not applicable when the number of A rows (={})"
+                         " is smaller than 3 x the number of requested eigenpairs (={})".format(msize, n))
+    method = "ortho" if method is None else method
+    iparams = {"m": msize, "n": n, "k": k, "niter": 1000 if niter is None else niter}
+    fparams = {"tol": tol}
+    bparams = {"largest": True if largest is None else largest}
+    for extra, tgt in ((ortho_iparams, iparams), (ortho_fparams, fparams), (ortho_bparams, bparams)):
+        if method == "ortho" and extra is not None:
+            tgt.update(extra)
+    if X is None:
+        X = torch.randn((msize, n), dtype=dtype, device=ref.device)
+    assert len(X.shape) == 2 and X.shape == (msize, n), (X.shape, (msize, n))
+    worker = LOBPCG(A, B, X, E, iK, iparams, fparams, bparams, method, tracker, profiler)
+    worker.run()
+    if return_rerr:
+        return worker.E[:k], worker.X[:, :k], worker.tvars["rerr"]
+    return worker.E[:k], worker.X[:, :k]
 
 
 def lobpcg(A, k: Optional[int] = None, B=None, X=None, E=None, n: Optional[int] = None, iK=None,
@@ -118,9 +163,15 @@ def lobpcg(A, k: Optional[int] = None, B=None, X=None, E=None, n: Optional[int] 
            method: Optional[str] = None, tracker=None, ortho_iparams=None, ortho_fparams=None, ortho_bparams=None,
            return_rerr=False, profiler=None):
     largest = True if largest is None else largest
-    if largest:
-        raise NotImplementedError("lobpcg: largest=True is not implemented (modal analysis needs largest=False)")
-    bm = _resolve(A, B)
+    bm = None
+    if not largest and iK is None and tracker is None and profiler is None:
+        try:
+            bm = _resolve(A, B)
+        except (TypeError, ValueError):
+            bm = None                    # not the FEM block structure: operator-form driver
+    if bm is None:
+        return _generic(A, k, B, X, E, n, iK, niter, tol, largest, method, tracker, ortho_iparams, ortho_fparams,
+                        ortho_bparams, return_rerr, profiler)
     pat = bm.pattern
     msize = pat.n
     k = (1 if X is None else X.shape[-1]) if k is None else k

@@ -229,6 +229,20 @@ def gram(A, B, out=None):
     return out
 
 
+def gram_sym2(S, KS, MS, tiles, GK, GM):
+    """GK = S^T KS, GM = S^T MS over the 8-column tiles `tiles` (ascending) of three (n, ld) fp64 blocks, ld <= 144,
+    in one pass (ds_gram_sym2_f64).  Only the upper-triangle tiles of GK / GM (row-major, common stride) are written."""
+    lib = _lib.load()
+    assert S.shape == KS.shape == MS.shape and S.is_contiguous() and KS.is_contiguous() and MS.is_contiguous()
+    assert GK.stride(0) == GM.stride(0) and GK.stride(1) == 1
+    n, ld = S.shape
+    scratch = torch.empty(lib.ds_gram_sym2_scratch_elems(), dtype=torch.float64, device=S.device)
+    arr = (C.c_int * len(tiles))(*[int(t) for t in tiles])
+    with torch.cuda.device(S.device):
+        _lib.check(lib.ds_gram_sym2_f64(_p(S), _p(KS), _p(MS), ld, n, arr, len(tiles), C.c_void_p(GK.data_ptr()),
+                                        C.c_void_p(GM.data_ptr()), GK.stride(0), _p(scratch), _stream()), "ds_gram_sym2_f64")
+
+
 def rr_update(bufs, prow, m, C1, C2, q2):
     """Fused LOBPCG basis update (ds_rr_update_f64): for each wide buffer A (n x 3m, fp64) returns A_out with
     A_out[:, :m] = A[:, :prow] C1 and A_out[:, 2m:2m+q2] = A[:, m:prow] C2 (other columns zero)."""
@@ -397,10 +411,12 @@ def pmg_prolong_add32(coarse, zc, z):
 
 def lobpcg(pattern, Kval, Mblk, X, nev, tol=1e-4, maxit=200, cheb_degree=8, sigma=0.0, cheb_ratio=30.0, n_rigid=6,
            verbose=0, coarse=None, smooth_steps=3, smooth_ratio=8.0, coarse_degree=20, coarse_ratio=160.0, nested=True,
-           nested_tol=3e-2, nested_degree=0, coords=None):
+           nested_tol=3e-2, nested_degree=0, coords=None, locked=None):
     """Lowest `nev` pairs of K u = lam M u from the start block X (n, m) fp64 (overwritten with the
     M-orthonormal Ritz vectors).  `coarse`: a CoarseLevel with assembled Kval -> two-level
-    preconditioner.  Returns (lam (m,), resid (m,), stats dict)."""
+    preconditioner.  `locked`: (n, q) fp64 contiguous, q a multiple of 16 -- M-orthonormal eigenvectors
+    found by earlier calls; the iteration stays M-orthogonal to them and returns the next lowest pairs.
+    Returns (lam (m,), resid (m,), stats dict)."""
     lib = _lib.load()
     assert X.dtype == torch.float64 and X.is_contiguous()
     n, m = X.shape
@@ -412,7 +428,12 @@ def lobpcg(pattern, Kval, Mblk, X, nev, tol=1e-4, maxit=200, cheb_degree=8, sigm
                            smooth_steps=int(smooth_steps), coarse_degree=int(coarse_degree),
                            smooth_ratio=float(smooth_ratio), coarse_ratio=float(coarse_ratio),
                            nested=int(bool(nested) and coarse is not None), nested_tol=float(nested_tol),
-                           nested_degree=int(nested_degree), coords=None)
+                           nested_degree=int(nested_degree), coords=None, locked=None, n_locked=0)
+    if locked is not None:
+        assert locked.dtype == torch.float64 and locked.is_contiguous() and locked.shape[0] == n
+        assert locked.shape[1] % 16 == 0 and locked.is_cuda
+        opts.locked = locked.data_ptr()
+        opts.n_locked = locked.shape[1]
     if coords is not None:
         assert coords.dtype == torch.float32 and coords.is_contiguous() and coords.shape == (pattern.n_nodes, 3)
         opts.coords = coords.data_ptr()
@@ -521,6 +542,71 @@ def force_fir(x, force, reverse=False):
         _lib.check(lib.ds_force_fir(_p(x), _p(force), B, T, force.shape[1], int(bool(reverse)), _p(out), _stream()),
                    "ds_force_fir")
     return out
+
+
+def filtered_noise_fwd(coeff, noise, T, gain=1.0):
+    """DDSP filtered noise (ds_filtered_noise_fwd): coeff (B, F, C) raw parameters, noise (B, F, L) uniform(-1, 1)
+    frames -> (B, T) fp32."""
+    lib = _lib.load()
+    assert coeff.dtype == noise.dtype == torch.float32 and coeff.is_contiguous() and noise.is_contiguous()
+    B, F, Cn = coeff.shape
+    L = noise.shape[2]
+    assert noise.shape[:2] == (B, F)
+    y = torch.empty(B, T, dtype=torch.float32, device=coeff.device)
+    with torch.cuda.device(coeff.device):
+        _lib.check(lib.ds_filtered_noise_fwd(_p(coeff), _p(noise), B, F, Cn, L, int(T), float(gain), _p(y), _stream()),
+                   "ds_filtered_noise_fwd")
+    return y
+
+
+def filtered_noise_bwd(coeff, noise, gy, gain=1.0):
+    lib = _lib.load()
+    B, F, Cn = coeff.shape
+    L = noise.shape[2]
+    g = torch.empty_like(coeff)
+    gy = gy.to(torch.float32).contiguous()
+    with torch.cuda.device(coeff.device):
+        _lib.check(lib.ds_filtered_noise_bwd(_p(coeff), _p(noise), _p(gy), B, F, Cn, L, gy.shape[1], float(gain), _p(g),
+                                             _stream()), "ds_filtered_noise_bwd")
+    return g
+
+
+def stft_power(x, n_fft, hop):
+    """Power spectrogram (B, n_fft/2+1, frames) fp32 of x (B, T): torchaudio Spectrogram(n_fft, hop) defaults."""
+    lib = _lib.load()
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2
+    B, T = x.shape
+    frames = lib.ds_stft_frames(T, int(hop))
+    S = torch.empty(B, n_fft // 2 + 1, frames, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.ds_stft_power(_p(x), B, T, int(n_fft), int(hop), _p(S), _stream()), "ds_stft_power")
+    return S
+
+
+def mss_loss_fwd(x_pred, x_true, n_fft, hop, mode, alpha, eps):
+    """One scale of the spectral loss (ds_mss_loss_fwd): returns (loss 0-dim fp64 device tensor, scratch)."""
+    lib = _lib.load()
+    assert x_pred.dtype == x_true.dtype == torch.float32 and x_pred.is_contiguous() and x_true.is_contiguous()
+    assert x_pred.shape == x_true.shape and x_pred.dim() == 2
+    B, T = x_pred.shape
+    scratch = torch.empty(lib.ds_mss_scratch_elems(B, T, int(n_fft), int(hop)) + 2, dtype=torch.float32, device=x_pred.device)
+    if scratch.data_ptr() % 8:
+        scratch = scratch[1:]
+    loss = torch.empty((), dtype=torch.float64, device=x_pred.device)
+    with torch.cuda.device(x_pred.device):
+        _lib.check(lib.ds_mss_loss_fwd(_p(x_pred), _p(x_true), B, T, int(n_fft), int(hop), int(mode), float(alpha),
+                                       float(eps), C.c_void_p(scratch.data_ptr()), _p(loss), _stream()), "ds_mss_loss_fwd")
+    return loss, scratch
+
+
+def mss_loss_bwd(x_pred, x_true, n_fft, hop, mode, alpha, eps, loss, upstream, scratch, gx, accumulate):
+    lib = _lib.load()
+    B, T = x_pred.shape
+    with torch.cuda.device(x_pred.device):
+        _lib.check(lib.ds_mss_loss_bwd(_p(x_pred), _p(x_true), B, T, int(n_fft), int(hop), int(mode), float(alpha),
+                                       float(eps), _p(loss), float(upstream), C.c_void_p(scratch.data_ptr()), _p(gx),
+                                       int(bool(accumulate)), _stream()), "ds_mss_loss_bwd")
+    return gx
 
 
 class prof:

@@ -23,6 +23,10 @@
 
 #include <stdint.h>
 
+/* The library is built with -fvisibility=hidden: only the C-ABI declared here is exported. */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -170,6 +174,11 @@ typedef struct ds_lobpcg_opts {
     const float* coords;/* device fp32 [n_nodes x 3] node coordinates or NULL.  When given, the FP32 preconditioner
                            stores its operator renumbered along a Morton curve through the nodes (a private
                            numbering: locality for the gathered rows of the SpMM); results are unaffected */
+    const double* locked;/* device fp64 [n x n_locked] (ld = n_locked) or NULL: M-orthonormal eigenvectors already
+                           converged by earlier calls.  The iteration is kept M-orthogonal to them (hard locking /
+                           deflation), so this call returns the NEXT lowest pairs: how DiffSoundObj solves
+                           mode_num + 6 > 44 pairs (geometry_train.py:147 asks for 64) in batches of one block */
+    int n_locked;       /* columns of `locked`, a multiple of 16, <= 192 (pad with zero columns) */
 } ds_lobpcg_opts;
 /* Coarse level of the two-level preconditioner: the P1 operator on the corner nodes of a quadratic
  * mesh (pattern + values from ds_pattern_* / ds_assemble_km at order 1 on ds_pmg_coarse_fill's
@@ -310,6 +319,37 @@ int ds_modal_synth_bwd(const float* amp, const float* damp, const float* freq, c
 int ds_force_fir(const float* x, const float* force, int64_t B, int64_t T, int F, int reverse, float* out,
                  void* stream);
 
+/* ---- filtered noise (the noise branch of GTDampedOscillator) ---------------------------------
+ * Replaces FilteredNoise.forward (ddsp/filtered_noise.py:20-67: irfft of a zero-phase response, roll,
+ * Hann window, FFT convolution with uniform noise frames, overlap-add by conv_transpose1d), added to
+ * the modal signal as `noise * noise_rate` (ddsp/oscillator.py:226,243; material_real_train.py:118).
+ * coeff: fp32 [B x F x C] raw coefficient_bank parameters (the modified sigmoid is applied inside);
+ * noise: fp32 [B x F x L] uniform(-1, 1) frames drawn by the caller (the reference draws them with
+ * torch.rand on the host generator); y: fp32 [B x T], F * L >= T.  C = filter_coeff_length <= 129,
+ * L = frame_length <= 256.  Backward: gy [B x T] -> gcoeff [B x F x C]. */
+int ds_filtered_noise_fwd(const float* coeff, const float* noise, int64_t B, int F, int C, int L, int64_t T,
+                          double gain, float* y, void* stream);
+int ds_filtered_noise_bwd(const float* coeff, const float* noise, const float* gy, int64_t B, int F, int C, int L,
+                          int64_t T, double gain, float* gcoeff, void* stream);
+
+/* ---- multi-scale spectral loss (one scale per call) ------------------------------------------
+ * Replaces SSSLoss (ddsp/mss_loss.py:70-121) on torchaudio.transforms.Spectrogram(n_fft, hop): periodic Hann
+ * window of n_fft, center = True / reflect padding, power 2, one-sided; frames = 1 + T / hop.
+ * ds_stft_power: S fp32 [B x (n_fft/2+1) x frames] (SSSLoss.spec / log_spec).
+ * ds_mss_loss_fwd: mode 0 = 'l1_loss' (alpha * weighted L1 of log2(S + eps) + weighted L1 of S, DC bin dropped,
+ * mss_loss.py:55-66,101-106), mode 1 = 'rmse_loss' (mss_loss.py:116-119).  x_pred, x_true: fp32 [B x T];
+ * scratch: fp32 [ds_mss_scratch_elems], 8-byte aligned; loss: one double on the device.
+ * ds_mss_loss_bwd: d(upstream * loss)/d x_pred into gx [B x T] (accumulate != 0: added to gx); `loss` is the
+ * forward result (needed by the RMSE chain rule).  No spectrogram is materialised by the loss calls. */
+int ds_stft_frames(int64_t T, int hop);
+int ds_stft_power(const float* x, int64_t B, int64_t T, int n_fft, int hop, float* S, void* stream);
+int64_t ds_mss_scratch_elems(int64_t B, int64_t T, int n_fft, int hop);
+int ds_mss_loss_fwd(const float* x_pred, const float* x_true, int64_t B, int64_t T, int n_fft, int hop, int mode,
+                    double alpha, double eps, float* scratch, double* loss, void* stream);
+int ds_mss_loss_bwd(const float* x_pred, const float* x_true, int64_t B, int64_t T, int n_fft, int hop, int mode,
+                    double alpha, double eps, const double* loss, double upstream, float* scratch, float* gx,
+                    int accumulate, void* stream);
+
 /* ---- device-side timing per kernel class ---------------------------------------
  * Replaces the reference's opt-in torch.profiler hook of lobpcg (src/lobpcg/_lobpcg.py:357-369)
  * and the TICK/TOCK macros (src/include/macro.h:31-44): CUDA events around every launch site,
@@ -327,5 +367,8 @@ int ds_prof_read(int cls, double* ms, int64_t* count);
 
 #ifdef __cplusplus
 }
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility pop
 #endif
 #endif /* DIFFSOUND_SM100_H */

@@ -14,7 +14,7 @@ obj = DiffSoundObj(torch.from_numpy(v).to(dev), torch.from_numpy(t).to(dev), mod
 leaf = obj.tetmesh.vertices.detach().clone().requires_grad_(True)
 obj.tetmesh.vertices = leaf
 for i in range(reps):
-    obj.deform = Deform(obj.tetmesh); obj._X = None; obj._Kval = obj._Mblk = None
+    obj.deform = Deform(obj.tetmesh); obj._X = None; obj._warm = []; obj._Kval = obj._Mblk = None
     torch.cuda.synchronize()
     print("MARK solve", i, flush=True)
     obj.eigen_decomposition()

@@ -22,7 +22,7 @@ obj.tetmesh.vertices = leaf
 
 
 def solve():
-    obj.deform = Deform(obj.tetmesh); obj._X = None; obj._Kval = obj._Mblk = None
+    obj.deform = Deform(obj.tetmesh); obj._X = None; obj._warm = []; obj._Kval = obj._Mblk = None
     obj.eigen_decomposition()
     vals = obj.get_vals()
     leaf.grad = None

@@ -235,11 +235,8 @@ def test_lobpcg_api_on_torch_sparse(meshes):
     vals2, vecs2, rerr = lobpcg(K.float(), k + 6, M.float(), niter=500, tol=1e-5, largest=False, return_rerr=True)
     assert vals2.dtype == torch.float32 and rerr.shape == (k + 6,)
     assert (np.abs(vals2[6:].cpu().numpy() - g["eigenvalues"]) / g["eigenvalues"]).max() <= 1e-5
-    with pytest.raises(NotImplementedError):
-        lobpcg(K, k, M)          # largest defaults to True in the reference API
-    with pytest.raises(ValueError):
-        bad = torch.sparse_coo_tensor(K.indices(), torch.ones_like(K.values()), K.shape).coalesce()
-        lobpcg(K, k, bad, largest=False)
+    with pytest.raises(RuntimeError):
+        lobpcg(K.cpu(), k, M.cpu(), largest=False)          # no CPU path
 
 
 def test_cuda_module_names(meshes):
