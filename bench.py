@@ -149,7 +149,8 @@ def cpu_reference_solve(N, order, k, threads):
     return dt, pt.shape[0], float(np.abs(g.numpy()).sum())
 
 
-CPU_CUBE_N = 16      # the CPU arm's bounded sample: 16^3 x 6 = 24 576 quadratic tets, n = 107 811 dofs
+CPU_CUBE_N = 10      # the CPU arm's bounded sample: 10^3 x 6 = 6 000 quadratic tets (n = 27 783 dofs), ~20 s per solve on
+                     # 16 host threads; 16^3 x 6 = 24 576 tets measured 266.6 s per solve (gpurun_out/r2a_bench.json)
 
 
 def cpu_baseline(sample_N, steps=1, warmup=0, budget_s=150.0):
@@ -314,14 +315,19 @@ def main():
     # the per-class breakdown comes from a second, untimed pass below
     with native.prof(classes=["cheb_step"]) as pf:
         e0.record()
+        marks = []
         for _ in range(args.steps):
             vals, grad = solve(obj, leaf)
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append(ev)
         e1.record()
         barrier()
     prof = pf.read()
     launches = int(lib.ds_launch_count() - launches0)
     sampler.stop_flag = True
     ms = e0.elapsed_time(e1)
+    each_ms = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
     with native.prof() as pf_all:
         for _ in range(2):
             solve(obj, leaf)
@@ -426,7 +432,7 @@ def main():
                 "launches_per_step": steps_total, "avg_launch_ms": t_avg * 1e3, "avg_cols": c_avg,
                 "bytes_per_launch": per_launch_bytes, "share_of_step": prof["cheb_step"]["ms"] / ms}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "ms_each_step": each_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.cube),
                        "sizes": f"n={n} dofs, nnz={9 * nnzb}; one independent mesh per GPU",

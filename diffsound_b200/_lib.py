@@ -26,7 +26,7 @@ class LobpcgOpts(C.Structure):
                 ("sigma", C.c_double), ("cheb_ratio", C.c_double), ("n_rigid", C.c_int), ("verbose", C.c_int),
                 ("smooth_steps", C.c_int), ("coarse_degree", C.c_int), ("smooth_ratio", C.c_double),
                 ("coarse_ratio", C.c_double), ("nested", C.c_int), ("nested_tol", C.c_double),
-                ("nested_degree", C.c_int), ("coords", C.c_void_p), ("locked", C.c_void_p), ("n_locked", C.c_int)]
+                ("nested_degree", C.c_int), ("coords", C.c_void_p), ("locked", C.c_void_p), ("n_locked", C.c_int), ("ortho_w", C.c_int)]
 
 
 class PmgLevel(C.Structure):
@@ -95,6 +95,12 @@ SIGNATURES = {
     "ds_mss_scratch_elems": (i64, [i64, i64, cint, cint]),
     "ds_mss_loss_fwd": (cint, [f32p, f32p, i64, i64, cint, cint, cint, dbl, dbl, f32p, f64p, ptr]),
     "ds_mss_loss_bwd": (cint, [f32p, f32p, i64, i64, cint, cint, cint, dbl, dbl, f64p, dbl, f32p, f32p, cint, ptr]),
+    "ds_prof_read_work": (cint, [cint, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "ds_gram_strip_scratch_elems": (i64, []),
+    "ds_gram_strip_f64": (cint, [f64p, f64p, i64, cint, f64p, i64, cint, i64, f64p, f64p, i64, f64p, ptr]),
+    "ds_rr_update2_f64": (cint, [f64p, f64p, f64p, i64, cint, cint, cint, f64p, i64, i64, f64p, f64p, f64p, i64, ptr]),
+    "ds_gram_algebra_f64": (cint, [f64p, f64p, f64p, f64p, i64, f64p, i64, f64p, cint, ptr]),
+    "ds_fp64_peak": (cint, [cint, cint, cint, f64p, C.POINTER(C.c_double), ptr]),
     "ds_prof_enable": (cint, [cint]),
     "ds_prof_enable_classes": (cint, [C.c_uint32]),
     "ds_prof_reset": (cint, []),

@@ -80,6 +80,8 @@ enum ProfClass {
 bool prof_enabled(int cls);
 void prof_begin(int cls, cudaStream_t s);
 void prof_end(int cls, cudaStream_t s);
+// algorithmic bytes / flops of a launch, accumulated per class while that class is being timed (bench.py: roofline_all)
+void prof_account(int cls, double bytes, double flops);
 struct ProfScope {
     int cls; cudaStream_t s; bool on;
     ProfScope(int c, cudaStream_t st) : cls(c), s(st), on(prof_enabled(c)) { if (on) prof_begin(cls, s); }

@@ -11,6 +11,10 @@ int spmm_km(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, const dou
 int spmm_dual(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, const double* Kval, const double* Mblk,
               const double* X, int64_t ldx, int ncols, double* YK, int64_t ldyk, double* YM, int64_t ldym,
               cudaStream_t stream, const int32_t* order = nullptr, const int32_t* chunk_row = nullptr, int nchunks = 0);
+// K Z, M Z for an fp32 block Z in a level's own (Morton) numbering; see k_spmm_dual_z32
+int spmm_dual_z32(const int32_t* brow, const int32_t* browP, const int32_t* bcolP, const int32_t* perm,
+                  const int32_t* chunk_row, int nchunks, int64_t n_nodes, const double* Kval, const double* Mblk,
+                  const float* Z, int ncols, double* YK, int64_t ldyk, double* YM, int64_t ldym, cudaStream_t stream);
 int spmm32_chunk_count(int64_t n_nodes);
 
 // precond32.cu -- FP32 preconditioner pieces
@@ -49,6 +53,8 @@ int fill_random_f32(float* V, int64_t count, uint64_t seed, cudaStream_t st);
 struct Level32 {
     const int32_t* brow = nullptr;           // row pointers in the level's own numbering
     const int32_t *perm = nullptr, *inv = nullptr;   // own row -> matrix row and back (NULL: identity)
+    bool want_bcolP = false;                 // set before setup(): also keep the column ids in the level's numbering
+    const int32_t* bcolP = nullptr;          // [nnzb] column ids in the level's numbering, rows in the level's order
     int64_t n_nodes = 0, nnzb = 0;
     unsigned char* rec = nullptr;
     float* invD = nullptr;
@@ -81,6 +87,17 @@ int block_gemm_f64(const double* A, int64_t lda, int p, const double* C, int64_t
 // fused Rayleigh-Ritz update of the three wide buffers: Y[:, :m] = A[:, :prow] C1, Y[:, 2m:2m+q2] = A[:, m:prow] C2
 int rr_update_f64(const double* const A[3], int64_t lda, int prow, int m, const double* C1, const double* C2, int q2,
                   int64_t ldc, int64_t n, double* const Y[3], int64_t ldy, cudaStream_t stream);
+// rr.cu: strips of the Gram pair that involve the new W, small-matrix recurrences for the rest, leaner basis update
+int64_t gram_strip_scratch_elems(int num_sms);
+int gram_strip(const double* KW, const double* MW, int64_t ldw, int wa, const double* S, int64_t lds, int ncol, int64_t n,
+               double* GsK, double* GsM, int64_t ldg, double* partial, int num_sms, cudaStream_t stream);
+int gram_algebra(const double* GK, const double* GM, double* GKn, double* GMn, int64_t ldg, const double* C, int64_t ldc,
+                 const double* theta, int m, cudaStream_t stream);
+int gram_insert(double* GK, double* GM, int64_t ldg, const double* GsK, const double* GsM, int64_t lds, int m, int wa,
+                cudaStream_t stream);
+int sym_upper(double* GK, double* GM, int64_t ldg, int N, cudaStream_t stream);
+int rr_update2_f64(const double* const A[3], int64_t lda, int m, int wa, int use_p, const double* C, int64_t ldc, int64_t n,
+                   double* const Y[3], int64_t ldy, cudaStream_t stream);
 // idx_host (may be NULL = identity): slot of compact index i inside the ldg x ldg Gram storage;
 // only the upper triangle of the storage is read; rows of C are written at the mapped slots.
 // sigma < 0 selects an automatic shift |sigma| * mean(diag(scaled GK)).

@@ -126,6 +126,7 @@ struct Driver {
     double *S[2], *KS[2], *MS[2];
     double *R;
     double *GK, *GM, *Cm, *theta, *eig_scratch, *gram_partial, *gram_partial2, *norm_partial, *norms, *lam_d;
+    double *GKn = nullptr, *GMn = nullptr, *GsK = nullptr, *GsM = nullptr, *strip_partial = nullptr;   // Gram recurrences (rr.cu)
     int* info_d;
     int cur = 0;
     int64_t spmm_count = 0;
@@ -153,6 +154,8 @@ struct Driver {
         add((size_t)gram_scratch_elems(64, 64)); add((size_t)norm_ctas * 2 * 128); add(2 * 128); add(128);
         add((size_t)gram_sym2_scratch_elems(ws->num_sms));
         add(64);
+        for (int i = 0; i < 4; ++i) add(144 * 144);
+        add((size_t)gram_strip_scratch_elems(ws->num_sms));
         if (nq) add((size_t)n * nq);
         DS_TRY(ws->arena.reserve(need, st));
         Arena& a = ws->arena;
@@ -179,14 +182,18 @@ struct Driver {
         norms = a.take<double>(2 * 128);
         lam_d = a.take<double>(128);
         info_d = a.take<int>(16);
+        GKn = a.take<double>(144 * 144); GMn = a.take<double>(144 * 144);
+        GsK = a.take<double>(144 * 144); GsM = a.take<double>(144 * 144);
+        strip_partial = a.take<double>((size_t)gram_strip_scratch_elems(ws->num_sms));
         if (nq) MQ = a.take<double>((size_t)n * nq);
-        DS_REQUIRE(info_d != nullptr && (!nq || MQ), "lobpcg: workspace arena exhausted");
+        DS_REQUIRE(info_d != nullptr && strip_partial != nullptr && (!nq || MQ), "lobpcg: workspace arena exhausted");
         for (int i = 0; i < 2; ++i) {   // never multiply uninitialised memory by zero coefficients
             DS_CUDA(cudaMemsetAsync(S[i], 0, 3 * blk * 8, st));
             DS_CUDA(cudaMemsetAsync(KS[i], 0, 3 * blk * 8, st));
             DS_CUDA(cudaMemsetAsync(MS[i], 0, 3 * blk * 8, st));
         }
         // FP32 copies of the operators (records + block-Jacobi inverses)
+        fine.want_bcolP = true;       // K W / M W are formed from the fp32 preconditioner output (k_spmm_dual_z32)
         DS_TRY(fine.setup(a, brow, bcol, n_nodes, nnzb, Kval, Mblk, o.sigma > 0.0 ? o.sigma : 0.0, o.coords, st));
         fine.prof_cls = fine_prof_cls;
         if (cl) {
@@ -380,25 +387,27 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
     DS_TRY(spmm_dual(brow, bcol, n_nodes, Kval, Mblk, Xb(0), ld, m, KS[0], ld, MS[0], ld, st, fine.perm, fine.chunk_row,
                      spmm32_chunk_count(n_nodes)));
     spmm_count += 2;
-    std::vector<int> idx(144);
-    auto rr = [&](int w, int nx, int nw, int np, const std::vector<int>& slots) -> int {
-        // both Gram matrices in one pass over [X | W | P]: upper-triangle 8x8 tiles over the used columns
+    // Small generalised eigen-solve on the slots in play.  full = true: both Gram matrices are recomputed over
+    // [X | W | P] in one pass (k_gram_sym2) -- the initial step, every REFRESH-th step and the fallback when the small
+    // Cholesky fails; otherwise GK / GM hold the recurrences of rr.cu plus the strips of the new W.
+    auto eig = [&](const std::vector<int>& slots) -> int {
+        DS_CUDA(cudaMemsetAsync(Cm, 0, sizeof(double) * 144 * 144, st));
+        return eigh_generalized_f64(GK, GM, (int)slots.size(), 144, slots.data(), -1e-6, theta, Cm, 144, eig_scratch, info_d, st);
+    };
+    auto full_gram = [&](int w, int nw, bool withP) -> int {
         DS_CUDA(cudaMemsetAsync(GK, 0, sizeof(double) * 144 * 144, st));
         DS_CUDA(cudaMemsetAsync(GM, 0, sizeof(double) * 144 * 144, st));
         int tiles[18], nt = 0;
         for (int t = 0; t < m / 8; ++t) tiles[nt++] = t;
         for (int t = 0; t < (nw + 7) / 8; ++t) tiles[nt++] = m / 8 + t;
-        for (int t = 0; t < (np + 7) / 8; ++t) tiles[nt++] = 2 * m / 8 + t;
+        if (withP) for (int t = 0; t < m / 8; ++t) tiles[nt++] = 2 * m / 8 + t;
         DS_TRY(gram_sym2(S[w], KS[w], MS[w], ld, n, tiles, nt, GK, GM, 144, gram_partial2, ws->num_sms, st));
-        DS_CUDA(cudaMemsetAsync(Cm, 0, sizeof(double) * 144 * 144, st));
-        int N = (int)slots.size();
-        (void)nx;
-        DS_TRY(eigh_generalized_f64(GK, GM, N, 144, slots.data(), -1e-6, theta, Cm, 144, eig_scratch, info_d, st));
-        return DS_OK;
+        return sym_upper(GK, GM, 144, 3 * m, st);
     };
     std::vector<int> slots;
     for (int j = 0; j < m; ++j) slots.push_back(j);
-    DS_TRY(rr(0, m, 0, 0, slots));
+    DS_TRY(full_gram(0, 0, false));
+    DS_TRY(eig(slots));
     int info_h[2] = {0, 0};
     DS_CUDA(cudaMemcpyAsync(info_h, info_d, sizeof(info_h), cudaMemcpyDeviceToHost, st));
     DS_CUDA(cudaStreamSynchronize(st));
@@ -412,11 +421,17 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
     DS_TRY(block_gemm_f64(MS[0], ld, m, Cm, 144, m, n, 1.0, 0.0, MS[1], ld, st));
     cur = 1;
     DS_CUDA(cudaMemcpyAsync(lam_d, theta, m * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    // Gram pair of [X' | - | -]: diag(theta), I  (C has no W / P rows yet: the recurrence reduces to exactly that)
+    DS_TRY(gram_algebra(GK, GM, GKn, GMn, 144, Cm, 144, theta, m, st));
+    std::swap(GK, GKn);
+    std::swap(GM, GMn);
 
     std::vector<double> lam(m), hn(2 * m), rel(m, 1.0);
-    std::vector<int> act, pslot_col;   // active X columns; X column of each P slot (previous active list)
-    int np = 0;                        // number of P slots in buffer `cur`
-    int it = 0, nconv = 0, status = 1;
+    std::vector<int> act;
+    bool haveP = false;                // the P slots of buffer `cur` hold the previous step's directions (slot j <-> X column j)
+    int it = 0, nconv = 0, status = 1, since_refresh = 0;
+    const int REFRESH = 8;
+    const bool z32 = fine.bcolP != nullptr && nq == 0 && !o.ortho_w;   // W = fp32 preconditioner output, unmodified
     const int res_threads = (1024 / m) * m;
     const size_t res_smem = (size_t)(res_threads / m) * 2 * m * sizeof(double);
     for (it = 0; it <= o.maxit; ++it) {
@@ -453,7 +468,6 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
         }
         if (nconv >= nev) { status = 0; break; }
         if (it == o.maxit) break;
-        // guard columns beyond nev stay active only while they help; cap the active count at m
         const int na = (int)act.size();
         const int wpad = (na + 15) & ~15;
         ColIdx ci;
@@ -463,51 +477,71 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
         float* Zres = nullptr;
         DS_TRY(apply_precond(wpad, &Zres));
         DS_TRY(widen_f32(Zres, wpad, n, Wb(cur), ld, st, fine.perm));
-        if (nq) DS_TRY(project_locked(Wb(cur), ld, wpad));
-        // ---- W <- W - X (MX^T W)
-        DS_TRY(gram_f64(MS[cur], ld, m, Wb(cur), ld, wpad, n, GK, 144, gram_partial, st));
-        DS_TRY(block_gemm_f64(Xb(cur), ld, m, GK, 144, wpad, n, -1.0, 1.0, Wb(cur), ld, st));
-        DS_TRY(spmm_dual(brow, bcol, n_nodes, Kval, Mblk, Wb(cur), ld, wpad, KS[cur] + m, ld, MS[cur] + m, ld, st, fine.perm,
-                         fine.chunk_row, spmm32_chunk_count(n_nodes)));
+        if (z32) {
+            // K W, M W straight from the fp32 block in the preconditioner's numbering: W is used as it comes out of T
+            // (the Rayleigh-Ritz step does not need W M-orthogonal to X; near convergence T R is M-orthogonal to X to
+            // O(residual) anyway), so no FP64 copy is gathered
+            DS_TRY(spmm_dual_z32(brow, fine.brow, fine.bcolP, fine.perm, fine.chunk_row, spmm32_chunk_count(n_nodes), n_nodes,
+                                 Kval, Mblk, Zres, wpad, KS[cur] + m, ld, MS[cur] + m, ld, st));
+        } else {
+            if (nq) DS_TRY(project_locked(Wb(cur), ld, wpad));
+            // ---- W <- W - X (MX^T W)
+            DS_TRY(gram_f64(MS[cur], ld, m, Wb(cur), ld, wpad, n, GsK, 144, gram_partial, st));
+            DS_TRY(block_gemm_f64(Xb(cur), ld, m, GsK, 144, wpad, n, -1.0, 1.0, Wb(cur), ld, st));
+            DS_TRY(spmm_dual(brow, bcol, n_nodes, Kval, Mblk, Wb(cur), ld, wpad, KS[cur] + m, ld, MS[cur] + m, ld, st, fine.perm,
+                             fine.chunk_row, spmm32_chunk_count(n_nodes)));
+        }
         spmm_count += 2;
-        // ---- Rayleigh-Ritz on [X, W(na), P(valid slots)]
-        std::vector<int> pvalid;   // P slots whose X column is still active
-        for (int s = 0; s < np; ++s)
-            if (std::find(act.begin(), act.end(), pslot_col[s]) != act.end()) pvalid.push_back(s);
-        bool useP = !pvalid.empty();
-        for (int attempt = 0; attempt < 2; ++attempt) {
+        // ---- Gram pair of [X | W | P]: the strips of the new W on top of the recurrences, or everything afresh
+        bool useP = haveP;
+        bool fresh = since_refresh >= REFRESH;
+        if (fresh) {
+            DS_TRY(full_gram(cur, wpad, haveP));
+            since_refresh = 0;
+        } else {
+            DS_TRY(gram_strip(KS[cur] + m, MS[cur] + m, ld, wpad, S[cur], ld, ld, n, GsK, GsM, 144, strip_partial, ws->num_sms, st));
+            DS_TRY(gram_insert(GK, GM, 144, GsK, GsM, 144, m, wpad, st));
+        }
+        // ---- Rayleigh-Ritz on [X, W(na), P(columns that are still active)]
+        for (int attempt = 0; attempt < 3; ++attempt) {
             slots.clear();
             for (int j = 0; j < m; ++j) slots.push_back(j);
             for (int s = 0; s < na; ++s) slots.push_back(m + s);
-            if (useP) for (int s : pvalid) slots.push_back(2 * m + s);
-            DS_TRY(rr(cur, m, na, useP ? np : 0, slots));
+            if (useP) for (int j : act) slots.push_back(2 * m + j);
+            DS_TRY(eig(slots));
             DS_CUDA(cudaMemcpyAsync(info_h, info_d, sizeof(info_h), cudaMemcpyDeviceToHost, st));
             DS_CUDA(cudaStreamSynchronize(st));
             if (info_h[0] == 0) break;
-            if (o.verbose) fprintf(stderr, "[ds_lobpcg] it %d: RR Cholesky failed (info %d)%s\n", it, info_h[0],
-                                   useP ? ", restarting without P" : "");
+            if (o.verbose) fprintf(stderr, "[ds_lobpcg] it %d: RR Cholesky failed (info %d, attempt %d)\n", it, info_h[0], attempt);
+            if (!fresh) {                      // first suspect: drift of the Gram recurrences
+                DS_TRY(full_gram(cur, wpad, haveP));
+                fresh = true;
+                since_refresh = 0;
+                continue;
+            }
             if (!useP) {
                 set_error("ds_lobpcg: Rayleigh-Ritz breakdown at iteration %d (info %d)", it, info_h[0]);
                 return DS_ERR_NUMERIC;
             }
-            useP = false;
+            useP = false;                      // then: P nearly dependent on [X, W] -- restart without it
         }
-        // ---- update: X' = [X W P] C[:, :m];  P' = [W P] C[m:, act]
+        if (info_h[0] != 0) {
+            set_error("ds_lobpcg: Rayleigh-Ritz breakdown at iteration %d (info %d)", it, info_h[0]);
+            return DS_ERR_NUMERIC;
+        }
+        // ---- update: P' = [W P] C[m:, :m] into the P slots, X' = X C[:m, :m] + P' into the X slots (all three buffers)
         int nxt = cur ^ 1;
-        const int prow = useP ? 3 * m : 2 * m;   // rows of C in play (slots beyond are zero anyway)
-        // gather the active columns of C (rows m..prow) into a compact (prow-m) x wpad matrix (GM storage, zeroed):
-        // rows = slots m.., cols = active list; then both products in one pass over each buffer
-        DS_CUDA(cudaMemsetAsync(GM, 0, sizeof(double) * 144 * 144, st));
-        k_gather_cols<<<(unsigned)ceil_div((int64_t)(prow - m) * wpad, 256), 256, 0, st>>>(
-            Cm + (size_t)m * 144, 144, ci, na, wpad, prow - m, GM, 144);
-        DS_LAUNCH_CHECK();
         {
             const double* Ain[3] = {S[cur], KS[cur], MS[cur]};
             double* Yout[3] = {S[nxt], KS[nxt], MS[nxt]};
-            DS_TRY(rr_update_f64(Ain, ld, prow, m, Cm, GM, wpad, 144, n, Yout, ld, st));
+            DS_TRY(rr_update2_f64(Ain, ld, m, wpad, useP ? 1 : 0, Cm, 144, n, Yout, ld, st));
         }
-        pslot_col = act;
-        np = na;
+        // ---- Gram pair of [X' | - | P'] from the small matrices (rows of C at unused slots are zero)
+        DS_TRY(gram_algebra(GK, GM, GKn, GMn, 144, Cm, 144, theta, m, st));
+        std::swap(GK, GKn);
+        std::swap(GM, GMn);
+        haveP = true;
+        since_refresh++;
         DS_CUDA(cudaMemcpyAsync(lam_d, theta, m * sizeof(double), cudaMemcpyDeviceToDevice, st));
         cur = nxt;
     }

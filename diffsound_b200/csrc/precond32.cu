@@ -1072,9 +1072,26 @@ static size_t morton_sort_temp(int64_t n_nodes) {
     return t;
 }
 
+// bcolP[browP[r] + p] = inv[bcol[brow[perm[r]] + p]]: the level's column ids as a plain int32 array (the FP64 SpMM on
+// fp32 iterates reads 4 bytes per block instead of fishing them out of the 48-byte records)
+__global__ void __launch_bounds__(256)
+k_perm_bcol(const int32_t* __restrict__ brow, const int32_t* __restrict__ bcol, const int32_t* __restrict__ browP,
+            const int32_t* __restrict__ perm, const int32_t* __restrict__ inv, int64_t n_nodes, int32_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (r >= n_nodes) return;
+    const int64_t src = perm ? (int64_t)perm[r] : r;
+    const int64_t b0 = brow[src], o0 = browP[r];
+    const int deg = (int)(brow[src + 1] - b0);
+    for (int p = lane; p < deg; p += 32) {
+        const int32_t j = bcol[b0 + p];
+        out[o0 + p] = inv ? inv[j] : j;
+    }
+}
+
 size_t Level32::bytes(int64_t n_nodes, int64_t nnzb) {
     auto al = [](size_t b) { return ((b + 255) & ~size_t(255)) + 256; };
-    return al((size_t)nnzb * S32_REC_BYTES + 64) + al((size_t)n_nodes * 9 * sizeof(float)) + al(1024 * sizeof(int32_t)) +
+    return al((size_t)nnzb * sizeof(int32_t)) + al((size_t)nnzb * S32_REC_BYTES + 64) + al((size_t)n_nodes * 9 * sizeof(float)) + al(1024 * sizeof(int32_t)) +
            6 * al((size_t)(n_nodes + 1) * sizeof(int32_t)) + al(morton_sort_temp(n_nodes)) + 2 * al(64);
 }
 
@@ -1133,6 +1150,15 @@ int Level32::setup(Arena& a, const int32_t* brow_, const int32_t* bcol, int64_t 
         brow = brow_w;
     }
     DS_TRY(pack_k32(brow_, bcol, n_nodes, Kval, Mblk, shift, rec, invD, st, nullptr, 0, perm, inv, perm ? brow : nullptr));
+    bcolP = nullptr;
+    if (want_bcolP) {
+        int32_t* bp = a.take<int32_t>((size_t)nnzb);
+        DS_REQUIRE(bp, "Level32: workspace arena exhausted");
+        ProfScope prof(PROF_COPY, st);
+        k_perm_bcol<<<(unsigned)ceil_div(n_nodes * 32, 256), 256, 0, st>>>(brow_, bcol, brow, perm, inv, n_nodes, bp);
+        DS_LAUNCH_CHECK();
+        bcolP = bp;
+    }
     return spmm32_chunks(brow, n_nodes, chunk_row, st);
 }
 

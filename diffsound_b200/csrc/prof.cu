@@ -20,6 +20,8 @@ struct ProfState {
     cudaEvent_t open_ev[PROF_NCLASS] = {};
     double ms[PROF_NCLASS] = {};
     int64_t count[PROF_NCLASS] = {};
+    double bytes[PROF_NCLASS] = {};
+    double flops[PROF_NCLASS] = {};
 };
 static ProfState g_prof;
 
@@ -51,6 +53,13 @@ void prof_end(int cls, cudaStream_t s) {
     cudaEvent_t e = take_event();
     cudaEventRecord(e, s);
     g_prof.pending.push_back({g_prof.open_ev[cls], e, cls});
+}
+
+void prof_account(int cls, double bytes, double flops) {
+    if (!prof_enabled(cls)) return;
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    g_prof.bytes[cls] += bytes;
+    g_prof.flops[cls] += flops;
 }
 
 static void drain() {
@@ -91,7 +100,7 @@ extern "C" int ds_prof_enable_classes(uint32_t mask) {
 extern "C" int ds_prof_reset(void) {
     std::lock_guard<std::mutex> lk(g_prof.mu);
     drain();
-    for (int c = 0; c < PROF_NCLASS; ++c) { g_prof.ms[c] = 0.0; g_prof.count[c] = 0; }
+    for (int c = 0; c < PROF_NCLASS; ++c) { g_prof.ms[c] = 0.0; g_prof.count[c] = 0; g_prof.bytes[c] = 0.0; g_prof.flops[c] = 0.0; }
     return DS_OK;
 }
 
@@ -107,5 +116,13 @@ extern "C" int ds_prof_read(int cls, double* ms, int64_t* count) {
     drain();
     *ms = g_prof.ms[cls];
     *count = g_prof.count[cls];
+    return DS_OK;
+}
+
+extern "C" int ds_prof_read_work(int cls, double* bytes, double* flops) {
+    DS_REQUIRE(cls >= 0 && cls < PROF_NCLASS && bytes && flops, "ds_prof_read_work: bad argument");
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    *bytes = g_prof.bytes[cls];
+    *flops = g_prof.flops[cls];
     return DS_OK;
 }

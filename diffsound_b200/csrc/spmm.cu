@@ -244,6 +244,109 @@ k_spmm_dual_v2(const int32_t* __restrict__ brow, const int32_t* __restrict__ bco
     }
 }
 
+// K Z and M Z for a block Z that is exactly representable in FP32 -- the output of the FP32 preconditioner, which
+// is what LOBPCG's new search directions W are (csrc/lobpcg.cu).  Same sweep as k_spmm_dual_v2 (one CTA per SM over a
+// chunk of the level's Morton row list, ticket-scheduled warps, L2 look-ahead for the streamed matrix data), but the
+// gathered operand is the level's own fp32 block in ITS numbering: rows r' of Z, column ids bcolP (already mapped to
+// that numbering, in the block order of the matrix row perm[r']), 4 bytes per gathered value instead of 8 and
+// Morton-contiguous rows instead of rows strided through the n x 3m iterate buffer.  Matrix values stay FP64, the
+// accumulation is FP64, results go to rows 3 perm[r'] + c of YK / YM.
+template <int CPL>
+__global__ void __launch_bounds__(SD2_THREADS, 1)
+k_spmm_dual_z32(const int32_t* __restrict__ brow, const int32_t* __restrict__ browP, const int32_t* __restrict__ bcolP,
+                const int32_t* __restrict__ perm, const int32_t* __restrict__ chunk_row,
+                const double* __restrict__ Kval, const double* __restrict__ Mblk, const float* __restrict__ Z, int ldz,
+                double* __restrict__ YK, int64_t ldyk, double* __restrict__ YM, int64_t ldym) {
+    __shared__ int s_ticket;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, half = lane >> 4, cl = lane & 15;
+    const int r_lo = chunk_row[blockIdx.x], r_hi = chunk_row[blockIdx.x + 1];
+    if (tid == 0) s_ticket = 0;
+    __syncthreads();
+    if (warp == SD2_THREADS / 32 - 1) {
+        for (int base = r_lo; base < r_hi; base += 32) {
+            while (base > r_lo + *(volatile int*)&s_ticket + SD2_AHEAD) __nanosleep(200);
+            const int r = base + lane;
+            if (r < r_hi) {
+                const int row = perm ? perm[r] : r;
+                const int64_t b0 = brow[row];
+                const int64_t deg = brow[row + 1] - b0;
+                if (deg > 0) {
+                    prefetch_l2_run(Kval + 9 * b0, 72 * deg);
+                    prefetch_l2_run(bcolP + browP[r], 4 * deg);
+                    prefetch_l2_run(Mblk + b0, 8 * deg);
+                }
+            }
+        }
+        return;
+    }
+    for (;;) {
+        int rr = 0;
+        if (lane == 0) rr = atomicAdd(&s_ticket, 1);
+        rr = __shfl_sync(0xffffffffu, rr, 0);
+        if (r_lo + rr >= r_hi) break;
+        const int rp = r_lo + rr;
+        const int64_t row = perm ? perm[rp] : rp;
+        const int64_t b0 = brow[row];
+        const int deg = (int)(brow[row + 1] - b0);
+        const int32_t* cp = bcolP + browP[rp];
+        double acc[3][CPL], accm[3][CPL];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int t = 0; t < CPL; ++t) acc[c][t] = accm[c][t] = 0.0;
+        const double* kbase = Kval + 9 * b0;
+        const int64_t rs = 3 * (int64_t)deg;
+        int jn = half < deg ? __ldg(cp + half) : 0;
+        for (int p = half; p < deg; p += 2) {
+            const int64_t j = jn;
+            if (p + 2 < deg) jn = __ldg(cp + p + 2);
+            const float* zr = Z + 3 * j * ldz + cl;
+            float x[3][CPL];
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+#pragma unroll
+                for (int t = 0; t < CPL; ++t) x[d][t] = __ldg(zr + d * ldz + 16 * t);
+            const double* kp = kbase + 3 * p;
+            double k[3][3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int d = 0; d < 3; ++d) k[c][d] = __ldg(kp + c * rs + d);
+            const double m = __ldg(Mblk + b0 + p);
+#pragma unroll
+            for (int t = 0; t < CPL; ++t) {
+                const double x0 = (double)x[0][t], x1 = (double)x[1][t], x2 = (double)x[2][t];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    double a = acc[c][t];
+                    a = fma(k[c][0], x0, a);
+                    a = fma(k[c][1], x1, a);
+                    a = fma(k[c][2], x2, a);
+                    acc[c][t] = a;
+                }
+                accm[0][t] = fma(m, x0, accm[0][t]);
+                accm[1][t] = fma(m, x1, accm[1][t]);
+                accm[2][t] = fma(m, x2, accm[2][t]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int t = 0; t < CPL; ++t) {
+                acc[c][t] += __shfl_xor_sync(0xffffffffu, acc[c][t], 16);
+                accm[c][t] += __shfl_xor_sync(0xffffffffu, accm[c][t], 16);
+            }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int t = 0; t < CPL; ++t) {
+                const int64_t col = cl + 16 * t;
+                if (half == 0) st_na_f64(YK + (3 * row + c) * ldyk + col, acc[c][t]);
+                else st_na_f64(YM + (3 * row + c) * ldym + col, accm[c][t]);
+            }
+    }
+}
+
 static inline unsigned row_blocks(int64_t n_nodes) { return (unsigned)ceil_div(n_nodes * 32, 256); }
 
 #define DS_DISPATCH_CPL(cpl, ...)                                              \
@@ -311,6 +414,27 @@ int spmm_dual(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, const d
                                                                   ldym)));
     DS_LAUNCH_CHECK();
     return DS_OK;
+}
+
+int spmm_dual_z32(const int32_t* brow, const int32_t* browP, const int32_t* bcolP, const int32_t* perm,
+                  const int32_t* chunk_row, int nchunks, int64_t n_nodes, const double* Kval, const double* Mblk,
+                  const float* Z, int ncols, double* YK, int64_t ldyk, double* YM, int64_t ldym, cudaStream_t stream) {
+    DS_REQUIRE(ncols > 0 && ncols % 16 == 0 && ncols <= 48, "spmm_dual_z32: ncols=%d must be 16, 32 or 48", ncols);
+    DS_REQUIRE(brow && browP && bcolP && chunk_row && nchunks > 0 && Kval && Mblk && Z && YK && YM, "spmm_dual_z32: null argument");
+    (void)n_nodes;
+    ProfScope prof(PROF_SPMM, stream);
+    auto go = [&](auto kern) -> int {
+        static bool carved = false;
+        if (!carved) {
+            DS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
+            carved = true;
+        }
+        kern<<<nchunks, SD2_THREADS, 0, stream>>>(brow, browP, bcolP, perm, chunk_row, Kval, Mblk, Z, ncols, YK, ldyk, YM, ldym);
+        DS_LAUNCH_CHECK();
+        return DS_OK;
+    };
+    const int cpl = ncols / 16;
+    return cpl == 1 ? go(k_spmm_dual_z32<1>) : (cpl == 2 ? go(k_spmm_dual_z32<2>) : go(k_spmm_dual_z32<3>));
 }
 
 }  // namespace ds

@@ -411,7 +411,7 @@ def pmg_prolong_add32(coarse, zc, z):
 
 def lobpcg(pattern, Kval, Mblk, X, nev, tol=1e-4, maxit=200, cheb_degree=8, sigma=0.0, cheb_ratio=30.0, n_rigid=6,
            verbose=0, coarse=None, smooth_steps=3, smooth_ratio=8.0, coarse_degree=20, coarse_ratio=160.0, nested=True,
-           nested_tol=3e-2, nested_degree=0, coords=None, locked=None):
+           nested_tol=3e-2, nested_degree=0, coords=None, locked=None, ortho_w=False):
     """Lowest `nev` pairs of K u = lam M u from the start block X (n, m) fp64 (overwritten with the
     M-orthonormal Ritz vectors).  `coarse`: a CoarseLevel with assembled Kval -> two-level
     preconditioner.  `locked`: (n, q) fp64 contiguous, q a multiple of 16 -- M-orthonormal eigenvectors
@@ -428,7 +428,8 @@ def lobpcg(pattern, Kval, Mblk, X, nev, tol=1e-4, maxit=200, cheb_degree=8, sigm
                            smooth_steps=int(smooth_steps), coarse_degree=int(coarse_degree),
                            smooth_ratio=float(smooth_ratio), coarse_ratio=float(coarse_ratio),
                            nested=int(bool(nested) and coarse is not None), nested_tol=float(nested_tol),
-                           nested_degree=int(nested_degree), coords=None, locked=None, n_locked=0)
+                           nested_degree=int(nested_degree), coords=None, locked=None, n_locked=0,
+                           ortho_w=int(bool(ortho_w)))
     if locked is not None:
         assert locked.dtype == torch.float64 and locked.is_contiguous() and locked.shape[0] == n
         assert locked.shape[1] % 16 == 0 and locked.is_cuda
@@ -644,3 +645,53 @@ class prof:
             if cnt.value:
                 out[lib.ds_prof_class_name(c).decode()] = {"ms": ms.value, "count": cnt.value}
         return out
+
+
+def gram_strip(KW, MW, S):
+    """(GsK, GsM) = (KW^T S, MW^T S): KW, MW (n, wa) row-major views, S (n, ncol <= 144) (ds_gram_strip_f64)."""
+    lib = _lib.load()
+    kp, ldw = _pv(KW)
+    mp, ldw2 = _pv(MW)
+    sp, lds = _pv(S)
+    assert ldw == ldw2
+    wa, ncol = KW.shape[1], S.shape[1]
+    GsK = torch.zeros(wa, ncol, dtype=torch.float64, device=S.device)
+    GsM = torch.zeros(wa, ncol, dtype=torch.float64, device=S.device)
+    part = torch.empty(lib.ds_gram_strip_scratch_elems(), dtype=torch.float64, device=S.device)
+    with torch.cuda.device(S.device):
+        _lib.check(lib.ds_gram_strip_f64(kp, mp, ldw, wa, sp, lds, ncol, S.shape[0], _p(GsK), _p(GsM), ncol, _p(part), _stream()),
+                   "ds_gram_strip_f64")
+    return GsK, GsM
+
+
+def rr_update2(bufs, m, wa, use_p, Cm):
+    """Lean LOBPCG basis update (ds_rr_update2_f64) of the three (n, 3m) buffers; returns the new buffers (W slots zero)."""
+    lib = _lib.load()
+    outs = [torch.zeros_like(b) for b in bufs]
+    ld = bufs[0].shape[1]
+    assert Cm.stride(1) == 1
+    with torch.cuda.device(bufs[0].device):
+        _lib.check(lib.ds_rr_update2_f64(_p(bufs[0]), _p(bufs[1]), _p(bufs[2]), ld, int(m), int(wa), int(bool(use_p)),
+                                         C.c_void_p(Cm.data_ptr()), Cm.stride(0), bufs[0].shape[0], _p(outs[0]), _p(outs[1]),
+                                         _p(outs[2]), ld, _stream()), "ds_rr_update2_f64")
+    return outs
+
+
+def gram_algebra(GK, GM, Cm, theta, m):
+    """Gram pair of [X' | - | P'] from the full symmetric Gram pair of [X | W | P] (ds_gram_algebra_f64)."""
+    lib = _lib.load()
+    assert GK.is_contiguous() and GM.is_contiguous() and Cm.stride(1) == 1
+    GKn, GMn = torch.empty_like(GK), torch.empty_like(GM)
+    with torch.cuda.device(GK.device):
+        _lib.check(lib.ds_gram_algebra_f64(_p(GK), _p(GM), _p(GKn), _p(GMn), GK.shape[1], C.c_void_p(Cm.data_ptr()),
+                                           Cm.stride(0), _p(theta), int(m), _stream()), "ds_gram_algebra_f64")
+    return GKn, GMn
+
+
+def fp64_peak(mode, iters=4096, ctas_per_sm=2):
+    """Register-resident FP64 throughput in TFLOP/s: mode 0 = DFMA, 1 = DMMA m8n8k4 (ds_fp64_peak)."""
+    lib = _lib.load()
+    scratch = torch.zeros(8, dtype=torch.float64, device="cuda")
+    out = C.c_double(0)
+    _lib.check(lib.ds_fp64_peak(int(mode), int(iters), int(ctas_per_sm), _p(scratch), C.byref(out), _stream()), "ds_fp64_peak")
+    return out.value

@@ -179,6 +179,9 @@ typedef struct ds_lobpcg_opts {
                            deflation), so this call returns the NEXT lowest pairs: how DiffSoundObj solves
                            mode_num + 6 > 44 pairs (geometry_train.py:147 asks for 64) in batches of one block */
     int n_locked;       /* columns of `locked`, a multiple of 16, <= 192 (pad with zero columns) */
+    int ortho_w;        /* != 0: M-orthogonalise the new search block W against X in FP64 before K W / M W are formed
+                           (round-1 behaviour; lobpcg/_lobpcg.py 'ortho').  0 (default): W is the fp32 preconditioner
+                           output as is and K W, M W are formed from it directly (k_spmm_dual_z32) */
 } ds_lobpcg_opts;
 /* Coarse level of the two-level preconditioner: the P1 operator on the corner nodes of a quadratic
  * mesh (pattern + values from ds_pattern_* / ds_assemble_km at order 1 on ds_pmg_coarse_fill's
@@ -364,6 +367,26 @@ int ds_prof_num_classes(void);
 int64_t ds_launch_count(void);
 const char* ds_prof_class_name(int cls);
 int ds_prof_read(int cls, double* ms, int64_t* count);
+/* algorithmic bytes and flops accounted by the launch sites of the class while it was being timed */
+int ds_prof_read_work(int cls, double* bytes, double* flops);
+
+/* ---- Rayleigh-Ritz pieces of the round-2 LOBPCG step (csrc/rr.cu; replaces the full Gram products and the basis
+ * update of lobpcg/_lobpcg.py:433-525).  All blocks fp64 row-major, 16-byte aligned, even leading dimensions.
+ * ds_gram_strip_f64:  GsK[wa x ncol] = KW^T S, GsM = MW^T S (KW, MW: n x wa, wa in {16,32,48}; S: n x ncol <= 144).
+ * ds_rr_update2_f64:  for A in {S, KS, MS} (n x 3m, columns [X | W | P]):  P' = A[:, m:m+wa] C[m:m+wa, :m]
+ *                     (+ A[:, 2m:3m] C[2m:3m, :m] when use_p);  A_out[:, 2m:3m] = P';  A_out[:, :m] = P' + A[:, :m] C[:m, :m].
+ * ds_gram_algebra_f64: Gram pair of [X' | . | P'] from the Gram pair G of [X | W | P] (full symmetric, ldg x ldg),
+ *                     the coefficient matrix C (rows = slots, columns = rank) and the Ritz values theta.
+ * ds_fp64_peak: register-resident FP64 throughput of this device, mode 0 = DFMA, 1 = DMMA m8n8k4 (TFLOP/s). */
+int64_t ds_gram_strip_scratch_elems(void);
+int ds_gram_strip_f64(const double* KW, const double* MW, int64_t ldw, int wa, const double* S, int64_t lds, int ncol,
+                      int64_t n, double* GsK, double* GsM, int64_t ldg, double* partial, void* stream);
+int ds_rr_update2_f64(const double* S, const double* KS, const double* MS, int64_t lda, int m, int wa, int use_p,
+                      const double* C, int64_t ldc, int64_t n, double* S_out, double* KS_out, double* MS_out, int64_t ldy,
+                      void* stream);
+int ds_gram_algebra_f64(const double* GK, const double* GM, double* GKn, double* GMn, int64_t ldg, const double* C,
+                        int64_t ldc, const double* theta, int m, void* stream);
+int ds_fp64_peak(int mode, int iters, int ctas_per_sm, double* scratch, double* tflops_host, void* stream);
 
 #ifdef __cplusplus
 }

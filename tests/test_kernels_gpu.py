@@ -254,3 +254,63 @@ def test_gram_sym2_matches_fp64(ld, tiles):
                 assert np.abs(gm[blk] - rm[blk]).max() <= 1e-12 * np.abs(rm).max()
             else:
                 assert (gk[blk] == -7.0).all() and (gm[blk] == -7.0).all()
+
+
+def test_gram_strip_matches_torch():
+    from diffsound_b200 import native
+    torch.manual_seed(3)
+    n = 5003
+    for wa in (16, 32, 48):
+        S = torch.randn(n, 144, dtype=torch.float64, device=DEV)
+        KS = torch.randn(n, 144, dtype=torch.float64, device=DEV)
+        MS = torch.randn(n, 144, dtype=torch.float64, device=DEV)
+        GsK, GsM = native.gram_strip(KS[:, 48:48 + wa], MS[:, 48:48 + wa], S)
+        rk, rm = KS[:, 48:48 + wa].T @ S, MS[:, 48:48 + wa].T @ S
+        assert float((GsK - rk).abs().max()) <= 1e-11 * float(rk.abs().max())
+        assert float((GsM - rm).abs().max()) <= 1e-11 * float(rm.abs().max())
+
+
+def test_rr_update2_matches_torch():
+    from diffsound_b200 import native
+    torch.manual_seed(4)
+    n = 4099
+    for m, wa, use_p in ((48, 48, True), (48, 32, True), (48, 16, False), (32, 32, True), (16, 16, True)):
+        bufs = [torch.randn(n, 3 * m, dtype=torch.float64, device=DEV) for _ in range(3)]
+        Cm = torch.randn(3 * m, 3 * m, dtype=torch.float64, device=DEV)
+        Cm[m + wa:2 * m] = 0
+        if not use_p:
+            Cm[2 * m:] = 0
+        outs = native.rr_update2(bufs, m, wa, use_p, Cm)
+        for A, Y in zip(bufs, outs):
+            P = A[:, m:] @ Cm[m:, :m]
+            X = A[:, :m] @ Cm[:m, :m] + P
+            sc = float(X.abs().max())
+            assert float((Y[:, 2 * m:] - P).abs().max()) <= 1e-12 * sc
+            assert float((Y[:, :m] - X).abs().max()) <= 1e-12 * sc
+
+
+def test_gram_algebra_matches_torch():
+    from diffsound_b200 import native
+    torch.manual_seed(5)
+    for m in (16, 48):
+        N = 3 * m
+        B = torch.randn(N, N, dtype=torch.float64, device=DEV)
+        GK, GM = B @ B.T, B.T @ B + torch.eye(N, dtype=torch.float64, device=DEV)
+        Cm = torch.randn(N, N, dtype=torch.float64, device=DEV)
+        theta = torch.rand(N, dtype=torch.float64, device=DEV)
+        GKn, GMn = native.gram_algebra(GK, GM, Cm, theta, m)
+        C1 = Cm[:, :m]
+        Cwp = C1.clone()
+        Cwp[:m] = 0
+        for G, Gn, diag in ((GK, GKn, theta[:m]), (GM, GMn, torch.ones(m, dtype=torch.float64, device=DEV))):
+            sc = float((C1.T @ G @ C1).abs().max())
+            assert float((Gn[:m, :m] - torch.diag(diag)).abs().max()) == 0.0
+            assert float((Gn[:m, 2 * m:] - C1.T @ G @ Cwp).abs().max()) <= 1e-12 * sc
+            assert float((Gn[2 * m:, :m] - (C1.T @ G @ Cwp).T).abs().max()) <= 1e-12 * sc
+            assert float((Gn[2 * m:, 2 * m:] - Cwp.T @ G @ Cwp).abs().max()) <= 1e-12 * sc
+            assert float(Gn[m:2 * m].abs().max()) == 0.0 and float(Gn[:, m:2 * m].abs().max()) == 0.0
+
+
+def test_fp64_peak_runs():
+    from diffsound_b200 import native
+    assert native.fp64_peak(0, 256, 1) > 1.0 and native.fp64_peak(1, 256, 1) > 1.0
