@@ -245,105 +245,161 @@ k_spmm_dual_v2(const int32_t* __restrict__ brow, const int32_t* __restrict__ bco
 }
 
 // K Z and M Z for a block Z that is exactly representable in FP32 -- the output of the FP32 preconditioner, which
-// is what LOBPCG's new search directions W are (csrc/lobpcg.cu).  Same sweep as k_spmm_dual_v2 (one CTA per SM over a
-// chunk of the level's Morton row list, ticket-scheduled warps, L2 look-ahead for the streamed matrix data), but the
-// gathered operand is the level's own fp32 block in ITS numbering: rows r' of Z, column ids bcolP (already mapped to
-// that numbering, in the block order of the matrix row perm[r']), 4 bytes per gathered value instead of 8 and
-// Morton-contiguous rows instead of rows strided through the n x 3m iterate buffer.  Matrix values stay FP64, the
-// accumulation is FP64, results go to rows 3 perm[r'] + c of YK / YM.
-template <int CPL>
-__global__ void __launch_bounds__(SD2_THREADS, 1)
+// is what LOBPCG's new search directions W are (csrc/lobpcg.cu).  The gathered operand is the level's own fp32 block
+// in ITS (Morton) numbering: rows r' of Z, column ids bcolP (already mapped to that numbering, in the block order of
+// the matrix row perm[r']) -- 4 bytes per gathered value instead of 8, Morton-contiguous rows instead of rows strided
+// through the n x 3m iterate buffer.  Matrix values stay FP64, the accumulation is FP64, results go to rows
+// 3 perm[r'] + c of YK / YM.
+// Mapping (the one of k_spmm32v, csrc/precond32.cu): one CTA per SM sweeps a contiguous chunk of the Morton row list,
+// warps take rows through a shared-memory ticket; LPR lanes cover the C = LPR * CPT columns with 128/64-bit loads, the
+// 32 / LPR lane groups walk alternate blocks of the row, two blocks per group in flight (the FP64 kernel above keeps
+// one block per half-warp in flight and is bound by load latency: long-scoreboard stalls at 37 % occupancy).
+constexpr int SZ_THREADS = 384;
+constexpr int SZ_PF = 48;        // rows of look-ahead of the L2 prefetch
+
+template <int LPR, int CPT>
+__device__ __forceinline__ void ld_row_f32(const float* __restrict__ row, int l, float* out) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(row) + l);
+    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+    if constexpr (CPT == 6) {
+        const float2 w = __ldg(reinterpret_cast<const float2*>(row + 4 * LPR) + l);
+        out[4] = w.x; out[5] = w.y;
+    }
+}
+template <int LPR, int CPT>
+__device__ __forceinline__ void st_row_f64(double* row, int l, const double* v) {
+    double2* p = reinterpret_cast<double2*>(row + 4 * l);
+    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v[0]), "d"(v[1]) : "memory");
+    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(p + 1), "d"(v[2]), "d"(v[3]) : "memory");
+    if constexpr (CPT == 6)
+        asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(row + 4 * LPR + 2 * l), "d"(v[4]), "d"(v[5]) : "memory");
+}
+
+template <int LPR, int CPT>
+__global__ void __launch_bounds__(SZ_THREADS, 1)
 k_spmm_dual_z32(const int32_t* __restrict__ brow, const int32_t* __restrict__ browP, const int32_t* __restrict__ bcolP,
                 const int32_t* __restrict__ perm, const int32_t* __restrict__ chunk_row,
-                const double* __restrict__ Kval, const double* __restrict__ Mblk, const float* __restrict__ Z, int ldz,
+                const double* __restrict__ Kval, const double* __restrict__ Mblk, const float* __restrict__ Z,
                 double* __restrict__ YK, int64_t ldyk, double* __restrict__ YM, int64_t ldym) {
+    constexpr int C = LPR * CPT, NG = 32 / LPR;
     __shared__ int s_ticket;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, half = lane >> 4, cl = lane & 15;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane / LPR, l = lane % LPR;
     const int r_lo = chunk_row[blockIdx.x], r_hi = chunk_row[blockIdx.x + 1];
     if (tid == 0) s_ticket = 0;
-    __syncthreads();
-    if (warp == SD2_THREADS / 32 - 1) {
-        for (int base = r_lo; base < r_hi; base += 32) {
-            while (base > r_lo + *(volatile int*)&s_ticket + SD2_AHEAD) __nanosleep(200);
-            const int r = base + lane;
-            if (r < r_hi) {
-                const int row = perm ? perm[r] : r;
-                const int64_t b0 = brow[row];
-                const int64_t deg = brow[row + 1] - b0;
-                if (deg > 0) {
-                    prefetch_l2_run(Kval + 9 * b0, 72 * deg);
-                    prefetch_l2_run(bcolP + browP[r], 4 * deg);
-                    prefetch_l2_run(Mblk + b0, 8 * deg);
-                }
-            }
+    auto prefetch_row = [&](int r) {
+        const int row = perm ? perm[r] : r;
+        const int64_t b0 = brow[row];
+        const int64_t deg = brow[row + 1] - b0;
+        if (deg > 0) {
+            prefetch_l2_run(Kval + 9 * b0, 72 * deg);
+            prefetch_l2_run(bcolP + browP[r], 4 * deg);
+            prefetch_l2_run(Mblk + b0, 8 * deg);
         }
-        return;
+    };
+    if (lane == 0) {
+        for (int q = warp; q < SZ_PF && r_lo + q < r_hi; q += SZ_THREADS / 32) prefetch_row(r_lo + q);
     }
+    __syncthreads();
     for (;;) {
         int rr = 0;
         if (lane == 0) rr = atomicAdd(&s_ticket, 1);
         rr = __shfl_sync(0xffffffffu, rr, 0);
-        if (r_lo + rr >= r_hi) break;
         const int rp = r_lo + rr;
+        if (rp >= r_hi) break;
+        if (lane == 0 && rp + SZ_PF < r_hi) prefetch_row(rp + SZ_PF);
         const int64_t row = perm ? perm[rp] : rp;
         const int64_t b0 = brow[row];
         const int deg = (int)(brow[row + 1] - b0);
-        const int32_t* cp = bcolP + browP[rp];
-        double acc[3][CPL], accm[3][CPL];
+        const int32_t* __restrict__ cp = bcolP + browP[rp];
+        const double* __restrict__ kb = Kval + 9 * b0;
+        const double* __restrict__ mb = Mblk + b0;
+        const int64_t rs = 3 * (int64_t)deg;
+        double acc[3][CPT], accm[3][CPT];
 #pragma unroll
         for (int c = 0; c < 3; ++c)
 #pragma unroll
-            for (int t = 0; t < CPL; ++t) acc[c][t] = accm[c][t] = 0.0;
-        const double* kbase = Kval + 9 * b0;
-        const int64_t rs = 3 * (int64_t)deg;
-        int jn = half < deg ? __ldg(cp + half) : 0;
-        for (int p = half; p < deg; p += 2) {
-            const int64_t j = jn;
-            if (p + 2 < deg) jn = __ldg(cp + p + 2);
-            const float* zr = Z + 3 * j * ldz + cl;
-            float x[3][CPL];
+            for (int t = 0; t < CPT; ++t) acc[c][t] = accm[c][t] = 0.0;
+        auto fma_block = [&](const float (&x)[3][CPT], const double (&k)[9], double mv) {
 #pragma unroll
-            for (int d = 0; d < 3; ++d)
-#pragma unroll
-                for (int t = 0; t < CPL; ++t) x[d][t] = __ldg(zr + d * ldz + 16 * t);
-            const double* kp = kbase + 3 * p;
-            double k[3][3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-#pragma unroll
-                for (int d = 0; d < 3; ++d) k[c][d] = __ldg(kp + c * rs + d);
-            const double m = __ldg(Mblk + b0 + p);
-#pragma unroll
-            for (int t = 0; t < CPL; ++t) {
+            for (int t = 0; t < CPT; ++t) {
                 const double x0 = (double)x[0][t], x1 = (double)x[1][t], x2 = (double)x[2][t];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     double a = acc[c][t];
-                    a = fma(k[c][0], x0, a);
-                    a = fma(k[c][1], x1, a);
-                    a = fma(k[c][2], x2, a);
+                    a = fma(k[3 * c], x0, a);
+                    a = fma(k[3 * c + 1], x1, a);
+                    a = fma(k[3 * c + 2], x2, a);
                     acc[c][t] = a;
                 }
-                accm[0][t] = fma(m, x0, accm[0][t]);
-                accm[1][t] = fma(m, x1, accm[1][t]);
-                accm[2][t] = fma(m, x2, accm[2][t]);
+                accm[0][t] = fma(mv, x0, accm[0][t]);
+                accm[1][t] = fma(mv, x1, accm[1][t]);
+                accm[2][t] = fma(mv, x2, accm[2][t]);
             }
+        };
+        int p = g;
+        int ja = p < deg ? __ldg(cp + p) : 0;
+        int jb = p + NG < deg ? __ldg(cp + p + NG) : 0;
+        for (; p + NG < deg; p += 2 * NG) {
+            const int jan = p + 2 * NG < deg ? __ldg(cp + p + 2 * NG) : 0;
+            const int jbn = p + 3 * NG < deg ? __ldg(cp + p + 3 * NG) : 0;
+            const float* xa = Z + (int64_t)3 * ja * C;
+            const float* xb = Z + (int64_t)3 * jb * C;
+            float x[3][CPT], y[3][CPT];
+            double ka[9], kq[9];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                ld_row_f32<LPR, CPT>(xa + d * C, l, x[d]);
+                ld_row_f32<LPR, CPT>(xb + d * C, l, y[d]);
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    ka[3 * c + d] = __ldg(kb + c * rs + 3 * p + d);
+                    kq[3 * c + d] = __ldg(kb + c * rs + 3 * (p + NG) + d);
+                }
+            const double ma = __ldg(mb + p), mq = __ldg(mb + p + NG);
+            fma_block(x, ka, ma);
+            fma_block(y, kq, mq);
+            ja = jan;
+            jb = jbn;
+        }
+        if (p < deg) {
+            const float* xa = Z + (int64_t)3 * ja * C;
+            float x[3][CPT];
+            double ka[9];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) ld_row_f32<LPR, CPT>(xa + d * C, l, x[d]);
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int d = 0; d < 3; ++d) ka[3 * c + d] = __ldg(kb + c * rs + 3 * p + d);
+            fma_block(x, ka, __ldg(mb + p));
         }
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
+        for (int off = LPR; off < 32; off <<= 1)
 #pragma unroll
-            for (int t = 0; t < CPL; ++t) {
-                acc[c][t] += __shfl_xor_sync(0xffffffffu, acc[c][t], 16);
-                accm[c][t] += __shfl_xor_sync(0xffffffffu, accm[c][t], 16);
-            }
+            for (int c = 0; c < 3; ++c)
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
+                for (int t = 0; t < CPT; ++t) {
+                    acc[c][t] += __shfl_xor_sync(0xffffffffu, acc[c][t], off);
+                    accm[c][t] += __shfl_xor_sync(0xffffffffu, accm[c][t], off);
+                }
+        // lane group c < 3 stores component row c of K Z, group (c + 1) % NG ... of M Z (NG >= 4), spreading the stores
+        if (g < 3) {
+            double v[CPT];
 #pragma unroll
-            for (int t = 0; t < CPL; ++t) {
-                const int64_t col = cl + 16 * t;
-                if (half == 0) st_na_f64(YK + (3 * row + c) * ldyk + col, acc[c][t]);
-                else st_na_f64(YM + (3 * row + c) * ldym + col, accm[c][t]);
-            }
+            for (int t = 0; t < CPT; ++t) v[t] = g == 0 ? acc[0][t] : (g == 1 ? acc[1][t] : acc[2][t]);
+            st_row_f64<LPR, CPT>(YK + (3 * row + g) * ldyk, l, v);
+        }
+        const int gm = NG - 1 - g;
+        if (gm < 3) {
+            double v[CPT];
+#pragma unroll
+            for (int t = 0; t < CPT; ++t) v[t] = gm == 0 ? accm[0][t] : (gm == 1 ? accm[1][t] : accm[2][t]);
+            st_row_f64<LPR, CPT>(YM + (3 * row + gm) * ldym, l, v);
+        }
     }
 }
 
@@ -429,12 +485,13 @@ int spmm_dual_z32(const int32_t* brow, const int32_t* browP, const int32_t* bcol
             DS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
             carved = true;
         }
-        kern<<<nchunks, SD2_THREADS, 0, stream>>>(brow, browP, bcolP, perm, chunk_row, Kval, Mblk, Z, ncols, YK, ldyk, YM, ldym);
+        kern<<<nchunks, SZ_THREADS, 0, stream>>>(brow, browP, bcolP, perm, chunk_row, Kval, Mblk, Z, YK, ldyk, YM, ldym);
         DS_LAUNCH_CHECK();
         return DS_OK;
     };
-    const int cpl = ncols / 16;
-    return cpl == 1 ? go(k_spmm_dual_z32<1>) : (cpl == 2 ? go(k_spmm_dual_z32<2>) : go(k_spmm_dual_z32<3>));
+    DS_REQUIRE(ldyk % 2 == 0 && ldym % 2 == 0 && (uintptr_t)YK % 16 == 0 && (uintptr_t)YM % 16 == 0 && (uintptr_t)Z % 16 == 0,
+               "spmm_dual_z32: outputs and Z must be 16-byte aligned with even leading dimensions");
+    return ncols == 16 ? go(k_spmm_dual_z32<4, 4>) : (ncols == 32 ? go(k_spmm_dual_z32<8, 4>) : go(k_spmm_dual_z32<8, 6>));
 }
 
 }  // namespace ds

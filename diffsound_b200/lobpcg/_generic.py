@@ -113,19 +113,27 @@ class LOBPCG(object):
                 self.call_tracker()
 
     # ------------------------------------------------------------------ one step
-    def _rayleigh_ritz(self, ncols):
-        """Lowest pairs of the pencil projected on the first `ncols` work columns.  Returns (theta, C) or None."""
+    def _rayleigh_ritz(self, ncols, idx=None):
+        """Lowest pairs of the pencil projected on the work columns `idx` (default: the first `ncols`).
+        Returns (theta, C) with C's rows at the work-column positions (zero rows elsewhere), or None."""
         w8 = ncols // 8
         native.gram_sym2(self._S, self._AS, self._BS, list(range(w8)), self._GK, self._GM)
         GK, GM = self._GK[:ncols, :ncols], self._GM[:ncols, :ncols]
+        GK = torch.triu(GK) + torch.triu(GK, 1).T                 # only the upper-triangle tiles are written by the kernel
+        GM = torch.triu(GM) + torch.triu(GM, 1).T
+        if idx is not None:
+            GK, GM = GK[idx][:, idx].contiguous(), GM[idx][:, idx].contiguous()
         # shift that makes the scaled projected A positive definite: Gershgorin bound of D GK D, D = diag(GM)^-1/2
         d = torch.rsqrt(torch.clamp(torch.diagonal(GM), min=1e-300))
-        U = torch.triu(GK) + torch.triu(GK, 1).T                # only the upper triangle is written by the kernel
-        sig = float((U * d[:, None] * d[None, :]).abs().sum(1).max()) * 1.0000001 + 1e-300
+        sig = float((GK * d[:, None] * d[None, :]).abs().sum(1).max()) * 1.0000001 + 1e-300
         for _ in range(6):
             theta, C, info = native.eigh_generalized(GK, GM, sig)
             code = int(info[0])
             if code == 0:
+                if idx is not None:
+                    Cf = torch.zeros(ncols, C.shape[1], dtype=C.dtype, device=C.device)
+                    Cf[idx] = C
+                    C = Cf
                 return theta, C
             if code < 1000:              # projected B is not positive definite: dependent search directions
                 return None
@@ -145,10 +153,11 @@ class LOBPCG(object):
             self.ivars["iterations_left"] = self.iparams["niter"]
             self.ivars["converged_count"] = 0
             self.ivars["converged_end"] = 0
+            self._best = None
             S.zero_(); AS.zero_(); BS.zero_()
             S[:, :n] = self.X.to(f64)
             if w > n:                      # padding columns: extra search directions
-                g = torch.Generator(device=S.device).manual_seed(1)
+                g = torch.Generator(device=S.device).manual_seed(0x5EED0B200)
                 S[:, n:w] = torch.randn(S.shape[0], w - n, dtype=f64, device=S.device, generator=g)
             AS[:, :w] = self._A(S[:, :w])
             BS[:, :w] = self._apply(self.B, S[:, :w])
@@ -157,9 +166,12 @@ class LOBPCG(object):
                 raise ValueError("lobpcg: the initial block X is not B-independent")
             ncols = w
         else:
-            # W = iK R, B-orthogonalised against X
+            # W = iK R for the columns that have not converged (the leading `converged_count` pairs are locked softly:
+            # they stay in the Rayleigh-Ritz basis but get no new search directions, _lobpcg.py:394-431), B-orthogonalised
+            # against X
+            nc = self.ivars["converged_count"]
             Rw = torch.zeros(S.shape[0], w, dtype=f64, device=S.device)
-            Rw[:, :n] = self.R.to(f64)
+            Rw[:, nc:n] = self.R.to(f64)[:, nc:]
             if w > n:
                 Rw[:, n:] = AS[:, n:w] - BS[:, n:w] * self._theta[n:w]
             W = self._apply(self.iK, Rw).contiguous()
@@ -168,11 +180,14 @@ class LOBPCG(object):
             S[:, w:2 * w] = W
             AS[:, w:2 * w] = self._A(W)
             BS[:, w:2 * w] = self._apply(self.B, W)
-            ncols = (3 if self._np else 2) * w
-            rr = self._rayleigh_ritz(ncols)
-            if rr is None and self._np:
+            act = torch.arange(nc, w, device=S.device)
+            rr = None
+            if self._np:
+                ncols = 3 * w
+                rr = self._rayleigh_ritz(ncols, torch.cat([torch.arange(w, device=S.device), w + act, 2 * w + act]))
+            if rr is None:
                 ncols = 2 * w
-                rr = self._rayleigh_ritz(ncols)
+                rr = self._rayleigh_ritz(ncols, torch.cat([torch.arange(w, device=S.device), w + act]))
             if rr is None:                 # search directions collapsed: nothing more to gain
                 self.ivars["iterations_left"] = 1
                 ncols, rr = w, self._rayleigh_ritz(w)
@@ -196,3 +211,15 @@ class LOBPCG(object):
         self.S[:, :n] = self.X
         self.ivars["iterations_left"] -= 1
         self.ivars["istep"] += 1
+        # Divergence guard: in low precision (fp32 operators) the attainable residual can sit above `tol`; iterating on
+        # noise-level residuals then degrades the basis.  Keep the best state seen (largest converged count, then
+        # smallest leading residual) and stop with it once the leading residual has grown tenfold over its best.
+        k = self.iparams["k"]
+        score = (self.ivars["converged_count"], -float(self.tvars["rerr"][:k].max()))
+        if self._best is None or score >= self._best[0]:
+            self._best = (score, self.E.clone(), self.X.clone(), self.tvars["rerr"].clone(), self.ivars["converged_count"])
+        elif -score[1] > 10.0 * -self._best[0][1] or self.ivars["iterations_left"] == 0:
+            _, self.E, self.X, rerr, cc = self._best
+            self.tvars["rerr"] = rerr
+            self.ivars["converged_count"] = cc
+            self.bvars["force_stop"] = True

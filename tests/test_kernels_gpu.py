@@ -256,6 +256,9 @@ def test_gram_sym2_matches_fp64(ld, tiles):
                 assert (gk[blk] == -7.0).all() and (gm[blk] == -7.0).all()
 
 
+DEV = "cuda:0"
+
+
 def test_gram_strip_matches_torch():
     from diffsound_b200 import native
     torch.manual_seed(3)
