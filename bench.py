@@ -431,6 +431,34 @@ def main():
                 "frac": per_launch_bytes / t_avg / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
                 "launches_per_step": steps_total, "avg_launch_ms": t_avg * 1e3, "avg_cols": c_avg,
                 "bytes_per_launch": per_launch_bytes, "share_of_step": prof["cheb_step"]["ms"] / ms}
+    # ---- every kernel class against the roofline that bounds it (algorithmic bytes / flops accounted at the launch sites,
+    # csrc/prof.cu; device time from the CUDA events of the untimed profiling pass)
+    fp64_peak = None
+    try:
+        fp64_peak = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))["dmma_m8n8k4_tflops"]
+    except Exception:
+        pass
+    roofline_all = {}
+    names = {"spmm": "k_spmm_dual_z32 / k_spmm_dual (FP64 K.W, M.W)", "assemble": "k_tet_geometry + k_assemble_rows",
+             "gram": "k_gram_strip / k_gram_sym2 / k_gram (DMMA)", "block_gemm": "k_rr_update2 / k_block_gemm (DMMA)",
+             "grad_shape": "k_eigval_grad_shape"}
+    for cls, kname in names.items():
+        v = prof_all.get(cls)
+        if not v or not v["ms"]:
+            continue
+        sec = v["ms"] * 1e-3
+        ent = {"kernels": kname, "ms_per_step": v["ms"] / 2, "launches_per_step": v["count"] / 2,
+               "algorithmic_GB_per_step": v["bytes"] / 2 / 1e9, "achieved_GBps": v["bytes"] / sec / 1e9,
+               "hbm_frac": v["bytes"] / sec / 1e9 / peak}
+        if v["flops"]:
+            ent["algorithmic_GFLOP_per_step"] = v["flops"] / 2 / 1e9
+            ent["achieved_TFLOPs"] = v["flops"] / sec / 1e12
+            if fp64_peak:
+                ent["fp64_frac"] = v["flops"] / sec / 1e12 / fp64_peak
+        roofline_all[cls] = ent
+    if roof:
+        roofline_all["cheb_step"] = {"kernels": "k_spmm32v (fine-level FP32 SpMM)", "ms_per_step": prof_all["cheb_step"]["ms"] / 2,
+                                     "achieved_GBps": roof["achieved"], "hbm_frac": roof["frac"]}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "ms_each_step": each_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -448,7 +476,8 @@ def main():
                     "steps": e2e_steps},
             "gpu_launches": launches, "clocks": sampler.summary(),
             "kernel_ms_per_step": {k: v["ms"] / 2 for k, v in prof_all.items()},
-            "roofline": roof}
+            "roofline": roof, "roofline_all": roofline_all,
+            "fp64_peak_tflops": fp64_peak}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"], _ = cpu_baseline(args.cpu_cube, steps=1, warmup=0, budget_s=120.0)
     if rank == 0:

@@ -99,7 +99,8 @@ SIGNATURES = {
     "ds_gram_strip_scratch_elems": (i64, []),
     "ds_gram_strip_f64": (cint, [f64p, f64p, i64, cint, f64p, i64, cint, i64, f64p, f64p, i64, f64p, ptr]),
     "ds_rr_update2_f64": (cint, [f64p, f64p, f64p, i64, cint, cint, cint, f64p, i64, i64, f64p, f64p, f64p, i64, ptr]),
-    "ds_gram_algebra_f64": (cint, [f64p, f64p, f64p, f64p, i64, f64p, i64, f64p, cint, ptr]),
+    "ds_gram_algebra_scratch_elems": (i64, []),
+    "ds_gram_algebra_f64": (cint, [f64p, f64p, f64p, f64p, i64, f64p, i64, f64p, cint, f64p, ptr]),
     "ds_fp64_peak": (cint, [cint, cint, cint, f64p, C.POINTER(C.c_double), ptr]),
     "ds_prof_enable": (cint, [cint]),
     "ds_prof_enable_classes": (cint, [C.c_uint32]),

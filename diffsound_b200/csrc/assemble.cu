@@ -329,6 +329,8 @@ extern "C" int ds_assemble_km(const float* verts, const int32_t* tets, int64_t T
     DS_REQUIRE(T > 0 && n_nodes > 0, "ds_assemble_km: empty mesh");
     int npe = order == 1 ? 4 : 10;
     ProfScope prof(PROF_ASSEMBLE, stream);
+    prof_account(PROF_ASSEMBLE, 2.0 * 9.0 * (double)nnzb * 8.0 + (double)T * npe * 4.0 + (double)n_nodes * 12.0 + (double)T * npe * npe * 4.0,
+                 0.0);
     k_tet_geometry<<<(unsigned)ceil_div(T, 128), 128, 0, stream>>>(verts, tets, T, npe, order, geom);
     DS_LAUNCH_CHECK();
     // grid-stride over rows: the per-order tables are staged into shared memory once per CTA

@@ -154,6 +154,7 @@ int gram_f64(const double* A, int64_t lda, int p, const double* B, int64_t ldb, 
     size_t smem = (size_t)GRAM_STAGES * GRAM_ROWS * (ps + qs) * sizeof(double) + 2 * GRAM_STAGES * sizeof(uint64_t);
     int ctas = gram_ctas(n);
     ProfScope prof(PROF_GRAM, stream);
+    prof_account(PROF_GRAM, (double)n * (p + q) * 8.0, 2.0 * (double)n * p * q);
     int ntile = (p / 8) * (q / 8);
     int maxt = (ntile + 7) / 8;
     auto launch = [&](auto kern) -> int {
@@ -234,6 +235,7 @@ int block_gemm_f64(const double* A, int64_t lda, int p, const double* C, int64_t
     DS_REQUIRE(A != Y, "block_gemm: A must not alias Y");
     int qs = pad8mod16(q);
     ProfScope prof(PROF_GEMM, stream);
+    prof_account(PROF_GEMM, (double)n * (p + (beta != 0.0 ? 2 : 1) * q) * 8.0, 2.0 * (double)n * p * q);
     size_t smem = (size_t)p * qs * sizeof(double);
     int64_t strips = (n + 7) / 8;
     int ctas = (int)std::min<int64_t>((strips + 7) / 8, 148 * 4);

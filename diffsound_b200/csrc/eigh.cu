@@ -7,8 +7,10 @@
 //   D = diag(GM)^-1/2;  L L^T = D GM D;  R R^T = D (GK + sigma GM) D;  Y = L^-1 R;
 //   one-sided Jacobi orthogonalises the ROWS of Y:  Q^T Y,  |row_j|^2 = theta_j + sigma;
 //   c_j = D R^-T row_j.
-// Three kernels:
-//   k_eigh_prepare (one CTA)      gather/scale, both Cholesky factorisations, Y -> global scratch
+// Four kernels (round 2: the factorisations and the triangular solves no longer sit on one CTA -- 0.40 + 0.12 ms of a
+// 1.2 ms solve were spent there with 147 SMs idle):
+//   k_eigh_chol    (two CTAs)     gather / scale; CTA 0 factorises D GM D, CTA 1 D (GK + sigma GM) D, concurrently
+//   k_eigh_solve   (ten CTAs)     Y = L^-1 R, one warp per column (columns are independent), Y -> global scratch
 //   k_eigh_jacobi  (cluster of 8) the Jacobi sweeps.  One WARP per pair of rows, rows in registers
 //                                 (5 elements per lane); pairs follow the odd-even transposition
 //                                 ordering on a line of positions, so per step exactly one row per warp
@@ -17,7 +19,7 @@
 //                                 neighbour sits in another CTA of the cluster, and one
 //                                 barrier.cluster per step.  One SM's FP64 pipe and shared-memory
 //                                 bandwidth were the limit of the single-CTA version (4.3 ms at N = 144).
-//   k_eigh_finish  (one CTA)      eigenvalues, ascending rank, back substitution, C.
+//   k_eigh_finish  (nine CTAs)    eigenvalues, ascending rank; c_j = D R^-T row_j, one warp per row (rows are independent).
 #include "common.cuh"
 #include "../../include/diffsound_sm100.h"
 #include "kernels.cuh"
@@ -35,12 +37,16 @@ constexpr int JC_LD = 32 * JC_E;                  // row pitch of Y in global sc
 constexpr int JC_SLOT = JC_LD + 8;                // mailbox slot: elements + |row|^2 at [JC_LD]
 static_assert(JC_GPC * JC_CL * 2 == EIG_MAXN, "line positions must tile the cluster");
 
-// scratch layout (doubles): L^T [N*N] | R [N*N] | Y [(N+1) * JC_LD] | scale [N] | sigma, fail [8]
+// scratch layout (doubles): L [N*N] | R [N*N] | Y [(N+1) * JC_LD] | scale [N] | 1/diag(L) [N] | 1/diag(R) [N] |
+// meta [8]: sigma, fail, code of CTA 0, code of CTA 1 | R^T [N*N]
 __host__ __device__ inline size_t eig_off_Rt(int N) { return (size_t)N * N; }
 __host__ __device__ inline size_t eig_off_Y(int N) { return 2 * (size_t)N * N; }
 __host__ __device__ inline size_t eig_off_scale(int N) { return eig_off_Y(N) + (size_t)(N + 1) * JC_LD; }
-__host__ __device__ inline size_t eig_off_meta(int N) { return eig_off_scale(N) + N; }
-int64_t eigh_scratch_elems(int N) { return (int64_t)eig_off_meta(N) + 8; }
+__host__ __device__ inline size_t eig_off_invL(int N) { return eig_off_scale(N) + N; }
+__host__ __device__ inline size_t eig_off_invR(int N) { return eig_off_invL(N) + N; }
+__host__ __device__ inline size_t eig_off_meta(int N) { return eig_off_invR(N) + N; }
+__host__ __device__ inline size_t eig_off_RT(int N) { return eig_off_meta(N) + 8; }      // R^T (row k = column k of R)
+int64_t eigh_scratch_elems(int N) { return (int64_t)eig_off_RT(N) + (int64_t)N * N; }
 
 constexpr int EIG_NB = 16;                        // block size of the blocked factorisations / substitutions
 
@@ -132,108 +138,107 @@ __device__ __forceinline__ double g_up(const double* __restrict__ G, int64_t ldg
     return a <= b ? G[(int64_t)a * ldg + b] : G[(int64_t)b * ldg + a];
 }
 
+// blockIdx.x = 0: L = chol(D GM D);  1: R = chol(D (GK + sigma GM) D).  Factors go to global scratch row-major with
+// their reciprocal diagonals; failure codes to meta[2 + blockIdx.x] (0 = ok, else failing column + 1).
 __global__ void __launch_bounds__(EIG_THREADS)
-k_eigh_prepare(const double* __restrict__ GK, const double* __restrict__ GM, int N, int64_t ldg,
-               const __grid_constant__ EigIdx ix, double sigma_in, double* __restrict__ scratch,
-               int* __restrict__ info) {
+k_eigh_chol(const double* __restrict__ GK, const double* __restrict__ GM, int N, int64_t ldg,
+            const __grid_constant__ EigIdx ix, double sigma_in, double* __restrict__ scratch) {
     extern __shared__ __align__(16) double S[];  // [N][ld]
     const int ld = N + 2;
     double* s_scale = S + (size_t)N * ld;        // [N]
     int* s_flag = reinterpret_cast<int*>(s_scale + N);
-    const int tid = threadIdx.x, nt = blockDim.x;
-    double* Lt = scratch;                        // L^T, row-major: Lt[k][i] = L[i][k]
-    double* Rg = scratch + eig_off_Rt(N);        // R, row-major [N][N]
-    double* Yg = scratch + eig_off_Y(N);
+    const int tid = threadIdx.x, nt = blockDim.x, which = blockIdx.x;
+    double* out = scratch + (which == 0 ? 0 : eig_off_Rt(N));
+    double* inv = scratch + (which == 0 ? eig_off_invL(N) : eig_off_invR(N));
     double* meta = scratch + eig_off_meta(N);
-    if (tid == 0) { s_flag[0] = 0; meta[1] = 1.0; }      // meta[1] = fail until the factorisations succeed
+    if (tid == 0) s_flag[0] = 0;
     for (int i = tid; i < N; i += nt) {
         double d = g_up(GM, ldg, ix, i, i);
         s_scale[i] = d > 0.0 ? rsqrt(d) : 1.0;
     }
     __syncthreads();
-    // sigma < 0: automatic shift = |sigma| * mean diagonal of the scaled GK
     double sigma = sigma_in;
-    if (sigma_in < 0.0) {
+    if (which == 1 && sigma_in < 0.0) {          // automatic shift = |sigma| * mean diagonal of the scaled GK
         double tr = 0.0;
         for (int i = 0; i < N; ++i) tr += fabs(g_up(GK, ldg, ix, i, i)) * s_scale[i] * s_scale[i];
         sigma = -sigma_in * tr / N;
     }
-    // ---- L = chol(D GM D)
-    for (int t = tid; t < N * N; t += nt) {
-        int i = t / N, j = t % N;
-        double v = (j <= i) ? g_up(GM, ldg, ix, i, j) : 0.0;
-        S[i * ld + j] = v * s_scale[i] * s_scale[j];
-    }
-    __syncthreads();
-    int bad = chol_lower(S, N, ld, s_flag);
-    if (bad) { if (tid == 0) { info[0] = bad; info[1] = 0; } return; }
-    for (int t = tid; t < N * N; t += nt) {
-        int k = t / N, i = t % N;   // Lt[k][i] = L[i][k]
-        Lt[t] = (k <= i) ? S[i * ld + k] : 0.0;
-    }
-    __syncthreads();
-    // ---- R = chol(D (GK + sigma GM) D)
     for (int t = tid; t < N * N; t += nt) {
         int i = t / N, j = t % N;
         double v = 0.0;
-        if (j <= i) v = g_up(GK, ldg, ix, i, j) + sigma * g_up(GM, ldg, ix, i, j);
+        if (j <= i) v = which == 0 ? g_up(GM, ldg, ix, i, j) : g_up(GK, ldg, ix, i, j) + sigma * g_up(GM, ldg, ix, i, j);
         S[i * ld + j] = v * s_scale[i] * s_scale[j];
     }
     __syncthreads();
-    bad = chol_lower(S, N, ld, s_flag);
-    if (bad) { if (tid == 0) { info[0] = 1000 + bad; info[1] = 0; } return; }
+    const int bad = chol_lower(S, N, ld, s_flag);
+    if (tid == 0) meta[2 + which] = (double)bad;
+    if (bad) return;
     for (int t = tid; t < N * N; t += nt) {
         int i = t / N, j = t % N;
-        Rg[t] = (j <= i) ? S[i * ld + j] : 0.0;
-        if (j > i) S[i * ld + j] = 0.0;
+        out[t] = (j <= i) ? S[i * ld + j] : 0.0;
     }
-    __threadfence_block();
-    __syncthreads();
-    // ---- Y = L^-1 R in place (Y lower triangular), blocked forward substitution: the EIG_NB rows of a
-    //      block are solved by one thread per column against the diagonal block of L (staged in shared
-    //      memory), then eliminated from all later rows by the whole CTA -- 3 barriers per block of rows
-    double* Ld = s_scale + N + 4;                    // [EIG_NB][EIG_NB] diagonal block of L
-    for (int kb = 0; kb < N; kb += EIG_NB) {
-        const int nb = min(EIG_NB, N - kb);
-        for (int t = tid; t < nb * nb; t += nt) {
-            const int k = t / nb, q = t - k * nb;    // Ld[k][q] = L[kb+k][kb+q] = Lt[(kb+q) * N + kb+k]
-            Ld[k * EIG_NB + q] = Lt[(size_t)(kb + q) * N + kb + k];
+    if (which == 1) {
+        double* RT = scratch + eig_off_RT(N);
+        for (int t = tid; t < N * N; t += nt) {
+            int k = t / N, q = t % N;            // RT[k][q] = R[q][k]
+            RT[t] = (k <= q) ? S[q * ld + k] : 0.0;
         }
-        __syncthreads();
-        const int w = kb + nb;                       // non-zero columns of these rows
-        if (tid < w) {
-            double y[EIG_NB];
-#pragma unroll
-            for (int k = 0; k < EIG_NB; ++k) {
-                if (k < nb) {
-                    double v = S[(size_t)(kb + k) * ld + tid];
-#pragma unroll
-                    for (int q = 0; q < EIG_NB; ++q)
-                        if (q < k) v -= Ld[k * EIG_NB + q] * y[q];
-                    y[k] = v / Ld[k * EIG_NB + k];
-                    S[(size_t)(kb + k) * ld + tid] = y[k];
-                }
-            }
-        }
-        __syncthreads();
-        const int r = N - kb - nb;
-        for (int t = tid; t < r * w; t += nt) {
-            const int ii = t / w, j = t - ii * w;
-            const int i = kb + nb + ii;
-            double v = 0.0;
-            for (int q = 0; q < nb; ++q) v = fma(Lt[(size_t)(kb + q) * N + i], S[(size_t)(kb + q) * ld + j], v);
-            S[(size_t)i * ld + j] -= v;
-        }
-        __syncthreads();
     }
-    // ---- rows of Y (zero padded to JC_LD, plus one zero row when N is odd) -> global
+    for (int i = tid; i < N; i += nt) inv[i] = 1.0 / S[i * ld + i];
+    if (which == 0) for (int i = tid; i < N; i += nt) scratch[eig_off_scale(N) + i] = s_scale[i];
+    if (which == 1 && tid == 0) meta[0] = sigma;
+}
+
+constexpr int ES_WARPS = 16;                     // columns (solve) / rows (finish) per CTA
+
+// Y = L^-1 R, column by column: warp w of CTA c owns column j = 16 c + w; lane l keeps y_k for k = l (mod 32).
+// Also merges the failure codes of k_eigh_chol into info / meta[1] and zero-pads Y to JC_LD columns, Np rows.
+__global__ void __launch_bounds__(ES_WARPS * 32)
+k_eigh_solve(int N, double* __restrict__ scratch, int* __restrict__ info) {
+    const double* __restrict__ L = scratch;
+    const double* __restrict__ R = scratch + eig_off_Rt(N);
+    const double* __restrict__ invL = scratch + eig_off_invL(N);
+    double* __restrict__ Yg = scratch + eig_off_Y(N);
+    double* meta = scratch + eig_off_meta(N);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c0 = (int)meta[2], c1 = (int)meta[3];
+    if (c0 || c1) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) { info[0] = c0 ? c0 : 1000 + c1; info[1] = 0; meta[1] = 1.0; }
+        return;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) meta[1] = 0.0;
     const int Np = (N + 1) & ~1;
-    for (int t = tid; t < Np * JC_LD; t += nt) {
-        int p = t / JC_LD, e = t - p * JC_LD;
-        Yg[t] = (p < N && e < N) ? S[p * ld + e] : 0.0;
+    const int j = blockIdx.x * ES_WARPS + warp;
+    if (j >= JC_LD) return;
+    if (j >= N) {                                // padding column
+        for (int i = lane; i < Np; i += 32) Yg[(size_t)i * JC_LD + j] = 0.0;
+        return;
     }
-    for (int i = tid; i < N; i += nt) scratch[eig_off_scale(N) + i] = s_scale[i];
-    if (tid == 0) { meta[0] = sigma; meta[1] = 0.0; }
+    double y[JC_E];
+#pragma unroll
+    for (int t = 0; t < JC_E; ++t) y[t] = 0.0;
+#pragma unroll
+    for (int ti = 0; ti < JC_E; ++ti) {          // i = 32 ti + ii: the register that receives y_i is static
+        for (int ii = 0; ii < 32; ++ii) {
+            const int i = 32 * ti + ii;
+            if (i < j || i >= N) continue;       // warp-uniform
+            const double* Li = L + (size_t)i * N;
+            double s = 0.0;
+#pragma unroll
+            for (int t = 0; t < JC_E; ++t) {
+                const int k = lane + 32 * t;
+                if (k >= j && k < i) s = fma(__ldg(Li + k), y[t], s);
+            }
+            s = warp_sum(s);
+            const double yi = (__ldg(R + (size_t)i * N + j) - s) * __ldg(invL + i);
+            if (lane == ii) y[ti] = yi;
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < JC_E; ++t) {
+        const int i = lane + 32 * t;
+        if (i < Np) Yg[(size_t)i * JC_LD + j] = (i >= j && i < N) ? y[t] : 0.0;
+    }
 }
 
 // ---- cluster primitives ----------------------------------------------------------------------
@@ -424,106 +429,87 @@ k_eigh_jacobi(int N, double* __restrict__ scratch, int* __restrict__ info) {
     cluster_sync_all();                                        // no CTA leaves while DSMEM traffic may be pending
 }
 
-__global__ void __launch_bounds__(EIG_THREADS)
+// Eigenvalues = |row|^2 - sigma, ascending rank (every CTA recomputes the 144 norms: cheap), then for the rows of this
+// CTA (one warp each)  c_j = D R^-T row_j:  x R = y_j by back substitution, lane l keeps x_k for k = l (mod 32).
+__global__ void __launch_bounds__(ES_WARPS * 32)
 k_eigh_finish(int N, const __grid_constant__ EigIdx ix, double* __restrict__ theta, double* __restrict__ C, int64_t ldc,
               const double* __restrict__ scratch, int* __restrict__ info) {
-    extern __shared__ __align__(16) double S[];  // [N][ld]
-    const int ld = N + 2;
-    double* s_scale = S + (size_t)N * ld;        // [N]
-    double* s_theta = s_scale + N;               // [N + 2]
-    int* s_rank = reinterpret_cast<int*>(s_theta + N + 2);   // [N]
-    int* s_flag = s_rank + N;                    // [2]
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const double* Rg = scratch + eig_off_Rt(N);  // R, row-major (lower triangular)
-    const double* Yg = scratch + eig_off_Y(N);
+    __shared__ double s_theta[EIG_MAXN + 2];
+    __shared__ int s_rank[EIG_MAXN + 2];
+    __shared__ int s_hole;
+    const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31;
+    const double* __restrict__ RT = scratch + eig_off_RT(N);
+    const double* __restrict__ invR = scratch + eig_off_invR(N);
+    const double* __restrict__ Yg = scratch + eig_off_Y(N);
+    const double* __restrict__ scale = scratch + eig_off_scale(N);
     const double* meta = scratch + eig_off_meta(N);
-    if (meta[1] != 0.0) return;                  // info was set by k_eigh_prepare
+    if (meta[1] != 0.0) return;                  // info was set by k_eigh_solve
     const double sigma = meta[0];
     const int Np = (N + 1) & ~1;
     // norms of all line positions; an odd N leaves exactly one zero row somewhere on the line
-    for (int p = tid / 32; p < Np; p += nt / 32) {
+    for (int p = warp; p < Np; p += nt / 32) {
         double v = 0.0;
-        for (int e = tid & 31; e < N; e += 32) { double a = Yg[(size_t)p * JC_LD + e]; v = fma(a, a, v); }
+        for (int e = lane; e < N; e += 32) { const double a = Yg[(size_t)p * JC_LD + e]; v = fma(a, a, v); }
         v = warp_sum(v);
-        if ((tid & 31) == 0) s_theta[p] = v;
+        if (lane == 0) s_theta[p] = v;
     }
-    for (int i = tid; i < N; i += nt) s_scale[i] = scratch[eig_off_scale(N) + i];
     __syncthreads();
     if (tid == 0) {
         int ph = Np;
         if (Np > N)
             for (int p = 0; p < Np; ++p)
                 if (s_theta[p] == 0.0) { ph = p; break; }
-        s_flag[0] = ph;
+        s_hole = ph;
     }
     __syncthreads();
-    const int ph = s_flag[0];
-    for (int t = tid; t < N * N; t += nt) {
-        int j = t / N, e = t - j * N;
-        S[(size_t)j * ld + e] = Yg[(size_t)(j + (j >= ph ? 1 : 0)) * JC_LD + e];
-    }
+    const int ph = s_hole;
+    // compact: row j of the problem sits at line position j + (j >= ph)
+    double mine = 0.0;
+    if (tid < N) mine = s_theta[tid + (tid >= ph ? 1 : 0)] - sigma;
     __syncthreads();
-    // ---- eigenvalues and ascending rank
-    for (int j = tid / 32; j < N; j += nt / 32) {
-        double v = 0.0;
-        for (int e = tid & 31; e < N; e += 32) { double a = S[(size_t)j * ld + e]; v = fma(a, a, v); }
-        v = warp_sum(v);
-        if ((tid & 31) == 0) s_theta[j] = v - sigma;
-    }
+    if (tid < N) s_theta[tid] = mine;
     __syncthreads();
     for (int j = tid; j < N; j += nt) {
-        double tj = s_theta[j];
+        const double tj = s_theta[j];
         int rk = 0;
         for (int i = 0; i < N; ++i) {
-            double ti = s_theta[i];
+            const double ti = s_theta[i];
             rk += (ti < tj) || (ti == tj && i < j);
         }
         s_rank[j] = rk;
-        theta[rk] = tj;
+        if (blockIdx.x == 0) theta[rk] = tj;
     }
     __syncthreads();
-    // ---- c_j^T = y_j R^-1 for all rows j at once (x R = y, R lower triangular), blocked back substitution from
-    //      the last block of columns: one thread per row solves the EIG_NB unknowns of the block against the
-    //      diagonal block of R (staged in shared memory), then the whole CTA eliminates them from the columns to
-    //      the left -- 3 barriers per block of columns; scaled and placed in column rank_j below
-    double* Rd = reinterpret_cast<double*>(s_flag + 2 + (N & 1));   // 8-byte aligned, [EIG_NB][EIG_NB]
-    for (int kb = ((N - 1) / EIG_NB) * EIG_NB; kb >= 0; kb -= EIG_NB) {
-        const int nb = min(EIG_NB, N - kb);
-        for (int t = tid; t < nb * nb; t += nt) {
-            const int k = t / nb, q = t - k * nb;    // Rd[k][q] = R[kb+k][kb+q]
-            Rd[k * EIG_NB + q] = Rg[(size_t)(kb + k) * N + kb + q];
-        }
-        __syncthreads();
-        if (tid < N) {
-            double* xr = S + (size_t)tid * ld + kb;
-            double x[EIG_NB];
+    const int j = blockIdx.x * ES_WARPS + warp;
+    if (j < N) {
+        const double* yrow = Yg + (size_t)(j + (j >= ph ? 1 : 0)) * JC_LD;
+        double x[JC_E];
 #pragma unroll
-            for (int k = EIG_NB - 1; k >= 0; --k) {
-                if (k < nb) {
-                    double v = xr[k];
+        for (int t = 0; t < JC_E; ++t) { const int k = lane + 32 * t; x[t] = k < N ? yrow[k] : 0.0; }
+        // x_k = (y_k - sum_{q > k} x_q R[q][k]) / R[k][k], k = N-1 .. 0; at step k the lanes hold final x_q for q > k
 #pragma unroll
-                    for (int q = EIG_NB - 1; q >= 0; --q)
-                        if (q > k && q < nb) v -= x[q] * Rd[q * EIG_NB + k];
-                    x[k] = v / Rd[k * EIG_NB + k];
-                    xr[k] = x[k];
+        for (int tk = JC_E - 1; tk >= 0; --tk) {     // k = 32 tk + kk: the register that holds x_k is static
+            for (int kk = 31; kk >= 0; --kk) {
+                const int k = 32 * tk + kk;
+                if (k >= N) continue;                // warp-uniform
+                double s = 0.0;
+#pragma unroll
+                for (int t = 0; t < JC_E; ++t) {
+                    const int q = lane + 32 * t;
+                    if (q > k && q < N) s = fma(x[t], __ldg(RT + (size_t)k * N + q), s);
                 }
+                s = warp_sum(s);
+                if (lane == kk) x[tk] = (x[tk] - s) * __ldg(invR + k);
             }
         }
-        __syncthreads();
-        for (int t = tid; t < N * kb; t += nt) {
-            const int j = t / kb, kp = t - j * kb;
-            const double* xr = S + (size_t)j * ld + kb;
-            double v = 0.0;
-            for (int q = 0; q < nb; ++q) v = fma(xr[q], Rg[(size_t)(kb + q) * N + kp], v);
-            S[(size_t)j * ld + kp] -= v;
+        const int col = s_rank[j];
+#pragma unroll
+        for (int t = 0; t < JC_E; ++t) {
+            const int k = lane + 32 * t;
+            if (k < N) C[(int64_t)ix.v[k] * ldc + col] = x[t] * scale[k];
         }
-        __syncthreads();
     }
-    for (int t = tid; t < N * N; t += nt) {
-        int k = t / N, j = t % N;
-        C[(int64_t)ix.v[k] * ldc + s_rank[j]] = S[(size_t)j * ld + k] * s_scale[k];
-    }
-    if (tid == 0) info[0] = 0;
+    if (blockIdx.x == 0 && tid == 0) info[0] = 0;
 }
 
 int eigh_generalized_f64(const double* GK, const double* GM, int N, int64_t ldg, const int* idx_host, double sigma,
@@ -533,21 +519,20 @@ int eigh_generalized_f64(const double* GK, const double* GM, int N, int64_t ldg,
     ProfScope prof(PROF_EIGH, stream);
     EigIdx ix;
     for (int i = 0; i < EIG_MAXN; ++i) ix.v[i] = (short)(i < N ? (idx_host ? idx_host[i] : i) : 0);
-    const size_t smem = ((size_t)N * (N + 2) + 2 * N + 2) * sizeof(double) + (N + 4) * sizeof(int) +
-                        (EIG_NB * EIG_NB + 8) * sizeof(double);
+    const size_t smem = ((size_t)N * (N + 2) + 2 * N + 2) * sizeof(double) + (N + 4) * sizeof(int);
     static bool attr = false;
     if (!attr) {
-        const int mx = (int)(((size_t)EIG_MAXN * (EIG_MAXN + 2) + 2 * EIG_MAXN + 2) * sizeof(double) +
-                             (EIG_MAXN + 4) * sizeof(int) + (EIG_NB * EIG_NB + 8) * sizeof(double));
-        DS_CUDA(cudaFuncSetAttribute(k_eigh_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-        DS_CUDA(cudaFuncSetAttribute(k_eigh_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        const int mx = (int)(((size_t)EIG_MAXN * (EIG_MAXN + 2) + 2 * EIG_MAXN + 2) * sizeof(double) + (EIG_MAXN + 4) * sizeof(int));
+        DS_CUDA(cudaFuncSetAttribute(k_eigh_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
         attr = true;
     }
-    k_eigh_prepare<<<1, EIG_THREADS, smem, stream>>>(GK, GM, N, ldg, ix, sigma, scratch, info);
+    k_eigh_chol<<<2, EIG_THREADS, smem, stream>>>(GK, GM, N, ldg, ix, sigma, scratch);
+    DS_LAUNCH_CHECK();
+    k_eigh_solve<<<JC_LD / ES_WARPS, ES_WARPS * 32, 0, stream>>>(N, scratch, info);
     DS_LAUNCH_CHECK();
     k_eigh_jacobi<<<JC_CL, JC_THREADS, 0, stream>>>(N, scratch, info);
     DS_LAUNCH_CHECK();
-    k_eigh_finish<<<1, EIG_THREADS, smem, stream>>>(N, ix, theta, C, ldc, scratch, info);
+    k_eigh_finish<<<(N + ES_WARPS - 1) / ES_WARPS, ES_WARPS * 32, 0, stream>>>(N, ix, theta, C, ldc, scratch, info);
     DS_LAUNCH_CHECK();
     return DS_OK;
 }

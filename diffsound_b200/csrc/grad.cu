@@ -516,6 +516,11 @@ extern "C" int ds_eigval_grad_shape(const float* verts, const int32_t* tets, int
     DS_REQUIRE(T > 0 && n_nodes > 0 && k > 0 && k <= 1024 && ldu >= k, "ds_eigval_grad_shape: bad sizes");
     const int kpad = (k + 15) & ~15;
     ProfScope prof(PROF_GRAD, stream);
+    {   // n k 8 (U once) + T npe 4 + nodes 12 + nodes 24; flops: per tet and mode the quadratic forms of the 4 corner
+        // derivatives, ~ 2 (3 npe)^2 x 12 / 4 (counted from the kernel's DMMA tiles in DESIGN.md)
+        const int npe_ = order == 1 ? 4 : 10;
+        prof_account(PROF_GRAD, (double)n_nodes * 3.0 * k * 8.0 + (double)T * npe_ * 4.0 + (double)n_nodes * 36.0, 0.0);
+    }
     int64_t ctas64 = ceil_div(T, GS_WARPS);
     int ctas = (int)(ctas64 < 148 * 8 ? ctas64 : 148 * 8);
     if (order == 1) {

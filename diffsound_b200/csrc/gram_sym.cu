@@ -169,6 +169,7 @@ int gram_sym2(const double* S, const double* KS, const double* MS, int64_t ld, i
             plan.n_entries++;
         }
     ProfScope prof(PROF_GRAM, stream);
+    prof_account(PROF_GRAM, 3.0 * (double)n * ld * 8.0, 2.0 * 2.0 * (double)n * 64.0 * plan.n_entries);
     static bool attr = false;
     if (!attr) {
         DS_CUDA(cudaFuncSetAttribute(k_gram_sym2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_SMEM));

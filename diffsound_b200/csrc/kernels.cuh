@@ -14,7 +14,8 @@ int spmm_dual(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, const d
 // K Z, M Z for an fp32 block Z in a level's own (Morton) numbering; see k_spmm_dual_z32
 int spmm_dual_z32(const int32_t* brow, const int32_t* browP, const int32_t* bcolP, const int32_t* perm,
                   const int32_t* chunk_row, int nchunks, int64_t n_nodes, const double* Kval, const double* Mblk,
-                  const float* Z, int ncols, double* YK, int64_t ldyk, double* YM, int64_t ldym, cudaStream_t stream);
+                  const float* Z, int ncols, double* YK, int64_t ldyk, double* YM, int64_t ldym, cudaStream_t stream,
+                  int64_t nnzb = 0);
 int spmm32_chunk_count(int64_t n_nodes);
 
 // precond32.cu -- FP32 preconditioner pieces
@@ -92,7 +93,8 @@ int64_t gram_strip_scratch_elems(int num_sms);
 int gram_strip(const double* KW, const double* MW, int64_t ldw, int wa, const double* S, int64_t lds, int ncol, int64_t n,
                double* GsK, double* GsM, int64_t ldg, double* partial, int num_sms, cudaStream_t stream);
 int gram_algebra(const double* GK, const double* GM, double* GKn, double* GMn, int64_t ldg, const double* C, int64_t ldc,
-                 const double* theta, int m, cudaStream_t stream);
+                 const double* theta, int m, double* scratch, cudaStream_t stream);
+int64_t gram_algebra_scratch_elems();
 int gram_insert(double* GK, double* GM, int64_t ldg, const double* GsK, const double* GsM, int64_t lds, int m, int wa,
                 cudaStream_t stream);
 int sym_upper(double* GK, double* GM, int64_t ldg, int N, cudaStream_t stream);

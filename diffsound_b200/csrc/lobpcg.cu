@@ -126,7 +126,7 @@ struct Driver {
     double *S[2], *KS[2], *MS[2];
     double *R;
     double *GK, *GM, *Cm, *theta, *eig_scratch, *gram_partial, *gram_partial2, *norm_partial, *norms, *lam_d;
-    double *GKn = nullptr, *GMn = nullptr, *GsK = nullptr, *GsM = nullptr, *strip_partial = nullptr;   // Gram recurrences (rr.cu)
+    double *GKn = nullptr, *GMn = nullptr, *GsK = nullptr, *GsM = nullptr, *strip_partial = nullptr, *alg_scratch = nullptr;   // Gram recurrences (rr.cu)
     int* info_d;
     int cur = 0;
     int64_t spmm_count = 0;
@@ -156,6 +156,7 @@ struct Driver {
         add(64);
         for (int i = 0; i < 4; ++i) add(144 * 144);
         add((size_t)gram_strip_scratch_elems(ws->num_sms));
+        add((size_t)gram_algebra_scratch_elems());
         if (nq) add((size_t)n * nq);
         DS_TRY(ws->arena.reserve(need, st));
         Arena& a = ws->arena;
@@ -185,8 +186,9 @@ struct Driver {
         GKn = a.take<double>(144 * 144); GMn = a.take<double>(144 * 144);
         GsK = a.take<double>(144 * 144); GsM = a.take<double>(144 * 144);
         strip_partial = a.take<double>((size_t)gram_strip_scratch_elems(ws->num_sms));
+        alg_scratch = a.take<double>((size_t)gram_algebra_scratch_elems());
         if (nq) MQ = a.take<double>((size_t)n * nq);
-        DS_REQUIRE(info_d != nullptr && strip_partial != nullptr && (!nq || MQ), "lobpcg: workspace arena exhausted");
+        DS_REQUIRE(info_d != nullptr && strip_partial != nullptr && alg_scratch != nullptr && (!nq || MQ), "lobpcg: workspace arena exhausted");
         for (int i = 0; i < 2; ++i) {   // never multiply uninitialised memory by zero coefficients
             DS_CUDA(cudaMemsetAsync(S[i], 0, 3 * blk * 8, st));
             DS_CUDA(cudaMemsetAsync(KS[i], 0, 3 * blk * 8, st));
@@ -262,13 +264,14 @@ struct Driver {
             DS_CUDA(cudaStreamSynchronize(st));
             return DS_OK;
         };
-        // ||A^(k+1) x|| / ||A^k x|| increases monotonically towards lmax for the SPD pencil; it is sampled after
-        // 8, 12, 16, ... steps and accepted once it moves by less than 1 % between two samples (cap 40 steps): a
-        // fixed 12 steps reached 0.95 lmax on the Kuhn cube but has no guarantee on sliver-rich meshes, and a
-        // Chebyshev interval that ends below lmax amplifies the top of the spectrum
-        double best = 0.0, prev = 0.0;
+        // e_k = max over columns of ||A^(k+1) x|| / ||A^k x|| increases monotonically towards lmax for the SPD pencil.
+        // It is sampled after 4, 8, 12, ... steps.  Accepted: a sample that moved by less than 1 % (x 1.1), or -- the usual
+        // case, 12 steps -- Aitken's extrapolation of the last three samples when it is consistent (between e_k and
+        // 1.5 e_k), which bounds the limit of the geometric tail instead of trusting a fixed step count (a
+        // Chebyshev interval that ends below lmax amplifies the top of the spectrum).  Cap: 40 steps.
+        double best = 0.0, e1 = 0.0, e2 = 0.0;
         for (int it = 0; it < 40; ++it) {
-            const bool sample = it >= 7 && (it - 7) % 4 == 0;
+            const bool sample = (it & 3) == 3;
             if (sample) DS_TRY(norms_of(a, n0));
             // b = a + (-1) (a - 0) + (-1) invD (0 - A a) = invD A a     (Zprev = R = the zero block)
             DS_TRY(spmm32(S32_MODE_CHEB, L.brow, L.rec, L.n_nodes, w, a, zero_r, L.invD, zero_r, b, -1.f, -1.f, L.prof_cls,
@@ -278,10 +281,19 @@ struct Driver {
             L.cols += w;
             if (sample) {
                 DS_TRY(norms_of(a, n1));
-                best = 0.0;
-                for (int c = 0; c < w; ++c) best = std::max(best, std::sqrt(n1[c] / n0[c]));
-                if (prev > 0.0 && best <= 1.01 * prev) break;
-                prev = best;
+                double e3 = 0.0;
+                for (int c = 0; c < w; ++c) e3 = std::max(e3, std::sqrt(n1[c] / n0[c]));
+                best = e3;
+                if (e2 > 0.0 && e3 <= 1.01 * e2) break;
+                if (e1 > 0.0) {
+                    const double d1 = e2 - e1, d2 = e3 - e2;
+                    if (d1 > d2 && d2 > 0.0) {
+                        const double lim = e3 + d2 * d2 / (d1 - d2);          // Aitken: e3 + d2 q / (1 - q), q = d2 / d1
+                        if (lim <= 1.5 * e3) { best = std::max(e3, lim / 1.1 * 1.05); break; }
+                    }
+                }
+                e1 = e2;
+                e2 = e3;
             }
         }
         L.lmax = 1.1 * best;
@@ -422,7 +434,7 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
     cur = 1;
     DS_CUDA(cudaMemcpyAsync(lam_d, theta, m * sizeof(double), cudaMemcpyDeviceToDevice, st));
     // Gram pair of [X' | - | -]: diag(theta), I  (C has no W / P rows yet: the recurrence reduces to exactly that)
-    DS_TRY(gram_algebra(GK, GM, GKn, GMn, 144, Cm, 144, theta, m, st));
+    DS_TRY(gram_algebra(GK, GM, GKn, GMn, 144, Cm, 144, theta, m, alg_scratch, st));
     std::swap(GK, GKn);
     std::swap(GM, GMn);
 
@@ -482,7 +494,7 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
             // (the Rayleigh-Ritz step does not need W M-orthogonal to X; near convergence T R is M-orthogonal to X to
             // O(residual) anyway), so no FP64 copy is gathered
             DS_TRY(spmm_dual_z32(brow, fine.brow, fine.bcolP, fine.perm, fine.chunk_row, spmm32_chunk_count(n_nodes), n_nodes,
-                                 Kval, Mblk, Zres, wpad, KS[cur] + m, ld, MS[cur] + m, ld, st));
+                                 Kval, Mblk, Zres, wpad, KS[cur] + m, ld, MS[cur] + m, ld, st, fine.nnzb));
         } else {
             if (nq) DS_TRY(project_locked(Wb(cur), ld, wpad));
             // ---- W <- W - X (MX^T W)
@@ -537,7 +549,7 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
             DS_TRY(rr_update2_f64(Ain, ld, m, wpad, useP ? 1 : 0, Cm, 144, n, Yout, ld, st));
         }
         // ---- Gram pair of [X' | - | P'] from the small matrices (rows of C at unused slots are zero)
-        DS_TRY(gram_algebra(GK, GM, GKn, GMn, 144, Cm, 144, theta, m, st));
+        DS_TRY(gram_algebra(GK, GM, GKn, GMn, 144, Cm, 144, theta, m, alg_scratch, st));
         std::swap(GK, GKn);
         std::swap(GM, GMn);
         haveP = true;

@@ -175,44 +175,54 @@ struct GramAlg {
     int m;                   // block size; slots [0, m) X, [m, 2m) W, [2m, 3m) P
 };
 
-__global__ void __launch_bounds__(1024)
-k_gram_algebra(const __grid_constant__ GramAlg g) {
+// T[q] = G[q][:, m:3m] C[m:3m, :m]   (N x m per matrix): grid (N / 16, 2), 16 rows of T per CTA
+__global__ void __launch_bounds__(256)
+k_gram_alg_t(const __grid_constant__ GramAlg g, double* __restrict__ Tg) {
     extern __shared__ __align__(16) double sm[];
-    const int m = g.m, N = 3 * m, q = blockIdx.x;
-    double* Cs = sm;                 // [N][m]   C[:, :m]
-    double* T = sm + (size_t)N * m;  // [N][m]   T = G[:, m:] C[m:, :m]
+    const int m = g.m, N = 3 * m, q = blockIdx.y, r0 = 16 * blockIdx.x;
+    double* Cw = sm;                       // [2m][m]   C[m:3m, :m]
+    double* Gr = sm + (size_t)2 * m * m;   // [16][2m]  G[r0 .. r0+16, m:3m]
     const double* __restrict__ G = g.G[q];
-    double* __restrict__ Gn = g.Gn[q];
-    const int tid = threadIdx.x, nt = blockDim.x;
-    for (int t = tid; t < N * m; t += nt) Cs[t] = g.C[(int64_t)(t / m) * g.ldc + (t % m)];
+    for (int t = threadIdx.x; t < 2 * m * m; t += blockDim.x) Cw[t] = g.C[(int64_t)(m + t / m) * g.ldc + (t % m)];
+    for (int t = threadIdx.x; t < 16 * 2 * m; t += blockDim.x)
+        Gr[t] = G[(int64_t)(r0 + t / (2 * m)) * g.ldg + m + (t % (2 * m))];
     __syncthreads();
-    for (int t = tid; t < N * m; t += nt) {
+    for (int t = threadIdx.x; t < 16 * m; t += blockDim.x) {
         const int i = t / m, j = t - i * m;
         double s = 0.0;
-        for (int k = m; k < N; ++k) s = fma(G[(int64_t)i * g.ldg + k], Cs[k * m + j], s);
-        T[t] = s;
+#pragma unroll 8
+        for (int k = 0; k < 2 * m; ++k) s = fma(Gr[i * 2 * m + k], Cw[k * m + j], s);
+        Tg[((size_t)q * N + r0 + i) * m + j] = s;
     }
+}
+
+// Gn: X'X' = diag(theta) | I;  X'P' = C1^T T;  P'P' = C_wp^T T.  grid (m / 8, 2): 8 columns a of C per CTA.
+// Gn must be zero on entry (W rows / columns stay zero until k_gram_insert fills them).
+__global__ void __launch_bounds__(256)
+k_gram_alg_g(const __grid_constant__ GramAlg g, const double* __restrict__ Tg) {
+    extern __shared__ __align__(16) double sm[];
+    const int m = g.m, N = 3 * m, q = blockIdx.y, a0 = 8 * blockIdx.x;
+    double* T = sm;                        // [N][m]
+    double* Ca = sm + (size_t)N * m;       // [N][8]   C[:, a0 .. a0+8]
+    double* __restrict__ Gn = g.Gn[q];
+    for (int t = threadIdx.x; t < N * m; t += blockDim.x) T[t] = Tg[(size_t)q * N * m + t];
+    for (int t = threadIdx.x; t < N * 8; t += blockDim.x) Ca[t] = g.C[(int64_t)(t / 8) * g.ldc + a0 + (t % 8)];
     __syncthreads();
-    for (int t = tid; t < (int)(g.ldg * g.ldg); t += nt) Gn[t] = 0.0;
-    __syncthreads();
-    // X'X' : diag(theta) | I
-    for (int a = tid; a < m; a += nt) Gn[(int64_t)a * g.ldg + a] = q == 0 ? g.theta[a] : 1.0;
-    // X'P' = C1^T T  (all rows),  P'P' = C_wp^T T  (rows m..N)
-    for (int t = tid; t < m * m; t += nt) {
-        const int a = t / m, j = t - a * m;
+    for (int t = threadIdx.x; t < 8 * m; t += blockDim.x) {
+        const int al = t / m, j = t - al * m, a = a0 + al;
         double sx = 0.0, sp = 0.0;
-        for (int i = 0; i < m; ++i) sx = fma(Cs[i * m + a], T[i * m + j], sx);
-        for (int i = m; i < N; ++i) sp = fma(Cs[i * m + a], T[i * m + j], sp);
+#pragma unroll 8
+        for (int i = 0; i < m; ++i) sx = fma(Ca[i * 8 + al], T[i * m + j], sx);
+#pragma unroll 8
+        for (int i = m; i < N; ++i) sp = fma(Ca[i * 8 + al], T[i * m + j], sp);
         sx += sp;
         Gn[(int64_t)a * g.ldg + 2 * m + j] = sx;
         Gn[(int64_t)(2 * m + j) * g.ldg + a] = sx;
-        T[(size_t)N * m + t] = sp;            // P'P' staged, symmetrised below  (space: see smem size)
+        Gn[(int64_t)(2 * m + a) * g.ldg + 2 * m + j] = sp;       // symmetric up to rounding; consumers read the upper triangle
     }
-    __syncthreads();
-    const double* PP = T + (size_t)N * m;
-    for (int t = tid; t < m * m; t += nt) {
-        const int a = t / m, j = t - a * m;
-        Gn[(int64_t)(2 * m + a) * g.ldg + 2 * m + j] = 0.5 * (PP[a * m + j] + PP[j * m + a]);
+    if (threadIdx.x < 8) {
+        const int a = a0 + threadIdx.x;
+        Gn[(int64_t)a * g.ldg + a] = q == 0 ? g.theta[a] : 1.0;
     }
 }
 
@@ -249,21 +259,29 @@ k_sym_upper(double* __restrict__ GK, double* __restrict__ GM, int64_t ldg, int N
     if (i > j) G[(int64_t)i * ldg + j] = G[(int64_t)j * ldg + i];
 }
 
+int64_t gram_algebra_scratch_elems() { return 2 * 144 * 48; }
+
 int gram_algebra(const double* GK, const double* GM, double* GKn, double* GMn, int64_t ldg, const double* C, int64_t ldc,
-                 const double* theta, int m, cudaStream_t stream) {
-    DS_REQUIRE(GK && GM && GKn && GMn && C && theta, "gram_algebra: null argument");
+                 const double* theta, int m, double* scratch, cudaStream_t stream) {
+    DS_REQUIRE(GK && GM && GKn && GMn && C && theta && scratch, "gram_algebra: null argument");
     DS_REQUIRE(m == 16 || m == 32 || m == 48, "gram_algebra: m=%d must be 16, 32 or 48", m);
     DS_REQUIRE(ldg >= 3 * m && ldc >= m && GK != GKn && GM != GMn, "gram_algebra: bad leading dimensions / aliasing");
     GramAlg g;
     g.G[0] = GK; g.G[1] = GM; g.Gn[0] = GKn; g.Gn[1] = GMn; g.C = C; g.theta = theta; g.ldg = ldg; g.ldc = ldc; g.m = m;
-    const size_t smem = ((size_t)2 * 3 * m * m + (size_t)m * m) * sizeof(double);
+    const int N = 3 * m;
+    ProfScope prof(PROF_EIGH, stream);
+    DS_CUDA(cudaMemsetAsync(GKn, 0, sizeof(double) * ldg * N, stream));
+    DS_CUDA(cudaMemsetAsync(GMn, 0, sizeof(double) * ldg * N, stream));
+    const size_t sm1 = ((size_t)2 * m * m + 16 * 2 * m) * sizeof(double), sm2 = ((size_t)N * m + N * 8) * sizeof(double);
     static bool attr = false;
     if (!attr) {
-        DS_CUDA(cudaFuncSetAttribute(k_gram_algebra, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2 * 3 * 48 * 48 + 48 * 48) * sizeof(double))));
+        DS_CUDA(cudaFuncSetAttribute(k_gram_alg_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2 * 48 * 48 + 16 * 96) * sizeof(double))));
+        DS_CUDA(cudaFuncSetAttribute(k_gram_alg_g, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((144 * 48 + 144 * 8) * sizeof(double))));
         attr = true;
     }
-    ProfScope prof(PROF_EIGH, stream);
-    k_gram_algebra<<<2, 1024, smem, stream>>>(g);
+    k_gram_alg_t<<<dim3(N / 16, 2), 256, sm1, stream>>>(g, scratch);
+    DS_LAUNCH_CHECK();
+    k_gram_alg_g<<<dim3(m / 8, 2), 256, sm2, stream>>>(g, scratch);
     DS_LAUNCH_CHECK();
     return DS_OK;
 }
@@ -494,7 +512,9 @@ extern "C" int ds_rr_update2_f64(const double* S, const double* KS, const double
     return rr_update2_f64(A, lda, m, wa, use_p, C, ldc, n, Y, ldy, (cudaStream_t)stream);
 }
 
+extern "C" int64_t ds_gram_algebra_scratch_elems(void) { return gram_algebra_scratch_elems(); }
+
 extern "C" int ds_gram_algebra_f64(const double* GK, const double* GM, double* GKn, double* GMn, int64_t ldg, const double* C,
-                                   int64_t ldc, const double* theta, int m, void* stream) {
-    return gram_algebra(GK, GM, GKn, GMn, ldg, C, ldc, theta, m, (cudaStream_t)stream);
+                                   int64_t ldc, const double* theta, int m, double* scratch, void* stream) {
+    return gram_algebra(GK, GM, GKn, GMn, ldg, C, ldc, theta, m, scratch, (cudaStream_t)stream);
 }

@@ -452,6 +452,12 @@ int spmm_dual(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, const d
     unsigned g = row_blocks(n_nodes);
     int cpl = ncols / 16;
     ProfScope prof(PROF_SPMM, stream);
+    {
+        int32_t nb = 0;      // nnzb is not an argument of this entry point: accounted only while profiling (one 4-byte D2H)
+        if (prof_enabled(PROF_SPMM) && cudaMemcpyAsync(&nb, brow + n_nodes, 4, cudaMemcpyDeviceToHost, stream) == cudaSuccess &&
+            cudaStreamSynchronize(stream) == cudaSuccess)
+            prof_account(PROF_SPMM, (double)nb * 84.0 + (double)n_nodes * 4.0 + 3.0 * n_nodes * ncols * 24.0, 2.0 * (double)nb * 12.0 * ncols);
+    }
     if (chunk_row && nchunks > 0 && cpl <= 3) {
         // ordered sweep, one CTA per chunk (= per SM), all of the SM's 256 KB as L1
         auto go = [&](auto kern) -> int {
@@ -474,11 +480,14 @@ int spmm_dual(const int32_t* brow, const int32_t* bcol, int64_t n_nodes, const d
 
 int spmm_dual_z32(const int32_t* brow, const int32_t* browP, const int32_t* bcolP, const int32_t* perm,
                   const int32_t* chunk_row, int nchunks, int64_t n_nodes, const double* Kval, const double* Mblk,
-                  const float* Z, int ncols, double* YK, int64_t ldyk, double* YM, int64_t ldym, cudaStream_t stream) {
+                  const float* Z, int ncols, double* YK, int64_t ldyk, double* YM, int64_t ldym, cudaStream_t stream,
+                  int64_t nnzb) {
     DS_REQUIRE(ncols > 0 && ncols % 16 == 0 && ncols <= 48, "spmm_dual_z32: ncols=%d must be 16, 32 or 48", ncols);
     DS_REQUIRE(brow && browP && bcolP && chunk_row && nchunks > 0 && Kval && Mblk && Z && YK && YM, "spmm_dual_z32: null argument");
-    (void)n_nodes;
     ProfScope prof(PROF_SPMM, stream);
+    // algorithmic bytes: 9 fp64 K values + 1 fp64 M scalar + 4 B column id per block, row pointers, Z once (fp32), K Z and M Z out
+    prof_account(PROF_SPMM, (double)nnzb * 84.0 + (double)n_nodes * 12.0 + 3.0 * n_nodes * ncols * (4.0 + 16.0),
+                 2.0 * (double)nnzb * 12.0 * ncols);
     auto go = [&](auto kern) -> int {
         static bool carved = false;
         if (!carved) {

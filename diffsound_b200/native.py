@@ -643,7 +643,10 @@ class prof:
             ms, cnt = C.c_double(0), C.c_int64(0)
             _lib.check(lib.ds_prof_read(c, C.byref(ms), C.byref(cnt)), "ds_prof_read")
             if cnt.value:
-                out[lib.ds_prof_class_name(c).decode()] = {"ms": ms.value, "count": cnt.value}
+                by, fl = C.c_double(0), C.c_double(0)
+                _lib.check(lib.ds_prof_read_work(c, C.byref(by), C.byref(fl)), "ds_prof_read_work")
+                out[lib.ds_prof_class_name(c).decode()] = {"ms": ms.value, "count": cnt.value, "bytes": by.value,
+                                                           "flops": fl.value}
         return out
 
 
@@ -682,9 +685,10 @@ def gram_algebra(GK, GM, Cm, theta, m):
     lib = _lib.load()
     assert GK.is_contiguous() and GM.is_contiguous() and Cm.stride(1) == 1
     GKn, GMn = torch.empty_like(GK), torch.empty_like(GM)
+    scratch = torch.empty(lib.ds_gram_algebra_scratch_elems(), dtype=torch.float64, device=GK.device)
     with torch.cuda.device(GK.device):
         _lib.check(lib.ds_gram_algebra_f64(_p(GK), _p(GM), _p(GKn), _p(GMn), GK.shape[1], C.c_void_p(Cm.data_ptr()),
-                                           Cm.stride(0), _p(theta), int(m), _stream()), "ds_gram_algebra_f64")
+                                           Cm.stride(0), _p(theta), int(m), _p(scratch), _stream()), "ds_gram_algebra_f64")
     return GKn, GMn
 
 

@@ -384,8 +384,9 @@ int ds_gram_strip_f64(const double* KW, const double* MW, int64_t ldw, int wa, c
 int ds_rr_update2_f64(const double* S, const double* KS, const double* MS, int64_t lda, int m, int wa, int use_p,
                       const double* C, int64_t ldc, int64_t n, double* S_out, double* KS_out, double* MS_out, int64_t ldy,
                       void* stream);
+int64_t ds_gram_algebra_scratch_elems(void);
 int ds_gram_algebra_f64(const double* GK, const double* GM, double* GKn, double* GMn, int64_t ldg, const double* C,
-                        int64_t ldc, const double* theta, int m, void* stream);
+                        int64_t ldc, const double* theta, int m, double* scratch, void* stream);
 int ds_fp64_peak(int mode, int iters, int ctas_per_sm, double* scratch, double* tflops_host, void* stream);
 
 #ifdef __cplusplus
