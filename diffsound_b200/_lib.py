@@ -102,6 +102,12 @@ SIGNATURES = {
     "ds_gram_algebra_scratch_elems": (i64, []),
     "ds_gram_algebra_f64": (cint, [f64p, f64p, f64p, f64p, i64, f64p, i64, f64p, cint, f64p, ptr]),
     "ds_fp64_peak": (cint, [cint, cint, cint, f64p, C.POINTER(C.c_double), ptr]),
+    "ds_mtet_count": (cint, [ptr, f32p, dbl, i64p, i64, i64, C.POINTER(C.c_int64), ptr]),
+    "ds_mtet_fill": (cint, [ptr, i64p, i64p, i64p, i64p, ptr]),
+    "ds_compact_ids_count": (cint, [ptr, i64p, i64, i64, C.POINTER(C.c_int64), ptr]),
+    "ds_compact_ids_fill": (cint, [ptr, i64p, i64p, i64p, ptr]),
+    "ds_tet_components_count": (cint, [ptr, i64p, i64, i64, i32p, C.POINTER(C.c_int64), ptr]),
+    "ds_tet_components_fill": (cint, [ptr, i64p, i64p, i64p, ptr]),
     "ds_prof_enable": (cint, [cint]),
     "ds_prof_enable_classes": (cint, [C.c_uint32]),
     "ds_prof_reset": (cint, []),

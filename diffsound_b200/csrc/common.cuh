@@ -106,4 +106,7 @@ struct ds_workspace {
     int64_t nnzb = 0;
     int num_sms = 0;
     ds_workspace* child = nullptr;   // arena of the nested coarse eigen-solve (created on first use)
+    // state carried between the *_count and *_fill halves of the marching-tets / compaction / component calls (mtet.cu)
+    void* mt_ptr[16] = {};
+    int64_t mt_val[16] = {};
 };

@@ -699,3 +699,56 @@ def fp64_peak(mode, iters=4096, ctas_per_sm=2):
     out = C.c_double(0)
     _lib.check(lib.ds_fp64_peak(int(mode), int(iters), int(ctas_per_sm), _p(scratch), C.byref(out), _stream()), "ds_fp64_peak")
     return out.value
+
+
+def marching_tets(sdf, thickness, tets):
+    """Topology of the hollow-shell tet mesh (ds_mtet_*): returns (interp_v (E, 2) int64, tets_out (Tn, 4) int64 over ids in
+    [0, n_verts + E), faces (Nf, 3) int64 over edge-vertex ids)."""
+    lib = _lib.load()
+    assert sdf.dtype == torch.float32 and sdf.is_contiguous() and tets.dtype == torch.int64 and tets.is_contiguous()
+    dev = sdf.device
+    ws = workspace(dev)
+    F, nv = tets.shape[0], sdf.shape[0]
+    counts = (C.c_int64 * 7)()
+    with torch.cuda.device(dev):
+        _lib.check(lib.ds_mtet_count(ws.handle, _p(sdf), float(thickness), _p(tets), F, nv, counts, _stream()), "ds_mtet_count")
+        n_int, n1, n3, n_in, n_tri = int(counts[2]), int(counts[3]), int(counts[4]), int(counts[5]), int(counts[6])
+        interp_v = torch.empty(n_int, 2, dtype=torch.int64, device=dev)
+        tets_out = torch.empty(n1 + 3 * n3 + n_in, 4, dtype=torch.int64, device=dev)
+        faces = torch.empty(n_tri, 3, dtype=torch.int64, device=dev)
+        _lib.check(lib.ds_mtet_fill(ws.handle, _p(tets), _p(interp_v), _p(tets_out), _p(faces), _stream()), "ds_mtet_fill")
+    return interp_v, tets_out, faces
+
+
+def compact_ids(ids, id_range):
+    """(unique ascending, inverse) of an int64 id array with values in [0, id_range) (ds_compact_ids_*)."""
+    lib = _lib.load()
+    flat = ids.reshape(-1).contiguous()
+    dev = ids.device
+    ws = workspace(dev)
+    nu = C.c_int64(0)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ds_compact_ids_count(ws.handle, _p(flat), flat.numel(), int(id_range), C.byref(nu), _stream()),
+                   "ds_compact_ids_count")
+        uniq = torch.empty(int(nu.value), dtype=torch.int64, device=dev)
+        inv = torch.empty_like(flat)
+        _lib.check(lib.ds_compact_ids_fill(ws.handle, _p(flat), _p(uniq), _p(inv), _stream()), "ds_compact_ids_fill")
+    return uniq, inv.reshape(ids.shape)
+
+
+def largest_tet_component(tets, n_verts):
+    """Connected components of a tet mesh on the device (ds_tet_components_*): returns (n_components, kept_verts (old ids,
+    ascending) int64, tets of the largest component renumbered (order kept) int64, labels int32 (n_verts,))."""
+    lib = _lib.load()
+    assert tets.dtype == torch.int64 and tets.is_contiguous()
+    dev = tets.device
+    ws = workspace(dev)
+    labels = torch.empty(n_verts, dtype=torch.int32, device=dev)
+    counts = (C.c_int64 * 3)()
+    with torch.cuda.device(dev):
+        _lib.check(lib.ds_tet_components_count(ws.handle, _p(tets), tets.shape[0], int(n_verts), _p(labels), counts, _stream()),
+                   "ds_tet_components_count")
+        kept = torch.empty(int(counts[1]), dtype=torch.int64, device=dev)
+        tout = torch.empty(int(counts[2]), 4, dtype=torch.int64, device=dev)
+        _lib.check(lib.ds_tet_components_fill(ws.handle, _p(tets), _p(kept), _p(tout), _stream()), "ds_tet_components_fill")
+    return int(counts[0]), kept, tout, labels

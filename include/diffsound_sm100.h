@@ -353,6 +353,30 @@ int ds_mss_loss_bwd(const float* x_pred, const float* x_true, int64_t B, int64_t
                     double alpha, double eps, const double* loss, double upstream, float* scratch, float* gx,
                     int accumulate, void* stream);
 
+/* ---- marching tetrahedra -> tet mesh of a hollow shell, compaction, largest connected component ----------------
+ * Replaces DMTet.__call__ and DMTetGeometry.get_largest_connected_component (src/dmtet/geometry/dmtet_thickness.py:99-200,
+ * :254-285; the same code in dmtet_interpolate.py:115-205,265-296 and dmtet_geometry.py:115-267,411-443): torch.unique
+ * sorts + mask gathers + a GPU -> CPU round trip through scipy.sparse.csgraph.connected_components.  Output order and
+ * numbering are the reference's bit for bit (they define the sparsity pattern downstream); see csrc/mtet.cu.
+ * sdf: fp32 [n_verts]; tets: int64 [F x 4]; a vertex is inside the shell when 0 < sdf <= (float)thickness.
+ * ds_mtet_count -> counts_host[7] = {valid tets, unique edges, crossing edges, one-tet tets, three-tet tets, inner tets,
+ * surface triangles}; ds_mtet_fill -> interp_v int64 [crossing x 2] (end points a < b of every crossing edge, ascending;
+ * edge e becomes vertex n_verts + e), tets_out int64 [(one + 3 three + inner) x 4] over ids in [0, n_verts + crossing),
+ * faces_out int64 [triangles x 3] over edge-vertex ids (may be NULL).
+ * ds_compact_ids_*: ascending unique values of ids[M] (all in [0, R)) and each id's rank among them
+ * (torch.unique(return_inverse=True) of dmtet_thickness.py:195-199).
+ * ds_tet_components_*: labels int32 [n_verts] = smallest vertex id of the vertex's component; counts_host[3] = {components,
+ * vertices, tets of the largest component (ties: the component with the smallest vertex id, the one SciPy labels
+ * first)}; fill -> kept_verts int64 [vertices] (old ids, ascending), tets_out int64 [tets x 4] renumbered, order kept. */
+int ds_mtet_count(ds_workspace* ws, const float* sdf, double thickness, const int64_t* tets, int64_t F, int64_t n_verts,
+                  int64_t* counts_host, void* stream);
+int ds_mtet_fill(ds_workspace* ws, const int64_t* tets, int64_t* interp_v, int64_t* tets_out, int64_t* faces_out, void* stream);
+int ds_compact_ids_count(ds_workspace* ws, const int64_t* ids, int64_t M, int64_t R, int64_t* n_unique_host, void* stream);
+int ds_compact_ids_fill(ds_workspace* ws, const int64_t* ids, int64_t* unique_out, int64_t* inverse_out, void* stream);
+int ds_tet_components_count(ds_workspace* ws, const int64_t* tets, int64_t T, int64_t n_verts, int32_t* labels,
+                            int64_t* counts_host, void* stream);
+int ds_tet_components_fill(ds_workspace* ws, const int64_t* tets, int64_t* kept_verts, int64_t* tets_out, void* stream);
+
 /* ---- device-side timing per kernel class ---------------------------------------
  * Replaces the reference's opt-in torch.profiler hook of lobpcg (src/lobpcg/_lobpcg.py:357-369)
  * and the TICK/TOCK macros (src/include/macro.h:31-44): CUDA events around every launch site,
