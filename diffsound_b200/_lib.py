@@ -26,7 +26,7 @@ class LobpcgOpts(C.Structure):
                 ("sigma", C.c_double), ("cheb_ratio", C.c_double), ("n_rigid", C.c_int), ("verbose", C.c_int),
                 ("smooth_steps", C.c_int), ("coarse_degree", C.c_int), ("smooth_ratio", C.c_double),
                 ("coarse_ratio", C.c_double), ("nested", C.c_int), ("nested_tol", C.c_double),
-                ("nested_degree", C.c_int), ("coords", C.c_void_p), ("locked", C.c_void_p), ("n_locked", C.c_int), ("ortho_w", C.c_int)]
+                ("nested_degree", C.c_int), ("coords", C.c_void_p), ("locked", C.c_void_p), ("n_locked", C.c_int), ("precond_fp64", C.c_int), ("ortho_w", C.c_int)]
 
 
 class PmgLevel(C.Structure):

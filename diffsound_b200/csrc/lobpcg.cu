@@ -21,6 +21,7 @@
 #include "kernels.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace ds {
@@ -83,6 +84,28 @@ __global__ void k_colnorm2(const double* __restrict__ V, int64_t ld, int w, int6
     }
 }
 
+// partial[cta][s] = sum over rows of R[row, idx[s]] * W[row, s]  (s < count): r_j^T T r_j, the preconditioned (energy) norm
+// of the residual of active column idx[s], whose search direction W[:, s] = T r_j has just been computed
+__global__ void k_coldot_rw(const double* __restrict__ R, int64_t ldr, const __grid_constant__ ColIdx idx, int count,
+                            const double* __restrict__ W, int64_t ldw, int64_t n, double* __restrict__ partial) {
+    extern __shared__ double sh[];
+    const int w = count, rpp = blockDim.x / w;
+    const int c = threadIdx.x % w, rr = threadIdx.x / w;
+    double s = 0.0;
+    if (rr < rpp) {
+        const int rc = idx.v[c];
+        for (int64_t row = (int64_t)blockIdx.x * rpp + rr; row < n; row += (int64_t)gridDim.x * rpp)
+            s = fma(R[row * ldr + rc], W[row * ldw + c], s);
+        sh[rr * w + c] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < w) {
+        double t = 0.0;
+        for (int r2 = 0; r2 < rpp; ++r2) t += sh[r2 * w + threadIdx.x];
+        partial[(size_t)blockIdx.x * w + threadIdx.x] = t;
+    }
+}
+
 // dst[:, s] = src[:, idx[s]] for s < count, zero for count <= s < width
 __global__ void k_gather_cols(const double* __restrict__ src, int64_t lds, const __grid_constant__ ColIdx idx,
                               int count, int width, int64_t n, double* __restrict__ dst, int64_t ldd) {
@@ -103,6 +126,59 @@ __global__ void k_fill_random(double* __restrict__ V, int64_t count, uint64_t se
     V[t] = (double)(z >> 11) * (2.0 / 9007199254740992.0) - 1.0;
 }
 
+// ---- FP64 fall-back preconditioner (ds_lobpcg_opts.precond_fp64): block-Jacobi Chebyshev on K in double precision.
+// The FP32 cycle loses the smooth part of a residual whose stiff components are >= 1e7 times larger (sliver elements of
+// marching-tets meshes: r = K x - lam M x amplifies the rounding noise of x along modes with lam_stiff / lam ~ 1e10);
+// the same polynomial in FP64 does not.  One SpMM (k_spmm) + one update kernel per step.
+__global__ void k_invd64(const int32_t* __restrict__ brow, const int32_t* __restrict__ bcol, int64_t n_nodes,
+                         const double* __restrict__ Kval, double* __restrict__ invD) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const int64_t b0 = brow[i];
+    const int deg = (int)(brow[i + 1] - b0);
+    int p = 0;
+    while (p < deg && bcol[b0 + p] != (int32_t)i) ++p;
+    double k[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if (p < deg)
+        for (int c = 0; c < 3; ++c)
+            for (int d = 0; d < 3; ++d) k[3 * c + d] = Kval[9 * b0 + (int64_t)c * 3 * deg + 3 * p + d];
+    const double c00 = k[4] * k[8] - k[5] * k[7], c01 = k[5] * k[6] - k[3] * k[8], c02 = k[3] * k[7] - k[4] * k[6];
+    const double id = 1.0 / (k[0] * c00 + k[1] * c01 + k[2] * c02);
+    double* o = invD + 9 * i;
+    o[0] = c00 * id; o[1] = (k[2] * k[7] - k[1] * k[8]) * id; o[2] = (k[1] * k[5] - k[2] * k[4]) * id;
+    o[3] = c01 * id; o[4] = (k[0] * k[8] - k[2] * k[6]) * id; o[5] = (k[2] * k[3] - k[0] * k[5]) * id;
+    o[6] = c02 * id; o[7] = (k[1] * k[6] - k[0] * k[7]) * id; o[8] = (k[0] * k[4] - k[1] * k[3]) * id;
+}
+
+// Znew = Z + ab (Z - Zp) + cc invD Res   (per node: 3 rows x w columns; Zp may alias Znew; Z == NULL: Znew = cc invD Res)
+__global__ void k_cheb64_update(const double* __restrict__ invD, const double* __restrict__ Res, int64_t ldr,
+                                const double* __restrict__ Z, const double* Zp, double* Znew, int64_t ldz, int64_t n_nodes,
+                                int w, double ab, double cc) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_nodes * w) return;
+    const int64_t i = t / w;
+    const int c = (int)(t - i * w);
+    const double* d = invD + 9 * i;
+    const double r0 = Res[(3 * i) * ldr + c], r1 = Res[(3 * i + 1) * ldr + c], r2 = Res[(3 * i + 2) * ldr + c];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const double dr = d[3 * q] * r0 + d[3 * q + 1] * r1 + d[3 * q + 2] * r2;
+        const int64_t o = (3 * i + q) * ldz + c;
+        double v = cc * dr;
+        if (Z) { const double z = Z[o]; v += z + ab * (z - Zp[o]); }
+        Znew[o] = v;
+    }
+}
+
+__global__ void k_gather_cols64(const double* __restrict__ src, int64_t lds, const __grid_constant__ ColIdx idx, int count,
+                                int width, int64_t n, double* __restrict__ dst) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n * width) return;
+    const int64_t row = t / width;
+    const int s = (int)(t - row * width);
+    dst[t] = s < count ? src[row * lds + idx.v[s]] : 0.0;
+}
+
 struct Driver {
     ds_workspace* ws;
     cudaStream_t st;
@@ -117,6 +193,7 @@ struct Driver {
     Level32 fine, coarse;
     float *R32, *Za, *Zb, *RC32, *ZCa, *ZCb;
     double *Xc = nullptr, *lamc = nullptr, *resc = nullptr;    // nested coarse eigen-solve
+    double *invD64 = nullptr, *R64 = nullptr, *Z64a = nullptr, *Z64b = nullptr, *RES64 = nullptr;   // FP64 preconditioner
     const double* Q = nullptr;   // locked (already converged, M-orthonormal) eigenvectors, n x nq, ld = nq
     int nq = 0;
     double* MQ = nullptr;        // M Q
@@ -158,6 +235,7 @@ struct Driver {
         add((size_t)gram_strip_scratch_elems(ws->num_sms));
         add((size_t)gram_algebra_scratch_elems());
         if (nq) add((size_t)n * nq);
+        if (o.precond_fp64) { add((size_t)n_nodes * 9); for (int i = 0; i < 4; ++i) add(blk); }
         DS_TRY(ws->arena.reserve(need, st));
         Arena& a = ws->arena;
         for (int i = 0; i < 2; ++i) {
@@ -188,6 +266,11 @@ struct Driver {
         strip_partial = a.take<double>((size_t)gram_strip_scratch_elems(ws->num_sms));
         alg_scratch = a.take<double>((size_t)gram_algebra_scratch_elems());
         if (nq) MQ = a.take<double>((size_t)n * nq);
+        if (o.precond_fp64) {
+            invD64 = a.take<double>((size_t)n_nodes * 9);
+            R64 = a.take<double>(blk); Z64a = a.take<double>(blk); Z64b = a.take<double>(blk); RES64 = a.take<double>(blk);
+            DS_REQUIRE(RES64 != nullptr, "lobpcg: workspace arena exhausted");
+        }
         DS_REQUIRE(info_d != nullptr && strip_partial != nullptr && alg_scratch != nullptr && (!nq || MQ), "lobpcg: workspace arena exhausted");
         for (int i = 0; i < 2; ++i) {   // never multiply uninitialised memory by zero coefficients
             DS_CUDA(cudaMemsetAsync(S[i], 0, 3 * blk * 8, st));
@@ -325,6 +408,30 @@ struct Driver {
         return DS_OK;
     }
 
+    // Wout (n x w, ld) = p(invD K) invD R64: `degree` Chebyshev steps on [lmax / ratio, lmax] in FP64, from zero
+    int apply_precond64(int w, int degree, double ratio, double lmax, double* Wout, int64_t ldw) {
+        ProfScope prof(PROF_CHEB, st);
+        const double lmin = lmax / ratio, theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sig = theta / delta;
+        double rho = 1.0 / sig;
+        const unsigned blocks = (unsigned)ceil_div(n_nodes * w, 256);
+        double *zc = Z64a, *zp = Z64b;
+        k_cheb64_update<<<blocks, 256, 0, st>>>(invD64, R64, w, nullptr, nullptr, zc, w, n_nodes, w, 0.0, 1.0 / theta);
+        DS_LAUNCH_CHECK();
+        DS_CUDA(cudaMemsetAsync(zp, 0, sizeof(double) * (size_t)n * w, st));
+        for (int k = 1; k < degree; ++k) {
+            const double rho_new = 1.0 / (2.0 * sig - rho);
+            // RES = R - K zc
+            DS_TRY(spmm_km(brow, bcol, n_nodes, Kval, nullptr, 0.0, zc, w, w, -1.0, 1.0, R64, w, RES64, w, st));
+            spmm_count++;
+            k_cheb64_update<<<blocks, 256, 0, st>>>(invD64, RES64, w, zc, zp, zp, w, n_nodes, w, rho_new * rho, 2.0 * rho_new / delta);
+            DS_LAUNCH_CHECK();
+            std::swap(zc, zp);
+            rho = rho_new;
+        }
+        DS_CUDA(cudaMemcpy2DAsync(Wout, ldw * 8, zc, (size_t)w * 8, (size_t)w * 8, n, cudaMemcpyDeviceToDevice, st));
+        return DS_OK;
+    }
+
     int run(double* X, double* lambda_out, double* resid_out, int64_t* stats);
 
     // Nested iteration: lowest pairs of the P1 problem (same driver, one-level Chebyshev preconditioner,
@@ -376,6 +483,10 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
     const int nev = o.nev;
     int nr = o.n_rigid < 0 ? 0 : o.n_rigid;
     DS_TRY(alloc());
+    if (o.precond_fp64) {
+        k_invd64<<<(unsigned)ceil_div(n_nodes, 256), 256, 0, st>>>(brow, bcol, n_nodes, Kval, invD64);
+        DS_LAUNCH_CHECK();
+    }
     if (Xc && !nq) DS_TRY(nested_start(X));
     DS_TRY(estimate_lmax(fine, Za, Zb, R32));
     if (cl) DS_TRY(estimate_lmax(coarse, ZCa, ZCb, RC32));
@@ -442,8 +553,11 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
     std::vector<int> act;
     bool haveP = false;                // the P slots of buffer `cur` hold the previous step's directions (slot j <-> X column j)
     int it = 0, nconv = 0, status = 1, since_refresh = 0;
-    const int REFRESH = 8;
-    const bool z32 = fine.bcolP != nullptr && nq == 0 && !o.ortho_w;   // W = fp32 preconditioner output, unmodified
+    int REFRESH = 8;
+    if (const char* e = getenv("DS_LOBPCG_REFRESH")) REFRESH = atoi(e);              // diagnostics only
+    if (const char* e = getenv("DS_LOBPCG_ORTHO_W")) o.ortho_w = atoi(e);
+    if (const char* e = getenv("DS_LOBPCG_VERBOSE")) o.verbose = atoi(e);
+    const bool z32 = fine.bcolP != nullptr && nq == 0 && !o.ortho_w && !o.precond_fp64;   // W = fp32 preconditioner output, unmodified
     const int res_threads = (1024 / m) * m;
     const size_t res_smem = (size_t)(res_threads / m) * 2 * m * sizeof(double);
     for (it = 0; it <= o.maxit; ++it) {
@@ -485,10 +599,36 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
         ColIdx ci;
         for (int s = 0; s < 128; ++s) ci.v[s] = (short)(s < na ? act[s] : 0);
         // ---- W = T(R[:, act])
-        DS_TRY(gather_cols_f32(R, m, ci, na, wpad, n, R32, st, fine.perm));
         float* Zres = nullptr;
-        DS_TRY(apply_precond(wpad, &Zres));
-        DS_TRY(widen_f32(Zres, wpad, n, Wb(cur), ld, st, fine.perm));
+        if (o.precond_fp64) {
+            k_gather_cols64<<<(unsigned)ceil_div(n * wpad, 256), 256, 0, st>>>(R, m, ci, na, wpad, n, R64);
+            DS_LAUNCH_CHECK();
+            const int deg64 = o.cheb_degree > 0 ? o.cheb_degree : 16;
+            DS_TRY(apply_precond64(wpad, deg64, o.cheb_ratio > 1.0 ? o.cheb_ratio : 0.4 * deg64 * deg64, 1.25 * fine.lmax / 1.1,
+                                   Wb(cur), ld));
+        } else {
+            DS_TRY(gather_cols_f32(R, m, ci, na, wpad, n, R32, st, fine.perm));
+            DS_TRY(apply_precond(wpad, &Zres));
+            DS_TRY(widen_f32(Zres, wpad, n, Wb(cur), ld, st, fine.perm));
+        }
+        if (o.verbose && !o.precond_fp64) {          // diagnostics: energy norm of the residuals, r_j^T T r_j / lambda_j
+            const int threads = (1024 / na) * na;
+            k_coldot_rw<<<norm_ctas, threads, (size_t)(threads / na) * na * sizeof(double), st>>>(R, m, ci, na, Wb(cur), ld, n, norm_partial);
+            DS_LAUNCH_CHECK();
+            k_colsum_reduce<<<1, 128, 0, st>>>(norm_partial, norm_ctas, na, norms);
+            DS_LAUNCH_CHECK();
+            std::vector<double> en(na);
+            DS_CUDA(cudaMemcpyAsync(en.data(), norms, na * sizeof(double), cudaMemcpyDeviceToHost, st));
+            DS_CUDA(cudaStreamSynchronize(st));
+            double worst = 0.0, worst_rel = 0.0;
+            for (int s2 = 0; s2 < na; ++s2) {
+                const int j = act[s2];
+                if (j < nr || j >= nev) continue;
+                const double e = en[s2] / std::fabs(lam[j]);
+                if (e > worst) { worst = e; worst_rel = rel[j]; }
+            }
+            fprintf(stderr, "[ds_lobpcg]        max energy residual r^T T r / lam = %.3e (its 2-norm rel res %.3e)\n", worst, worst_rel);
+        }
         if (z32) {
             // K W, M W straight from the fp32 block in the preconditioner's numbering: W is used as it comes out of T
             // (the Rayleigh-Ritz step does not need W M-orthogonal to X; near convergence T R is M-orthogonal to X to

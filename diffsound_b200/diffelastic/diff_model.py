@@ -216,8 +216,16 @@ class DiffSoundObj:
     smooth_ratio = 8.0      # ... damping the upper [lmax / ratio, lmax] of the spectrum
     coarse_degree = 0       # Chebyshev steps of the P1 coarse solve (0: automatic, ~ n_coarse^(1/3) / 1.2)
     coarse_ratio = 0.0      # 0: automatic, 0.4 * degree^2
+    cheb_degree = 0         # one-level Chebyshev preconditioner (linear meshes): polynomial degree, 0 = automatic
     morton = True           # the FP32 preconditioner keeps its operator in a Morton node numbering (SpMM locality)
     eig_maxit = 400
+    # Sliver elements (marching-tets meshes) put stiff components into the residuals that exceed their smooth part by more than
+    # FP32 resolves; the FP32 cycle then stalls.  Policy: meshes whose worst element is `sliver_ratio`
+    # times flatter than the median go straight to the FP64 Chebyshev preconditioner (ds_lobpcg_opts.precond_fp64); others try
+    # the FP32 cycle for at most `eig_fast_maxit` iterations and fall back to FP64 from the block reached so far.
+    fp64_fallback = True
+    eig_fast_maxit = 80
+    sliver_ratio = 2e-3
 
     def __init__(self, vertices=None, tets=None, mode_num=16, mat=MatSet.Ceramic, order=1, mat_model=FixedLinear,
                  task=None, mesh_dir=None):
@@ -360,6 +368,21 @@ class DiffSoundObj:
             X[2::3, 5], X[0::3, 5] = -p[:, 0], p[:, 2]
         return X, False
 
+    def _has_slivers(self):
+        """True when the flattest element of the mesh (smallest height over longest edge, from the corner nodes) is
+        `sliver_ratio` times flatter than the median element."""
+        if "_sliver" not in self.__dict__:
+            with torch.no_grad():
+                t = self.tetmesh.tets
+                c = t[:, [0, 2, 4, 9]] if self.tetmesh.order == 2 else t
+                p = self.tetmesh.vertices.detach()[c].double()
+                e = p[:, [1, 2, 3, 2, 3, 3]] - p[:, [0, 0, 0, 1, 1, 2]]
+                lmax = e.norm(dim=2).max(dim=1).values
+                vol = torch.einsum("ij,ij->i", e[:, 0], torch.cross(e[:, 1], e[:, 2], dim=1)).abs() / 6
+                q = vol / lmax ** 3
+                self._sliver = bool(q.min() < self.sliver_ratio * q.median())
+        return self._sliver
+
     #: pairs one eigensolver call has to converge at most (block 48 = 40 wanted + 8 guard columns); larger
     #: requests (geometry_train.py:147: mode_num = 64) are solved in batches with the converged vectors locked
     max_batch = 40
@@ -379,7 +402,7 @@ class DiffSoundObj:
         pat = self.deform.pattern
         if pat.n < 3 * 16 or pat.n < need + 16:
             raise ValueError(f"mesh too small for {k} modes (n={pat.n})")
-        deg = int(min(40, max(8, round(pat.n ** (1.0 / 3.0) / 3.0))))
+        deg = int(self.cheb_degree) or int(min(40, max(8, round(pat.n ** (1.0 / 3.0) / 3.0))))
         kw = {}
         coarse = self.deform.coarse if self.two_level else None
         if coarse is not None and 3 * coarse.n_nodes >= 3 * 48:
@@ -411,10 +434,27 @@ class DiffSoundObj:
                 locked[:, :done] = torch.cat(found_X, dim=1)
             if kw:
                 kw["nested"] = self.nested_start and not is_warm and batch == 0
-            lam, res, stats = native.lobpcg(pat, self._Kval, self._Mblk, X, nev=want, tol=self.eig_tol,
-                                            maxit=self.eig_maxit, cheb_degree=deg, cheb_ratio=0.4 * deg * deg,
-                                            n_rigid=6 if batch == 0 else 0,
-                                            coords=self._verts32 if self.morton else None, locked=locked, **kw)
+            common = dict(nev=want, tol=self.eig_tol, n_rigid=6 if batch == 0 else 0,
+                          coords=self._verts32 if self.morton else None, locked=locked)
+            stats = None
+            if not (self.fp64_fallback and self._has_slivers()):
+                try:
+                    lam, res, stats = native.lobpcg(pat, self._Kval, self._Mblk, X, cheb_degree=deg, cheb_ratio=0.4 * deg * deg,
+                                                    maxit=min(self.eig_maxit, self.eig_fast_maxit) if self.fp64_fallback
+                                                    else self.eig_maxit, **common, **kw)
+                except RuntimeError:
+                    if not self.fp64_fallback:
+                        raise
+                    stats = None
+                if stats is not None and stats["status"] != 0 and self.fp64_fallback:
+                    fast_stats, stats = stats, None
+                    if not bool(torch.isfinite(X).all()):
+                        X, _ = self._start_block(m, batch)
+            if stats is None:
+                deg64 = int(self.cheb_degree) or int(min(40, max(12, round(pat.n ** (1.0 / 3.0) / 1.5))))
+                lam, res, stats = native.lobpcg(pat, self._Kval, self._Mblk, X, cheb_degree=deg64, cheb_ratio=0.4 * deg64 * deg64,
+                                                maxit=self.eig_maxit, precond_fp64=True, **common)
+                stats["precond"] = "fp64"
             if stats["status"] != 0:
                 raise RuntimeError(f"eigensolver did not converge (batch {batch}): {stats}, "
                                    f"max residual {float(res[:want].max()):.3e}")

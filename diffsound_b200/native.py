@@ -411,7 +411,7 @@ def pmg_prolong_add32(coarse, zc, z):
 
 def lobpcg(pattern, Kval, Mblk, X, nev, tol=1e-4, maxit=200, cheb_degree=8, sigma=0.0, cheb_ratio=30.0, n_rigid=6,
            verbose=0, coarse=None, smooth_steps=3, smooth_ratio=8.0, coarse_degree=20, coarse_ratio=160.0, nested=True,
-           nested_tol=3e-2, nested_degree=0, coords=None, locked=None, ortho_w=False):
+           nested_tol=3e-2, nested_degree=0, coords=None, locked=None, ortho_w=False, precond_fp64=False):
     """Lowest `nev` pairs of K u = lam M u from the start block X (n, m) fp64 (overwritten with the
     M-orthonormal Ritz vectors).  `coarse`: a CoarseLevel with assembled Kval -> two-level
     preconditioner.  `locked`: (n, q) fp64 contiguous, q a multiple of 16 -- M-orthonormal eigenvectors
@@ -429,7 +429,7 @@ def lobpcg(pattern, Kval, Mblk, X, nev, tol=1e-4, maxit=200, cheb_degree=8, sigm
                            smooth_ratio=float(smooth_ratio), coarse_ratio=float(coarse_ratio),
                            nested=int(bool(nested) and coarse is not None), nested_tol=float(nested_tol),
                            nested_degree=int(nested_degree), coords=None, locked=None, n_locked=0,
-                           ortho_w=int(bool(ortho_w)))
+                           ortho_w=int(bool(ortho_w)), precond_fp64=int(bool(precond_fp64)))
     if locked is not None:
         assert locked.dtype == torch.float64 and locked.is_contiguous() and locked.shape[0] == n
         assert locked.shape[1] % 16 == 0 and locked.is_cuda

@@ -179,6 +179,10 @@ typedef struct ds_lobpcg_opts {
                            deflation), so this call returns the NEXT lowest pairs: how DiffSoundObj solves
                            mode_num + 6 > 44 pairs (geometry_train.py:147 asks for 64) in batches of one block */
     int n_locked;       /* columns of `locked`, a multiple of 16, <= 192 (pad with zero columns) */
+    int precond_fp64;   /* != 0: the preconditioner is a block-Jacobi Chebyshev polynomial of degree cheb_degree on K evaluated in
+                           FP64 (one level, no coarse correction).  Robust fall-back for meshes with sliver elements
+                           (marching-tets output), where a residual's stiff components exceed its smooth part by more than
+                           the 2^24 an FP32 cycle resolves.  0 (default): the FP32 cycle */
     int ortho_w;        /* != 0: M-orthogonalise the new search block W against X in FP64 before K W / M W are formed
                            (round-1 behaviour; lobpcg/_lobpcg.py 'ortho').  0 (default): W is the fp32 preconditioner
                            output as is and K W, M W are formed from it directly (k_spmm_dual_z32) */

@@ -123,3 +123,22 @@ def test_thickness_candidates_on_grid64_are_consistent():
         th = coef * float(geo.marching_tets.max_thickness)
         shell = 4 / 3 * np.pi * (0.6 ** 3 - (0.6 - th) ** 3)
         assert abs(float(vol.sum()) - shell) <= 0.02 * shell
+
+
+def test_sliver_mesh_eigenvalues_match_arpack():
+    """Marching-tets output has sliver elements (sigma_min / sigma_max down to 3e-3 here): the solver must detect them, use
+    the FP64 preconditioner and still meet the 1e-6 eigenvalue bar against SciPy ARPACK on the oracle's K, M."""
+    from oracle import modal_oracle as mo
+    from diffsound_b200.diffelastic.diff_model import DiffSoundObj
+    from diffsound_b200.diffelastic.material_model import MatSet
+    g = golden("marching_tets")
+    v, t = torch.tensor(g["g32_sphere_lcc_verts"]), torch.tensor(g["g32_sphere_lcc_tets"])
+    rho, E, nu = MatSet.Steel[:3]
+    K, M = mo.assemble(v, t, 1, E, nu, rho)
+    lam, _, _, _ = mo.eig_arpack(K, M, 16)
+    obj = DiffSoundObj(v.to(DEV), t.to(DEV), mode_num=16, order=1, mat=MatSet.Steel)
+    assert obj._has_slivers()
+    obj.eigen_decomposition()
+    assert obj.eig_stats.get("precond") == "fp64"
+    got = obj.eigenvalues.cpu().numpy()
+    assert (np.abs(got - lam) / lam).max() <= 1e-6
