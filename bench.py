@@ -236,6 +236,109 @@ def verify_solution(obj, leaf, solve, native, torch):
             "iterations_tol1e-5": it5, "iterations_tol1e-9": it9}
 
 
+def run_rowpart(args):
+    """ONE mesh on N GPUs ("scaling": "strong"): assembly replicated on every rank, LOBPCG on row slabs
+    (diffsound_b200/parallel/rowpart_lobpcg.py: halo rows of the FP32 smoother read over NVLink inside the SpMM kernel, NCCL
+    all-reduce of Gram strips / residual sums / partial coarse residuals, all-gather of the new search block), shape gradient
+    replicated.  The partition and the peer-visible buffers are set up once per topology, outside the timed region."""
+    import torch
+    import torch.distributed as dist
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+    from diffsound_b200 import native
+    from diffsound_b200.diffelastic.diff_model import DiffSoundObj
+    from diffsound_b200.parallel.rowpart_lobpcg import eigen_decomposition_rowpart
+    v_np, t_np = kuhn_cube(args.cube)
+    leaf0 = torch.from_numpy(v_np).to(dev)
+    obj = DiffSoundObj(leaf0, torch.from_numpy(t_np).to(dev), mode_num=MODES, order=2, mat=STEEL)
+    leaf = obj.tetmesh.vertices.detach().clone().requires_grad_(True)
+    obj.tetmesh.vertices = leaf
+    state = {"solver": None}
+
+    def solve():
+        obj._X = None
+        obj._warm = []
+        obj._Kval = obj._Mblk = None
+        stats, state["solver"] = eigen_decomposition_rowpart(obj, solver=state["solver"], keep=True)
+        vals = obj.get_vals()
+        leaf.grad = None
+        (vals[:, 0] * (1.0 / obj.eigenvalues).float()).sum().backward()
+        return stats
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        stats = solve()
+    lib = native._lib.load()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = lib.ds_launch_count()
+    e0.record()
+    for _ in range(args.steps):
+        stats = solve()
+    e1.record()
+    barrier()
+    launches = int(lib.ds_launch_count() - launches0)
+    sampler.stop_flag = True
+    tms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+    with native.prof() as pf_all:
+        for _ in range(2):
+            solve()
+        torch.cuda.synchronize()
+    prof_all = pf_all.read()
+    # wall time per phase of the driver with a device synchronize at every boundary (diagnostic pass, untimed)
+    import time as _time
+    sv = state["solver"]
+    sv.profile, sv.phase_ms = True, {}
+    t_a = _time.perf_counter()
+    solve()
+    torch.cuda.synchronize()
+    t_total = (_time.perf_counter() - t_a) * 1e3
+    phases = dict(sv.phase_ms)
+    phases["outside_solver (assembly, start block, gradient)"] = t_total - sum(phases.values())
+    sv.profile = False
+    # the eigenvalues against the single-GPU driver on the same mesh (rank 0)
+    lam_rp = obj.eigenvalues.clone()
+    check = None
+    if rank == 0:
+        obj._X, obj._warm, obj._Kval, obj._Mblk = None, [], None, None
+        obj.eigen_decomposition()
+        check = float(((obj.eigenvalues - lam_rp).abs() / lam_rp).max())
+    pat = obj.deform.pattern
+    line = {"metric": METRIC, "value": args.steps / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "mode": "rowpart",
+            "config": {"workload": workload_name(args.cube),
+                       "sizes": f"n={pat.n} dofs, nnz={9 * pat.nnzb}; ONE mesh, rows split over {world} GPU(s)",
+                       "eig_tol": DiffSoundObj.eig_tol, "lobpcg_iterations": stats["iterations"],
+                       "nested_p1_iterations": stats.get("nested_iterations"),
+                       "replicated": "assembly, nested P1 eigen-solve, P1 coarse Chebyshev solves, small eigen-solves, gradient",
+                       "max_rel_dlambda_vs_single_gpu_driver": check},
+            "gpu_launches": launches, "clocks": sampler.summary(),
+            "kernel_ms_per_step_rank0": {k: v["ms"] / 2 for k, v in prof_all.items()},
+            "phase_wall_ms_rank0_synchronised": phases}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    state["solver"].close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -246,9 +349,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-cube", type=int, default=CPU_CUBE_N, help="cells per side of the CPU arm's bounded sample")
     ap.add_argument("--no-verify", action="store_true", help="skip the FP64 verification of the timed solve")
+    ap.add_argument("--mode", default="sweep", choices=["sweep", "rowpart"],
+                    help="sweep: one independent mesh per GPU (weak scaling, the default and the driver's line); rowpart: ONE "
+                         "mesh, eigen-solve row-partitioned over the GPUs (strong scaling)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+        return
+    if args.mode == "rowpart":
+        run_rowpart(args)
         return
 
     import numpy as np

@@ -108,6 +108,16 @@ SIGNATURES = {
     "ds_compact_ids_fill": (cint, [ptr, i64p, i64p, i64p, ptr]),
     "ds_tet_components_count": (cint, [ptr, i64p, i64, i64, i32p, C.POINTER(C.c_int64), ptr]),
     "ds_tet_components_fill": (cint, [ptr, i64p, i64p, i64p, ptr]),
+    "ds_lobpcg_residual": (cint, [f64p, f64p, i64, cint, i64, f64p, f64p, i64, f64p, f64p, ptr]),
+    "ds_gather_cols_f32": (cint, [f64p, i64, C.POINTER(C.c_int), cint, cint, i64, f32p, ptr]),
+    "ds_widen_f32": (cint, [f32p, cint, i64, f64p, i64, ptr]),
+    "ds_jacobi32": (cint, [f32p, f32p, i64, cint, dbl, f32p, ptr]),
+    "ds_spmm_dual_z32": (cint, [i32p, i32p, i64, i64, i32p, f64p, f64p, f32p, cint, f64p, i64, f64p, i64, ptr]),
+    "ds_pmg_restrict32_range": (cint, [i32p, i32p, i64, f32p, cint, i64, i64, f32p, ptr]),
+    "ds_pmg_prolong64": (cint, [i32p, i64, f64p, i64, cint, f64p, i64, ptr]),
+    "ds_gram_insert_f64": (cint, [f64p, f64p, i64, f64p, f64p, i64, cint, cint, ptr]),
+    "ds_sym_upper_f64": (cint, [f64p, f64p, i64, cint, ptr]),
+    "ds_eigh_generalized_idx_f64": (cint, [f64p, f64p, cint, i64, C.POINTER(C.c_int), dbl, f64p, f64p, i64, f64p, ptr, ptr]),
     "ds_prof_enable": (cint, [cint]),
     "ds_prof_enable_classes": (cint, [C.c_uint32]),
     "ds_prof_reset": (cint, []),

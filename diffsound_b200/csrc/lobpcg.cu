@@ -727,6 +727,21 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
 
 using namespace ds;
 
+// R = KX - MX diag(lam) and the column sums of R^2 and MX^2 (sums[2m], device) over the rows given: the residual step of
+// the iteration as a stand-alone call (row-partitioned driver: the sums are all-reduced over the ranks)
+extern "C" int ds_lobpcg_residual(const double* KX, const double* MX, int64_t ld, int m, int64_t n, const double* lam, double* R,
+                                  int64_t ldr, double* sums, double* partial, void* stream) {
+    DS_REQUIRE(KX && MX && lam && R && sums && partial && m > 0 && m <= 64 && n > 0, "ds_lobpcg_residual: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(PROF_RESIDUAL, st);
+    const int ctas = 296, threads = (1024 / m) * m;
+    k_residual<<<ctas, threads, (size_t)(threads / m) * 2 * m * sizeof(double), st>>>(KX, MX, ld, m, n, lam, R, ldr, partial);
+    DS_LAUNCH_CHECK();
+    k_colsum_reduce<<<1, 256, 0, st>>>(partial, ctas, 2 * m, sums);
+    DS_LAUNCH_CHECK();
+    return DS_OK;
+}
+
 extern "C" int ds_lobpcg(ds_workspace* ws, const int32_t* brow, const int32_t* bcol, int64_t n_nodes,
                          const double* Kval, const double* Mblk, const ds_pmg_level* coarse, double* X, int m,
                          const ds_lobpcg_opts* opts, double* lambda_out, double* resid_out, int64_t* stats_host,

@@ -924,12 +924,27 @@ static int dispatch_spmm32(int mode, const int32_t* brow, const void* rec, int64
 }
 
 // chunk_row: s32v_grid(n_nodes) + 1 row offsets from spmm32_chunks (NULL: built into a stream-ordered temporary)
+// Stream-ordered temporaries come from the device's default memory pool; its release threshold is 0 by default, so every
+// synchronisation hands the pool back to the driver and the next cudaMallocAsync pays a full allocation.  Keep the pool.
+static void keep_async_pool() {
+    static thread_local int done_for = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done_for = dev;
+}
+
 struct ChunkTmp {
     int32_t* p = nullptr;
     cudaStream_t st;
     int get(const int32_t* brow, int64_t n_nodes, const int32_t* given, cudaStream_t s, const int32_t** out) {
         st = s;
         if (given) { *out = given; return DS_OK; }
+        keep_async_pool();
         DS_CUDA(cudaMallocAsync(&p, sizeof(int32_t) * (s32v_grid(n_nodes) + 1), s));
         DS_TRY(spmm32_chunks(brow, n_nodes, p, s));
         *out = p;
@@ -1303,6 +1318,7 @@ extern "C" int ds_cheb32_solve(const int32_t* brow, const void* rec, const float
     L.invD = const_cast<float*>(invD);
     L.lmax = lmax;
     int32_t* tmp = nullptr;
+    keep_async_pool();
     DS_CUDA(cudaMallocAsync(&tmp, sizeof(int32_t) * (1024 + 16), st));
     L.chunk_row = tmp;
     L.gbar = reinterpret_cast<unsigned*>(tmp + 1024);

@@ -357,6 +357,34 @@ int ds_mss_loss_bwd(const float* x_pred, const float* x_true, int64_t B, int64_t
                     double alpha, double eps, const double* loss, double upstream, float* scratch, float* gx,
                     int accumulate, void* stream);
 
+/* ---- pieces of a row-partitioned LOBPCG step (csrc/slab.cu; host driver diffsound_b200/parallel/rowpart_lobpcg.py) -------
+ * One large mesh on several GPUs: rank r owns a contiguous slab of node rows.  These are the kernels
+ * of the single-GPU driver (ds_lobpcg) as stand-alone calls on a slab; the exchanges between them (all-reduce of Gram strips,
+ * residual sums and partial coarse residuals, all-gather of the new fp32 search block) are NCCL collectives issued by the host.
+ * ds_lobpcg_residual: R = KX - MX diag(lam) (n x m) and sums[2m] = column sums of R^2 | MX^2; partial: 296 * 2m doubles.
+ * ds_gather_cols_f32: dst (n x width, fp32) = src[:, cols_host[0..count)] (zero padded); ds_widen_f32: fp32 -> fp64 block.
+ * ds_jacobi32: Out = cc invD R (first Chebyshev step from zero).  ds_spmm_dual_z32: YK = K Z, YM = M Z for the rows of a
+ * slab (brow local, bcolP = column ids as ROW INDICES OF Z, chunk_row from ds_spmm32_chunks) with Z an fp32 block (ld = ncols).
+ * ds_pmg_restrict32_range: rc = 0.5 sum of the gather lists restricted to the fine nodes [fine_lo, fine_hi) (res_local holds
+ * exactly those rows): a partial coarse residual, summed over ranks by the caller.  ds_pmg_prolong64: x_i = 0.5 (xc[p0] + xc[p1]).
+ * ds_gram_insert_f64 / ds_sym_upper_f64: rows and columns [m, 2m) of the Gram pair from the strips / mirror the upper triangle.
+ * ds_eigh_generalized_idx_f64: ds_eigh_generalized_f64 on the slots idx_host[0..N) of the ldg x ldg Gram storage. */
+int ds_lobpcg_residual(const double* KX, const double* MX, int64_t ld, int m, int64_t n, const double* lam, double* R, int64_t ldr,
+                       double* sums, double* partial, void* stream);
+int ds_gather_cols_f32(const double* src, int64_t lds, const int* cols_host, int count, int width, int64_t n, float* dst, void* stream);
+int ds_widen_f32(const float* src, int width, int64_t n, double* dst, int64_t ldd, void* stream);
+int ds_jacobi32(const float* invD, const float* R, int64_t n_nodes, int ncols, double cc, float* Out, void* stream);
+int ds_spmm_dual_z32(const int32_t* brow, const int32_t* bcolP, int64_t n_rows, int64_t nnzb, const int32_t* chunk_row,
+                     const double* Kval, const double* Mblk, const float* Z, int ncols, double* YK, int64_t ldyk, double* YM,
+                     int64_t ldym, void* stream);
+int ds_pmg_restrict32_range(const int32_t* rptr, const int32_t* rlist, int64_t n_coarse, const float* res_local, int ncols,
+                            int64_t fine_lo, int64_t fine_hi, float* rc, void* stream);
+int ds_pmg_prolong64(const int32_t* parents, int64_t n_fine, const double* xc, int64_t ldc, int w, double* x, int64_t ldx, void* stream);
+int ds_gram_insert_f64(double* GK, double* GM, int64_t ldg, const double* GsK, const double* GsM, int64_t lds, int m, int wa, void* stream);
+int ds_sym_upper_f64(double* GK, double* GM, int64_t ldg, int N, void* stream);
+int ds_eigh_generalized_idx_f64(const double* GK, const double* GM, int N, int64_t ldg, const int* idx_host, double sigma,
+                                double* theta, double* C, int64_t ldc, double* scratch, int* info, void* stream);
+
 /* ---- marching tetrahedra -> tet mesh of a hollow shell, compaction, largest connected component ----------------
  * Replaces DMTet.__call__ and DMTetGeometry.get_largest_connected_component (src/dmtet/geometry/dmtet_thickness.py:99-200,
  * :254-285; the same code in dmtet_interpolate.py:115-205,265-296 and dmtet_geometry.py:115-267,411-443): torch.unique

@@ -85,3 +85,58 @@ def test_rowpart_world1_bit_exact(ncols):
 def test_rowpart_world2_bit_exact():
     import torch.multiprocessing as mp
     mp.spawn(_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
+# ---- LOBPCG on row slabs (parallel/rowpart_lobpcg.py): the same eigenpairs as the single-GPU driver ---------------------
+def _lobpcg_case(dev, group=None, N=6, k=10):
+    import bench
+    from diffsound_b200.diffelastic.diff_model import DiffSoundObj
+    from diffsound_b200.parallel.rowpart_lobpcg import eigen_decomposition_rowpart
+    v, t = bench.kuhn_cube(N)
+    vd, td = torch.from_numpy(v).to(dev), torch.from_numpy(t).to(dev)
+    ref = DiffSoundObj(vd, td, mode_num=k, order=2, mat=STEEL)
+    ref.eig_tol = 1e-7
+    ref.eigen_decomposition()
+    obj = DiffSoundObj(vd, td, mode_num=k, order=2, mat=STEEL)
+    obj.eig_tol = 1e-7
+    stats = eigen_decomposition_rowpart(obj, group=group)
+    lam_ref, lam = ref.eigenvalues.cpu().numpy(), obj.eigenvalues.cpu().numpy()
+    # residual 1e-7 -> eigenvalue error ~1e-14 relative to the spectrum; both solves sit on the same pairs
+    assert np.abs(lam - lam_ref).max() / lam_ref.max() <= 1e-10, (lam, lam_ref)
+    # M-orthonormal block of full height on every rank, and a usable backward
+    U = obj.U_hat_full
+    assert U.shape == ref.U_hat_full.shape
+    MU = torch.empty_like(U)
+    KU = torch.empty_like(U)
+    from diffsound_b200 import native
+    native.spmm_k_and_m(obj.deform.pattern, obj._Kval, obj._Mblk, U.contiguous(), KU, MU)
+    G = (U.T @ MU).cpu().numpy()
+    assert np.abs(G - np.eye(G.shape[0])).max() <= 1e-10
+    res = (KU[:, 6:] - MU[:, 6:] * obj.eigenvalues[None, :]).norm(dim=0) / (obj.eigenvalues * MU[:, 6:].norm(dim=0))
+    assert float(res.max()) <= 1e-6
+    return stats
+
+
+def test_rowpart_lobpcg_world1_matches_single_gpu_driver():
+    stats = _lobpcg_case(torch.device("cuda:0"))
+    assert stats["status"] == 0 and stats["world"] == 1
+
+
+def _lobpcg_worker(rank, world, port):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        stats = _lobpcg_case(dev)
+        assert stats["status"] == 0 and stats["world"] == world
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_rowpart_lobpcg_world2_matches_single_gpu_driver():
+    import torch.multiprocessing as mp
+    mp.spawn(_lobpcg_worker, args=(2, _free_port()), nprocs=2, join=True)
