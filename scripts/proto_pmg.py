@@ -212,6 +212,9 @@ def main():
         import torch
         d = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "meshes.npz"))
         N = sys.argv[1]
+        if N.startswith("mtet:"):      # marching-tets output of the reference (sliver elements): tests/golden/marching_tets.npz
+            d = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "marching_tets.npz"))
+            N = N[5:] + "_lcc"
         v, t = torch.tensor(d[f"{N}_verts"]), torch.tensor(d[f"{N}_tets"].astype(np.int64))
     else:
         N = int(sys.argv[1]) if len(sys.argv) > 1 else 8
