@@ -20,6 +20,10 @@
 //                                 barrier.cluster per step.  One SM's FP64 pipe and shared-memory
 //                                 bandwidth were the limit of the single-CTA version (4.3 ms at N = 144).
 //   k_eigh_finish  (nine CTAs)    eigenvalues, ascending rank; c_j = D R^-T row_j, one warp per row (rows are independent).
+// Measured and dropped (round 2): blocks of two rows per line position / four rows per warp with pairs of independent
+// rotations interleaved (half the mailbox hand-overs): 2.16 ms against 1.78 ms at N = 144 on a dense test pencil.  A
+// rotation is ~1000 cycles of dependent FP64 latency (5-stage warp sum, sqrt, divide, rsqrt); the hand-over is only
+// ~150 of the ~1150 cycles of a step, and N - 1 sequential rotation rounds per sweep are the floor of any ordering.
 #include "common.cuh"
 #include "../../include/diffsound_sm100.h"
 #include "kernels.cuh"

@@ -198,11 +198,12 @@ struct Driver {
     int nq = 0;
     double* MQ = nullptr;        // M Q
     int64_t nested_iters = 0, nested_status = 0;
+    double child_lmax = 0.0;     // spectral-radius estimate of the nested solve's fine level = this solve's coarse level
 
     int ld;                      // 3m
     double *S[2], *KS[2], *MS[2];
     double *R;
-    double *GK, *GM, *Cm, *theta, *eig_scratch, *gram_partial, *gram_partial2, *norm_partial, *norms, *lam_d;
+    double *GK, *GM, *Cm, *theta, *eig_scratch, *gram_partial, *gram_partial2, *norm_partial, *norms, *lam_d, *lmax_samples = nullptr;
     double *GKn = nullptr, *GMn = nullptr, *GsK = nullptr, *GsM = nullptr, *strip_partial = nullptr, *alg_scratch = nullptr;   // Gram recurrences (rr.cu)
     int* info_d;
     int cur = 0;
@@ -230,7 +231,7 @@ struct Driver {
         add(144 * 144); add(144 * 144); add(144 * 144); add(144); add((size_t)eigh_scratch_elems(144));
         add((size_t)gram_scratch_elems(64, 64)); add((size_t)norm_ctas * 2 * 128); add(2 * 128); add(128);
         add((size_t)gram_sym2_scratch_elems(ws->num_sms));
-        add(64);
+        add(64); add(128);
         for (int i = 0; i < 4; ++i) add(144 * 144);
         add((size_t)gram_strip_scratch_elems(ws->num_sms));
         add((size_t)gram_algebra_scratch_elems());
@@ -261,6 +262,7 @@ struct Driver {
         norms = a.take<double>(2 * 128);
         lam_d = a.take<double>(128);
         info_d = a.take<int>(16);
+        lmax_samples = a.take<double>(2 * (LMAX_STEPS0 / 4) * LMAX_W);
         GKn = a.take<double>(144 * 144); GMn = a.take<double>(144 * 144);
         GsK = a.take<double>(144 * 144); GsM = a.take<double>(144 * 144);
         strip_partial = a.take<double>((size_t)gram_strip_scratch_elems(ws->num_sms));
@@ -272,11 +274,11 @@ struct Driver {
             DS_REQUIRE(RES64 != nullptr, "lobpcg: workspace arena exhausted");
         }
         DS_REQUIRE(info_d != nullptr && strip_partial != nullptr && alg_scratch != nullptr && (!nq || MQ), "lobpcg: workspace arena exhausted");
-        for (int i = 0; i < 2; ++i) {   // never multiply uninitialised memory by zero coefficients
-            DS_CUDA(cudaMemsetAsync(S[i], 0, 3 * blk * 8, st));
-            DS_CUDA(cudaMemsetAsync(KS[i], 0, 3 * blk * 8, st));
-            DS_CUDA(cudaMemsetAsync(MS[i], 0, 3 * blk * 8, st));
-        }
+        // Never multiply uninitialised memory by zero coefficients: k_gram_strip reads ALL 3m columns of S (unused W / P
+        // slots included; their products land in Gram entries that the small-matrix recurrences later multiply by zero
+        // rows of C), so S starts finite.  KS / MS are only ever read at slots that were written (k_residual: X;
+        // k_rr_update2: X, W[:wa], P when in use; k_gram_sym2: active tiles), so they need no 1.9 GB of memsets each.
+        for (int i = 0; i < 2; ++i) DS_CUDA(cudaMemsetAsync(S[i], 0, 3 * blk * 8, st));
         // FP32 copies of the operators (records + block-Jacobi inverses)
         fine.want_bcolP = true;       // K W / M W are formed from the fp32 preconditioner output (k_spmm_dual_z32)
         DS_TRY(fine.setup(a, brow, bcol, n_nodes, nnzb, Kval, Mblk, o.sigma > 0.0 ? o.sigma : 0.0, o.coords, st));
@@ -331,56 +333,99 @@ struct Driver {
         return DS_OK;
     }
 
-    // largest eigenvalue of invD A by power iteration on invD A itself (16 fp32 columns, 12 steps; the
-    // un-shifted iteration reaches 0.95 lmax where I + invD A needs 16-20 steps, scripts/proto_pmg.py)
-    int estimate_lmax(Level32& L, float* a, float* b, float* zero_r) {
-        const int w = 16;
+    // largest eigenvalue of invD A by power iteration on invD A itself (16 fp32 columns; the un-shifted iteration
+    // reaches 0.95 lmax in 12 steps where I + invD A needs 16-20, scripts/proto_pmg.py).
+    // e_k = max over columns of ||A^(k+1) x|| / ||A^k x|| increases monotonically towards lmax for the SPD pencil.
+    // It is sampled after 4, 8, 12, ... steps.  Accepted: a sample that moved by less than 1 % (x 1.1), or -- the usual
+    // case, 12 steps -- Aitken's extrapolation of the last three samples when it is consistent (between e_k and
+    // 1.5 e_k), which bounds the limit of the geometric tail instead of trusting a fixed step count (a
+    // Chebyshev interval that ends below lmax amplifies the top of the spectrum).  Cap: 40 steps.
+    // Two halves: lmax_enqueue launches the first 12 steps and their three samples on any stream with NO host
+    // synchronisation (the samples stay on the device), lmax_finish reads them back, applies the acceptance rule in the
+    // order the samples were taken (the result is the one a step-by-step host loop would have stopped at) and only
+    // continues step by step in the rare case that neither rule fired.
+    static constexpr int LMAX_W = 16, LMAX_STEPS0 = 12;
+    int lmax_norms(const float* v, int64_t nl, double* out_dev, cudaStream_t s) {
+        DS_TRY(colnorm2_f32(v, LMAX_W, nl, norm_partial, norm_ctas, s));
+        k_colsum_reduce<<<1, 128, 0, s>>>(norm_partial, norm_ctas, LMAX_W, out_dev);
+        DS_LAUNCH_CHECK();
+        return DS_OK;
+    }
+    int lmax_step(Level32& L, float*& a, float*& b, float* zero_r, cudaStream_t s) {
+        // b = a + (-1) (a - 0) + (-1) invD (0 - A a) = invD A a     (Zprev = R = the zero block)
+        DS_TRY(spmm32(S32_MODE_CHEB, L.brow, L.rec, L.n_nodes, LMAX_W, a, zero_r, L.invD, zero_r, b, -1.f, -1.f, L.prof_cls,
+                      s, L.chunk_row));
+        std::swap(a, b);
+        L.launches++;
+        L.cols += LMAX_W;
+        return DS_OK;
+    }
+    // samples_dev: [2 * LMAX_STEPS0 / 4][LMAX_W] doubles; uses norm_partial (one estimate in flight per driver)
+    int lmax_enqueue(Level32& L, float* a, float* b, float* zero_r, double* samples_dev, cudaStream_t s) {
         const int64_t nl = 3 * L.n_nodes;
-        DS_CUDA(cudaMemsetAsync(zero_r, 0, sizeof(float) * nl * w, st));
-        DS_TRY(fill_random_f32(a, nl * w, 0x1234567ull, st));
-        std::vector<double> n0(w), n1(w);
-        auto norms_of = [&](const float* v, std::vector<double>& out) -> int {
-            DS_TRY(colnorm2_f32(v, w, nl, norm_partial, norm_ctas, st));
-            k_colsum_reduce<<<1, 128, 0, st>>>(norm_partial, norm_ctas, w, norms);
-            DS_LAUNCH_CHECK();
-            DS_CUDA(cudaMemcpyAsync(out.data(), norms, w * sizeof(double), cudaMemcpyDeviceToHost, st));
-            DS_CUDA(cudaStreamSynchronize(st));
+        DS_CUDA(cudaMemsetAsync(zero_r, 0, sizeof(float) * nl * LMAX_W, s));
+        DS_TRY(fill_random_f32(a, nl * LMAX_W, 0x1234567ull, s));
+        for (int it = 0; it < LMAX_STEPS0; ++it) {
+            const bool sample = (it & 3) == 3;
+            if (sample) DS_TRY(lmax_norms(a, nl, samples_dev + (size_t)(2 * (it / 4)) * LMAX_W, s));
+            DS_TRY(lmax_step(L, a, b, zero_r, s));
+            if (sample) DS_TRY(lmax_norms(a, nl, samples_dev + (size_t)(2 * (it / 4) + 1) * LMAX_W, s));
+        }
+        return DS_OK;
+    }
+    int lmax_finish(Level32& L, float* a, float* b, float* zero_r, const double* samples_dev, cudaStream_t s) {
+        constexpr int NS = LMAX_STEPS0 / 4;
+        const int64_t nl = 3 * L.n_nodes;
+        double h[2 * NS * LMAX_W];
+        DS_CUDA(cudaMemcpyAsync(h, samples_dev, sizeof(h), cudaMemcpyDeviceToHost, s));
+        DS_CUDA(cudaStreamSynchronize(s));
+        double best = 0.0, e1 = 0.0, e2 = 0.0;
+        bool done = false;
+        auto accept = [&](double e3) {          // the acceptance rule after one more sample
+            best = e3;
+            if (e2 > 0.0 && e3 <= 1.01 * e2) return true;
+            if (e1 > 0.0) {
+                const double d1 = e2 - e1, d2 = e3 - e2;
+                if (d1 > d2 && d2 > 0.0) {
+                    const double lim = e3 + d2 * d2 / (d1 - d2);          // Aitken: e3 + d2 q / (1 - q), q = d2 / d1
+                    if (lim <= 1.5 * e3) { best = std::max(e3, lim / 1.1 * 1.05); return true; }
+                }
+            }
+            e1 = e2;
+            e2 = e3;
+            return false;
+        };
+        for (int k = 0; k < NS && !done; ++k) {
+            double e3 = 0.0;
+            for (int c = 0; c < LMAX_W; ++c)
+                e3 = std::max(e3, std::sqrt(h[(2 * k + 1) * LMAX_W + c] / h[(2 * k) * LMAX_W + c]));
+            done = accept(e3);
+        }
+        // LMAX_STEPS0 is even: after the enqueued steps the iterate is back in `a`
+        std::vector<double> n0(LMAX_W), n1(LMAX_W);
+        auto norms_sync = [&](const float* v, std::vector<double>& out) -> int {
+            DS_TRY(lmax_norms(v, nl, norms, s));
+            DS_CUDA(cudaMemcpyAsync(out.data(), norms, LMAX_W * sizeof(double), cudaMemcpyDeviceToHost, s));
+            DS_CUDA(cudaStreamSynchronize(s));
             return DS_OK;
         };
-        // e_k = max over columns of ||A^(k+1) x|| / ||A^k x|| increases monotonically towards lmax for the SPD pencil.
-        // It is sampled after 4, 8, 12, ... steps.  Accepted: a sample that moved by less than 1 % (x 1.1), or -- the usual
-        // case, 12 steps -- Aitken's extrapolation of the last three samples when it is consistent (between e_k and
-        // 1.5 e_k), which bounds the limit of the geometric tail instead of trusting a fixed step count (a
-        // Chebyshev interval that ends below lmax amplifies the top of the spectrum).  Cap: 40 steps.
-        double best = 0.0, e1 = 0.0, e2 = 0.0;
-        for (int it = 0; it < 40; ++it) {
+        for (int it = LMAX_STEPS0; it < 40 && !done; ++it) {
             const bool sample = (it & 3) == 3;
-            if (sample) DS_TRY(norms_of(a, n0));
-            // b = a + (-1) (a - 0) + (-1) invD (0 - A a) = invD A a     (Zprev = R = the zero block)
-            DS_TRY(spmm32(S32_MODE_CHEB, L.brow, L.rec, L.n_nodes, w, a, zero_r, L.invD, zero_r, b, -1.f, -1.f, L.prof_cls,
-                          st, L.chunk_row));
-            std::swap(a, b);
-            L.launches++;
-            L.cols += w;
+            if (sample) DS_TRY(norms_sync(a, n0));
+            DS_TRY(lmax_step(L, a, b, zero_r, s));
             if (sample) {
-                DS_TRY(norms_of(a, n1));
+                DS_TRY(norms_sync(a, n1));
                 double e3 = 0.0;
-                for (int c = 0; c < w; ++c) e3 = std::max(e3, std::sqrt(n1[c] / n0[c]));
-                best = e3;
-                if (e2 > 0.0 && e3 <= 1.01 * e2) break;
-                if (e1 > 0.0) {
-                    const double d1 = e2 - e1, d2 = e3 - e2;
-                    if (d1 > d2 && d2 > 0.0) {
-                        const double lim = e3 + d2 * d2 / (d1 - d2);          // Aitken: e3 + d2 q / (1 - q), q = d2 / d1
-                        if (lim <= 1.5 * e3) { best = std::max(e3, lim / 1.1 * 1.05); break; }
-                    }
-                }
-                e1 = e2;
-                e2 = e3;
+                for (int c = 0; c < LMAX_W; ++c) e3 = std::max(e3, std::sqrt(n1[c] / n0[c]));
+                done = accept(e3);
             }
         }
         L.lmax = 1.1 * best;
         return DS_OK;
+    }
+    int estimate_lmax(Level32& L, float* a, float* b, float* zero_r) {
+        DS_TRY(lmax_enqueue(L, a, b, zero_r, lmax_samples, st));
+        return lmax_finish(L, a, b, zero_r, lmax_samples, st);
     }
 
     // W32 = T R32 (w columns): Chebyshev polynomial (one level) or the two-level V-cycle
@@ -466,6 +511,7 @@ struct Driver {
         int64_t cstats[12] = {0};
         DS_TRY(dc.run(Xc, lamc, resc, cstats));
         nested_iters = cstats[0];
+        child_lmax = dc.fine.lmax;
         nested_status = cstats[3];
         spmm_count += cstats[2];
         coarse.launches += cstats[4];           // the nested solve's SpMMs are coarse-level work
@@ -488,8 +534,16 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
         DS_LAUNCH_CHECK();
     }
     if (Xc && !nq) DS_TRY(nested_start(X));
+    // Spectral radii of the Chebyshev intervals: 12 SpMM launches and three samples per level without a host
+    // synchronisation in between.  The P1 operator of the coarse level is the nested solve's fine level (same records, same
+    // start vector), so its estimate is taken over.  (Running the fine-level estimate on a side stream next to the nested
+    // solve was measured and dropped: full-SM SpMM CTAs cannot share an SM with the nested solve's cooperative kernels, the
+    // two streams only delay each other's launches -- no gain, and one 100 ms stall in four runs.)
     DS_TRY(estimate_lmax(fine, Za, Zb, R32));
-    if (cl) DS_TRY(estimate_lmax(coarse, ZCa, ZCb, RC32));
+    if (cl) {
+        if (child_lmax > 0.0) coarse.lmax = child_lmax;
+        else DS_TRY(estimate_lmax(coarse, ZCa, ZCb, RC32));
+    }
     if (o.verbose)
         fprintf(stderr, "[ds_lobpcg] n=%lld m=%d nev=%d lmax(invD K)=%.4f %s deg=%d coarse: n=%lld lmax=%.4f deg=%d nu=%d\n",
                 (long long)n, m, nev, fine.lmax / 1.1, cl ? "two-level" : "chebyshev", o.cheb_degree,
