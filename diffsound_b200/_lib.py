@@ -47,6 +47,8 @@ SIGNATURES = {
     "ds_pattern_expand_csr": (cint, [i32p, i32p, i64, i64, i64p, i64p, ptr]),
     "ds_assemble_km": (cint, [f32p, i32p, i64, cint, i64, dbl, dbl, f64p, f64p, i32p, i32p, i32p, i32p, i64,
                               f64p, f64p, f64p, ptr]),
+    "ds_assemble_km_tets": (cint, [f32p, i32p, i64, cint, i64, dbl, dbl, f64p, f64p, i32p, i32p, i32p, i32p, i32p, cint, i64,
+                                   f64p, f64p, f64p, ptr]),
     "ds_mass_expand": (cint, [i32p, i64, i64, f64p, f64p, ptr]),
     "ds_assemble_mass_coo": (cint, [f64p, i32p, i64, cint, f64p, dbl, f64p, i32p, i32p, ptr]),
     "ds_spmm_km": (cint, [i32p, i32p, i64, f64p, f64p, dbl, f64p, i64, cint, dbl, dbl, f64p, i64, f64p, i64, ptr]),

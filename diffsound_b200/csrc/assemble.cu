@@ -263,6 +263,127 @@ k_assemble_rows(const double* __restrict__ geom, const double* __restrict__ ctab
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Round 2: tet-sequential rows (quadratic tets).  The balanced kernel above pays per CONTRIBUTION: it decodes (tet, a, b),
+// fetches ~14 scattered 8-byte geometry values that differ from lane to lane (one L1 wavefront per distinct tet and
+// instruction: L1 data pipe 68 %) and scatters 9 doubles per slot.  Here a warp still owns one node row i, but walks the
+// tets AROUND node i one after the other (they are the contributors of the row's diagonal slot, ascending).  For tet e
+// with i = local node a, lane (b, c) = (lane / 3, lane % 3) produces row c of the 3x3 block (a, b): every geometry load is
+// one broadcast address per warp, the block lands at slot[e, a, b] - brow[i] of a shared-memory image of the row
+// (11 doubles per slot: 9 stiffness entries + the mass scalar + padding; lanes of one tet hit distinct slots, tets are strictly
+// ordered, so the sums are deterministic and need no atomics), and the finished row leaves as three contiguous runs of
+// 3 deg doubles (the reference's scalar-CSR value order) + deg mass scalars: fully coalesced streaming stores.
+// `slot` is the element -> pattern-slot map ds_pattern_fill already produces (4 B per (tet, a, b)).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int AT_WARPS = 8;
+constexpr int AT_SLOT = 11;                       // doubles per slot of the row image: 9 + 1 + one of padding (an odd pitch
+                                                  // spreads the 64-bit accesses over all bank pairs; 10 gave 5-way conflicts)
+
+__global__ void __launch_bounds__(32 * AT_WARPS)
+k_assemble_rows_tets2(const double* __restrict__ geom, const double* __restrict__ ctab_g, const double* __restrict__ mtab_g,
+                      const int32_t* __restrict__ brow, const int32_t* __restrict__ bcol,
+                      const int32_t* __restrict__ contrib_ptr, const int32_t* __restrict__ contrib,
+                      const int32_t* __restrict__ slot, int64_t n_nodes, int cap, double mu, double lam,
+                      double* __restrict__ Kval, double* __restrict__ Mblk) {
+    constexpr int NPE = 10, NPE2 = 100;
+    extern __shared__ __align__(16) double s_dyn[];
+    double* s_ct4 = s_dyn;                        // [a][b][li][mi]: the <= 2 x 2 support products of ctab, zero where absent
+    double* s_mtab = s_ct4 + NPE2 * 4;            // [a][b]
+    double* s_acc = s_mtab + NPE2;                // [AT_WARPS][cap][AT_SLOT]
+    for (int t = threadIdx.x; t < NPE2 * 4; t += blockDim.x) {
+        const int ab = t >> 2, li = (t >> 1) & 1, mi = t & 1;
+        const int a = ab / NPE, b = ab - a * NPE;
+        const bool ok = li < c_nsup2[a] && mi < c_nsup2[b];
+        s_ct4[t] = ok ? ctab_g[ab * 16 + c_sup2[a][li] * 4 + c_sup2[b][mi]] : 0.0;
+    }
+    for (int t = threadIdx.x; t < NPE2; t += blockDim.x) s_mtab[t] = mtab_g[t];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* acc = s_acc + (size_t)warp * cap * AT_SLOT;
+    for (int t = lane; t < cap * AT_SLOT; t += 32) acc[t] = 0.0;
+    __syncthreads();
+    const int b = lane / 3, c = lane - 3 * b;     // lanes 30, 31 idle in the tet loop
+    const bool lane_on = lane < 3 * NPE;
+    const int bb = lane_on ? b : 0;
+    const int mb0 = 3 * c_sup2[bb][0], mb1 = 3 * c_sup2[bb][1];
+    for (int64_t row = (int64_t)blockIdx.x * AT_WARPS + warp; row < n_nodes; row += (int64_t)gridDim.x * AT_WARPS) {
+        const int b0 = brow[row];
+        const int deg = brow[row + 1] - b0;
+        if (deg <= 0) continue;
+        if (deg > cap) asm volatile("trap;");     // the caller's max_deg is wrong: fail loudly rather than overrun the row image
+        // diagonal slot: bcol is ascending inside a row
+        int lo = b0, hi = b0 + deg - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(bcol + mid) < (int32_t)row) lo = mid + 1; else hi = mid;
+        }
+        const int q0 = contrib_ptr[lo], q1 = contrib_ptr[lo + 1];
+        int pair = q0 < q1 ? __ldg(contrib + q0) : 0;
+        int pair_next = q0 + 1 < q1 ? __ldg(contrib + q0 + 1) : 0;
+        for (int q = q0; q < q1; ++q) {
+            const int pair_next2 = q + 2 < q1 ? __ldg(contrib + q + 2) : 0;      // two entries ahead: an L2 round trip is longer than a step
+            const int e = pair / NPE2;
+            const int a = (pair - e * NPE2) / NPE;                       // the entry is (e, a, a)
+            const double* __restrict__ g = geom + (int64_t)e * GEOM_STRIDE;
+            const int la0 = 3 * c_sup2[a][0], la1 = 3 * c_sup2[a][1];    // warp-uniform
+            const int so = lane_on ? __ldg(slot + (int64_t)e * NPE2 + a * NPE + bb) - b0 : 0;
+            const double2 ct01 = *reinterpret_cast<const double2*>(s_ct4 + (a * NPE + bb) * 4);       // (l0,m0) (l0,m1)
+            const double2 ct23 = *reinterpret_cast<const double2*>(s_ct4 + (a * NPE + bb) * 4 + 2);   // (l1,m0) (l1,m1)
+            double gl0[3], gl1[3], gm0[3], gm1[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                gl0[d] = __ldg(g + la0 + d);
+                gl1[d] = __ldg(g + la1 + d);
+                gm0[d] = __ldg(g + mb0 + d);
+                gm1[d] = __ldg(g + mb1 + d);
+            }
+            const double detK = __ldg(g + 12), detM = __ldg(g + 13);
+            // w_l = sum_m ct[l][m] G_m;  S = sum_l G_l w_l^T
+            double w0[3], w1[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                w0[d] = fma(ct01.x, gm0[d], ct01.y * gm1[d]);
+                w1[d] = fma(ct23.x, gm0[d], ct23.y * gm1[d]);
+            }
+            const double glc0 = c == 0 ? gl0[0] : (c == 1 ? gl0[1] : gl0[2]);
+            const double glc1 = c == 0 ? gl1[0] : (c == 1 ? gl1[1] : gl1[2]);
+            const double wc0 = c == 0 ? w0[0] : (c == 1 ? w0[1] : w0[2]);
+            const double wc1 = c == 0 ? w1[0] : (c == 1 ? w1[1] : w1[2]);
+            const double tr = mu * (fma(gl0[0], w0[0], fma(gl0[1], w0[1], gl0[2] * w0[2])) +
+                                    fma(gl1[0], w1[0], fma(gl1[1], w1[1], gl1[2] * w1[2])));
+            if (lane_on) {
+                double* out = acc + so * AT_SLOT + 3 * c;
+                double v[3];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const double Scd = fma(glc0, w0[d], glc1 * w1[d]);          // S[c][d]
+                    const double Sdc = fma(gl0[d], wc0, gl1[d] * wc1);          // S[d][c]
+                    v[d] = fma(mu, Sdc, lam * Scd);
+                }
+                out[0] += detK * (c == 0 ? v[0] + tr : v[0]);
+                out[1] += detK * (c == 1 ? v[1] + tr : v[1]);
+                out[2] += detK * (c == 2 ? v[2] + tr : v[2]);
+                if (c == 0) acc[so * AT_SLOT + 9] += s_mtab[a * NPE + bb] * detM;
+            }
+            __syncwarp();
+            pair = pair_next;
+            pair_next = pair_next2;
+        }
+        // the finished row: three runs of 3 deg stiffness values, deg mass scalars; the image is cleared on the way out
+        double* krow = Kval + 9 * (int64_t)b0;
+        const int rs = 3 * deg;
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc)
+            for (int t = lane; t < rs; t += 32) {
+                const int s = t / 3, d = t - 3 * s;
+                __stcs(krow + cc * rs + t, acc[s * AT_SLOT + 3 * cc + d]);
+            }
+        for (int s = lane; s < deg; s += 32) __stcs(Mblk + b0 + s, acc[s * AT_SLOT + 9]);
+        __syncwarp();
+        for (int t = lane; t < deg * AT_SLOT; t += 32) acc[t] = 0.0;
+        __syncwarp();
+    }
+}
+
 __global__ void k_mass_expand(const int32_t* __restrict__ brow, int64_t n_nodes, const double* __restrict__ Mblk,
                               double* __restrict__ Mval) {
     int lane = threadIdx.x & 31;
@@ -341,6 +462,41 @@ extern "C" int ds_assemble_km(const float* verts, const int32_t* tets, int64_t T
     else
         k_assemble_rows<2><<<blocks, 32 * AS_WARPS, 0, stream>>>(geom, ctab, mtab, brow, contrib_ptr, contrib, n_nodes,
                                                                  mu, lam, Kval, Mblk);
+    DS_LAUNCH_CHECK();
+    return DS_OK;
+}
+
+// Same result as ds_assemble_km for quadratic tets through the tet-sequential row kernel (k_assemble_rows_tets2);
+// slot: the element -> pattern-slot map of ds_pattern_fill; max_deg: the longest block row (sizes the row image).
+extern "C" int ds_assemble_km_tets(const float* verts, const int32_t* tets, int64_t T, int order, int64_t n_nodes,
+                                   double mu, double lam, const double* ctab, const double* mtab,
+                                   const int32_t* brow, const int32_t* bcol, const int32_t* contrib_ptr,
+                                   const int32_t* contrib, const int32_t* slot, int max_deg, int64_t nnzb, double* geom,
+                                   double* Kval, double* Mblk, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DS_REQUIRE(order == 2, "ds_assemble_km_tets: quadratic tets only (order 1 goes through ds_assemble_km)");
+    DS_REQUIRE(verts && tets && ctab && mtab && brow && bcol && contrib_ptr && contrib && slot && geom && Kval && Mblk,
+               "ds_assemble_km_tets: null argument");
+    DS_REQUIRE(T > 0 && n_nodes > 0, "ds_assemble_km_tets: empty mesh");
+    DS_REQUIRE(max_deg >= 1 && max_deg <= 256, "ds_assemble_km_tets: max_deg=%d must be in [1, 256] (longer rows: ds_assemble_km)",
+               max_deg);
+    const int npe = 10;
+    ProfScope prof(PROF_ASSEMBLE, stream);
+    prof_account(PROF_ASSEMBLE, 2.0 * 9.0 * (double)nnzb * 8.0 + (double)T * npe * 4.0 + (double)n_nodes * 12.0 + (double)T * npe * npe * 4.0,
+                 0.0);
+    k_tet_geometry<<<(unsigned)ceil_div(T, 128), 128, 0, stream>>>(verts, tets, T, npe, order, geom);
+    DS_LAUNCH_CHECK();
+    const int cap = (max_deg + 3) & ~3;
+    const size_t smem = (size_t)(100 * 4 + 100 + (size_t)AT_WARPS * cap * AT_SLOT) * sizeof(double);
+    DS_CUDA(cudaFuncSetAttribute(k_assemble_rows_tets2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    DS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assemble_rows_tets2, 32 * AT_WARPS, smem));
+    int dev = 0, sms = 148;
+    DS_CUDA(cudaGetDevice(&dev));
+    DS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(n_nodes, AT_WARPS), (int64_t)sms * std::max(per_sm, 1));
+    k_assemble_rows_tets2<<<blocks, 32 * AT_WARPS, smem, stream>>>(geom, ctab, mtab, brow, bcol, contrib_ptr, contrib, slot,
+                                                                  n_nodes, cap, mu, lam, Kval, Mblk);
     DS_LAUNCH_CHECK();
     return DS_OK;
 }

@@ -91,9 +91,10 @@ def unique_rows3(rows_f32):
 
 
 class Pattern:
-    """Block-CSR sparsity pattern of K and M plus per-slot contributor lists."""
+    """Block-CSR sparsity pattern of K and M plus per-slot contributor lists.  want_slot: also keep the element -> slot map
+    (int32 per (tet, a, b)) that the tet-sequential assembly of quadratic meshes reads (default: quadratic meshes)."""
 
-    def __init__(self, tets_i32, n_nodes, want_slot=False):
+    def __init__(self, tets_i32, n_nodes, want_slot=None):
         lib = _lib.load()
         assert tets_i32.dtype == torch.int32 and tets_i32.is_cuda and tets_i32.is_contiguous()
         T, npe = tets_i32.shape
@@ -111,9 +112,13 @@ class Pattern:
             self.bcol = torch.empty(self.nnzb, **i32)
             self.contrib_ptr = torch.empty(self.nnzb + 1, **i32)
             self.contrib = torch.empty(T * npe * npe, **i32)
+            if want_slot is None:
+                want_slot = npe == 10
             self.slot = torch.empty(T * npe * npe, **i32) if want_slot else None
             _lib.check(lib.ds_pattern_fill(ws.handle, self.n_nodes, _p(self.brow), _p(self.bcol), _p(self.contrib_ptr),
                                            _p(self.contrib), _p(self.slot), _stream()), "ds_pattern_fill")
+            # longest block row: sizes the shared-memory row image of the tet-sequential assembly
+            self.max_deg = int((self.brow[1:] - self.brow[:-1]).max()) if want_slot else 0
         self._csr = None
 
     @property
@@ -143,7 +148,10 @@ class Pattern:
         return torch.stack([rows, col], dim=0)
 
 
-def assemble_km(verts_f32, tets_i32, order, pattern, mu, lam, ctab, mtab, Kval=None, Mblk=None, geom=None):
+def assemble_km(verts_f32, tets_i32, order, pattern, mu, lam, ctab, mtab, Kval=None, Mblk=None, geom=None, kernel=None):
+    """K (scalar-CSR value order of the reference) and M (one scalar per block) into the fixed pattern.  kernel: 'tets'
+    (tet-sequential rows: quadratic meshes whose pattern carries the slot map and whose rows have <= 256 blocks), 'rows'
+    (balanced contributor lists: everything else) or None = pick."""
     lib = _lib.load()
     dev = verts_f32.device
     assert verts_f32.dtype == torch.float32 and tets_i32.dtype == torch.int32
@@ -155,6 +163,18 @@ def assemble_km(verts_f32, tets_i32, order, pattern, mu, lam, ctab, mtab, Kval=N
         Mblk = torch.empty(pattern.nnzb, **f64)
     if geom is None:
         geom = torch.empty(T * 14, **f64)
+    can_tets = order == 2 and getattr(pattern, "slot", None) is not None and 1 <= pattern.max_deg <= 256
+    if kernel is None:
+        kernel = "tets" if can_tets else "rows"
+    if kernel == "tets":
+        if not can_tets:
+            raise ValueError("assemble_km(kernel='tets') needs a quadratic mesh, Pattern(want_slot=True) and rows of <= 256 blocks")
+        with torch.cuda.device(dev):
+            _lib.check(lib.ds_assemble_km_tets(_p(verts_f32), _p(tets_i32), T, order, pattern.n_nodes, float(mu), float(lam),
+                                               _p(ctab), _p(mtab), _p(pattern.brow), _p(pattern.bcol), _p(pattern.contrib_ptr),
+                                               _p(pattern.contrib), _p(pattern.slot), pattern.max_deg, pattern.nnzb, _p(geom),
+                                               _p(Kval), _p(Mblk), _stream()), "ds_assemble_km_tets")
+        return Kval, Mblk
     with torch.cuda.device(dev):
         _lib.check(lib.ds_assemble_km(_p(verts_f32), _p(tets_i32), T, order, pattern.n_nodes, float(mu), float(lam),
                                       _p(ctab), _p(mtab), _p(pattern.brow), _p(pattern.bcol), _p(pattern.contrib_ptr),

@@ -77,6 +77,16 @@ int ds_assemble_km(const float* verts, const int32_t* tets, int64_t T, int order
                    const double* mtab, const int32_t* brow, const int32_t* bcol,
                    const int32_t* contrib_ptr, const int32_t* contrib, int64_t nnzb,
                    double* geom, double* Kval, double* Mblk, void* stream);
+/* Same result for quadratic tets (order 2) through the tet-sequential row kernel: a warp owns a node row and walks the
+ * tets around that node in ascending order, every geometry load is one broadcast address per warp, the row is summed in a
+ * shared-memory image and leaves as coalesced streaming stores (csrc/assemble.cu, k_assemble_rows_tets2).  Replaces the
+ * same reference lines as ds_assemble_km.  slot: int32 [T*npe*npe], the element -> pattern-slot map ds_pattern_fill
+ * writes when asked to; max_deg: the longest block row of the pattern, 1..256 (longer rows: use ds_assemble_km). */
+int ds_assemble_km_tets(const float* verts, const int32_t* tets, int64_t T, int order, int64_t n_nodes,
+                        double mu, double lam, const double* ctab, const double* mtab,
+                        const int32_t* brow, const int32_t* bcol, const int32_t* contrib_ptr,
+                        const int32_t* contrib, const int32_t* slot, int max_deg, int64_t nnzb, double* geom,
+                        double* Kval, double* Mblk, void* stream);
 int ds_mass_expand(const int32_t* brow, int64_t n_nodes, int64_t nnzb, const double* Mblk,
                    double* Mval, void* stream);
 /* Legacy twin of the reference export `assemble_mass_matrix` (massMatrixDouble.cu:138-158):

@@ -62,6 +62,30 @@ def test_pattern_bit_exact(meshes, name, order):
     assert np.array_equal(np.sort(contrib), np.arange(contrib.size))
 
 
+@pytest.mark.parametrize("name", ["cube2", "cube3", "grid16", "bowl"])
+def test_assembly_tet_sequential_matches_row_kernel(meshes, name):
+    """The two assembly kernels of quadratic meshes (tet-sequential rows = the default, balanced contributor lists = the
+    fall-back for rows of more than 256 blocks) sum the same element contributions in the same ascending-tet order per
+    slot; they differ only in how a slot's sum is associated (<= a few ulp of the largest contribution)."""
+    from diffsound_b200 import native
+    from diffsound_b200.diffelastic import mass_matrix as mmx
+    v, t = meshes[name]
+    pv, pt = mo.promote(torch.tensor(v), torch.tensor(t), 2)
+    dev = torch.device("cuda:0")
+    verts, tets = pv.to(dev).contiguous(), pt.to(torch.int32).to(dev).contiguous()
+    pat = native.Pattern(tets, verts.shape[0])
+    assert pat.slot is not None and 1 <= pat.max_deg <= 256
+    mu, lam = mo.lame(STEEL[1], STEEL[2])
+    ctab, mtab = mmx.stiffness_contraction_table(2).to(dev), mmx.mass_density_table(2, STEEL[0]).to(dev)
+    K1, M1 = native.assemble_km(verts, tets, 2, pat, mu, lam, ctab, mtab, kernel="tets")
+    K2, M2 = native.assemble_km(verts, tets, 2, pat, mu, lam, ctab, mtab, kernel="rows")
+    assert float((K1 - K2).abs().max()) <= 1e-13 * float(K2.abs().max())
+    assert float((M1 - M2).abs().max()) <= 1e-14 * float(M2.abs().max())
+    # a second call reuses the cleared row images: identical bits
+    K3, M3 = native.assemble_km(verts, tets, 2, pat, mu, lam, ctab, mtab, kernel="tets")
+    assert torch.equal(K1, K3) and torch.equal(M1, M3)
+
+
 @pytest.mark.parametrize("name,order", [("cube3", 1), ("cube3", 2), ("grid16", 1), ("grid16", 2), ("bowl", 2)])
 def test_assembly_vs_oracle_and_golden(meshes, name, order):
     from diffsound_b200 import native
