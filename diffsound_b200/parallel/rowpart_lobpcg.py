@@ -226,19 +226,37 @@ class RowPartLOBPCG:
         g = torch.Generator(device=self.dev).manual_seed(1234 + self.rank)
         Z[0].copy_(torch.rand(3 * self.nl, w, device=self.dev, generator=g) * 2 - 1)
         zero = torch.zeros(3 * self.nl, w, dtype=torch.float32, device=self.dev)
+        # The first 12 steps and their three samples are queued without a host synchronisation (the ratios stay on the
+        # device); the usual case reads them back once.  Same acceptance rule as before, applied in sample order.
         cur, est, prev = 0, 0.0, None
-        for it in range(24):
-            sample = it % 4 == 3
-            if sample:
-                n0 = self._allreduce((Z[cur].double() ** 2).sum(0))
+        ratios = []
+
+        def step(sample):
+            nonlocal cur
+            n0 = self._allreduce((Z[cur].double() ** 2).sum(0)) if sample else None
             self._barrier()
             self._spmm32(2, cur, w, Z[cur ^ 1], R=zero, Zprev=zero, ab=-1.0, cc=-1.0)        # invD K z
             cur ^= 1
             if sample:
                 n1 = self._allreduce((Z[cur].double() ** 2).sum(0))
-                est = float(torch.sqrt(n1 / n0).max())
-                if prev is not None and est <= 1.01 * prev and it >= 11:
-                    break
+                return torch.sqrt(n1 / n0).max()
+            return None
+
+        for it in range(12):
+            r = step(it % 4 == 3)
+            if r is not None:
+                ratios.append(r)
+        for it, e in zip((3, 7, 11), torch.stack(ratios).tolist()):      # one device -> host copy
+            est = e
+            done = prev is not None and est <= 1.01 * prev and it >= 11
+            prev = est
+        for it in range(12, 24):
+            if done:
+                break
+            r = step(it % 4 == 3)
+            if r is not None:
+                est = float(r)
+                done = est <= 1.01 * prev
                 prev = est
         return 1.1 * est
 
@@ -275,12 +293,14 @@ class RowPartLOBPCG:
         zc0 = torch.zeros(3 * co.n_nodes, 16, dtype=torch.float32, device=dev)
         g = torch.Generator(device=dev).manual_seed(99)
         a = torch.rand(3 * co.n_nodes, 16, device=dev, generator=g) * 2 - 1
-        est = 0.0
+        est = None
         for it in range(16):
             b = native.spmm32(co.pattern, self.rec_c, a, mode=2, R=zc0, invD=self.invD_c, Zprev=zc0, ab=-1.0, cc=-1.0)
-            if it >= 11:
-                est = max(est, float(torch.sqrt((b.double() ** 2).sum(0) / (a.double() ** 2).sum(0)).max()))
+            if it >= 11:      # the ratio grows monotonically towards lmax; kept on the device, read back once
+                r = torch.sqrt((b.double() ** 2).sum(0) / (a.double() ** 2).sum(0)).max()
+                est = r if est is None else torch.maximum(est, r)
             a = b
+        est = float(est)
         self.lmax_c = 1.1 * est
         self.lmax_f = self._estimate_lmax()
         # ---- nested iteration: the P1 eigen-problem, replicated, then prolonged (every rank prolongs all rows: the initial
