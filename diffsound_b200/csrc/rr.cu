@@ -24,17 +24,18 @@ namespace ds {
 // ---------------------------------------------------------------------------------------------------------------
 // strips: GsK[r][c] = sum_rows KW[row][r] S[row][c],  GsM likewise;  r < wa (16 | 32 | 48), c < ld (<= 144)
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int ST_ROWS = 8;
-constexpr int ST_STAGES = 8;
-constexpr int ST_THREADS = 512;
+constexpr int ST_THREADS = 512;              // 16 compute warps (+ one producer warp in the PRODUCER variants)
 constexpr int ST_WARPS = ST_THREADS / 32;
 constexpr int ST_PITCH = 252;              // doubles per staged row: [KW 48 | MW 48 | S 144] = 240, 252 = 12 (mod 16)
 constexpr int ST_MAXA = 12, ST_MAXB = 18;  // A-side tiles (K and M strips), B-side tiles
 constexpr int ST_WA = 4, ST_WB = 4;        // warp grid
 constexpr int ST_TA = 3, ST_TB = 5;        // tiles per warp: 4 x 3 >= 12, 4 x 5 >= 18
-constexpr size_t ST_SMEM = (size_t)ST_STAGES * ST_ROWS * ST_PITCH * sizeof(double) + 2 * ST_STAGES * sizeof(uint64_t);
+constexpr size_t st_smem(int rows, int stages) { return (size_t)stages * rows * ST_PITCH * sizeof(double) + 2 * stages * sizeof(uint64_t); }
 
-__global__ void __launch_bounds__(ST_THREADS, 1)
+// ST_ROWS rows per ring stage, ST_STAGES stages; PRODUCER: a 17th warp issues the bulk copies (the compute warps never wait
+// on the `empty` barriers), else warp 0 issues them between its own tile products
+template <int ST_ROWS, int ST_STAGES, bool PRODUCER>
+__global__ void __launch_bounds__(ST_THREADS + (PRODUCER ? 32 : 0), 1)
 k_gram_strip(const double* __restrict__ KW, const double* __restrict__ MW, int64_t ldw, int wa,
              const double* __restrict__ S, int64_t lds, int ncol, int64_t n, double* __restrict__ partial) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -82,8 +83,14 @@ k_gram_strip(const double* __restrict__ KW, const double* __restrict__ MW, int64
             tma_load_1d(dst + 2 * wa, S + (r0 + lane) * lds, sbytes, &full[s]);
         }
     };
-    if (warp == 0)
+    if (PRODUCER) {
+        if (warp == ST_WARPS) {              // producer warp: the whole ring, nothing else
+            for (int64_t it = 0; it < mine; ++it) issue(it);
+            return;
+        }
+    } else if (warp == 0) {
         for (int64_t it = 0; it < min((int64_t)ST_STAGES, mine); ++it) issue(it);
+    }
 
     const int kk = lane & 3, mm = lane >> 2;
     for (int64_t it = 0; it < mine; ++it) {
@@ -106,7 +113,7 @@ k_gram_strip(const double* __restrict__ KW, const double* __restrict__ MW, int64
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
-        if (warp == 0 && it >= 1 && it - 1 + ST_STAGES < mine) issue(it - 1 + ST_STAGES);
+        if (!PRODUCER && warp == 0 && it >= 1 && it - 1 + ST_STAGES < mine) issue(it - 1 + ST_STAGES);
     }
     // partial[cta][at][bt][64]: lane holds C[row = lane>>2][col = 2 (lane&3) + {0,1}]
     double* out = partial + (size_t)blockIdx.x * ST_MAXA * ST_MAXB * 64;
@@ -148,14 +155,19 @@ int gram_strip(const double* KW, const double* MW, int64_t ldw, int wa, const do
                "gram_strip: blocks must be 16-byte aligned with even leading dimensions");
     DS_REQUIRE(n > 0, "gram_strip: n must be positive");
     ProfScope prof(PROF_GRAM, stream);
+    // Ring geometry measured at n = 823 875, wa = 48 (scripts/bench_dense.py, profiles/r2q_gram_strip_variants.txt):
+    // 8 rows x 8 stages, copies issued by warp 0: 1.058 ms (21.5 TFLOP/s); the same with a producer warp: 0.854 ms;
+    // 16 rows x 5 stages + producer warp: 0.840 ms (27.1 TFLOP/s = 0.73 of the measured DMMA peak).
+    constexpr int ROWS = 16, STAGES = 5;
+    constexpr size_t smem = st_smem(ROWS, STAGES);
     static bool attr = false;
     if (!attr) {
-        DS_CUDA(cudaFuncSetAttribute(k_gram_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
+        DS_CUDA(cudaFuncSetAttribute(k_gram_strip<ROWS, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
-    const int64_t chunks = ceil_div(n, ST_ROWS);
+    const int64_t chunks = ceil_div(n, ROWS);
     const int ctas = (int)(chunks < num_sms ? chunks : num_sms);
-    k_gram_strip<<<ctas, ST_THREADS, ST_SMEM, stream>>>(KW, MW, ldw, wa, S, lds, ncol, n, partial);
+    k_gram_strip<ROWS, STAGES, true><<<ctas, ST_THREADS + 32, smem, stream>>>(KW, MW, ldw, wa, S, lds, ncol, n, partial);
     DS_LAUNCH_CHECK();
     k_gram_strip_reduce<<<(2 * wa / 8) * (ncol / 8), 64, 0, stream>>>(partial, ctas, wa, ncol / 8, GsK, GsM, ldg);
     DS_LAUNCH_CHECK();
