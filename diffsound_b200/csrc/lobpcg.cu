@@ -55,13 +55,19 @@ __global__ void k_residual(const double* __restrict__ KX, const double* __restri
     }
 }
 
-__global__ void k_colsum_reduce(const double* __restrict__ partial, int nparts, int width, double* __restrict__ out) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
+// out[t] = sum over the per-CTA partials of column t: one WARP per column (lane l adds partials l, l + 32, ... in order, the
+// 32 lane sums meet in a fixed butterfly: deterministic).  One thread per column took 30 us for 296 partials -- a
+// latency-bound chain that ran 34 times per modal solve.
+__global__ void __launch_bounds__(256) k_colsum_reduce(const double* __restrict__ partial, int nparts, int width,
+                                                       double* __restrict__ out) {
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (t >= width) return;
     double s = 0.0;
-    for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * width + t];
-    out[t] = s;
+    for (int p = lane; p < nparts; p += 32) s += partial[(size_t)p * width + t];
+    s = warp_sum(s);
+    if (lane == 0) out[t] = s;
 }
+static inline unsigned colsum_blocks(int width) { return (unsigned)((width * 32 + 255) / 256); }
 
 // per-column sum of squares of a block (n x w, ld)
 __global__ void k_colnorm2(const double* __restrict__ V, int64_t ld, int w, int64_t n, double* __restrict__ partial) {
@@ -325,7 +331,7 @@ struct Driver {
         size_t sm = (size_t)(threads / w) * w * sizeof(double);
         k_colnorm2<<<norm_ctas, threads, sm, st>>>(V, ldv, w, n, norm_partial);
         DS_LAUNCH_CHECK();
-        k_colsum_reduce<<<1, 128, 0, st>>>(norm_partial, norm_ctas, w, norms);
+        k_colsum_reduce<<<colsum_blocks(w), 256, 0, st>>>(norm_partial, norm_ctas, w, norms);
         DS_LAUNCH_CHECK();
         out.resize(w);
         DS_CUDA(cudaMemcpyAsync(out.data(), norms, w * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -347,7 +353,7 @@ struct Driver {
     static constexpr int LMAX_W = 16, LMAX_STEPS0 = 12;
     int lmax_norms(const float* v, int64_t nl, double* out_dev, cudaStream_t s) {
         DS_TRY(colnorm2_f32(v, LMAX_W, nl, norm_partial, norm_ctas, s));
-        k_colsum_reduce<<<1, 128, 0, s>>>(norm_partial, norm_ctas, LMAX_W, out_dev);
+        k_colsum_reduce<<<colsum_blocks(LMAX_W), 256, 0, s>>>(norm_partial, norm_ctas, LMAX_W, out_dev);
         DS_LAUNCH_CHECK();
         return DS_OK;
     }
@@ -619,7 +625,7 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
         { ProfScope prof(PROF_RESIDUAL, st);
         k_residual<<<norm_ctas, res_threads, res_smem, st>>>(KS[cur], MS[cur], ld, m, n, lam_d, R, m, norm_partial);
         DS_LAUNCH_CHECK();
-        k_colsum_reduce<<<1, 256, 0, st>>>(norm_partial, norm_ctas, 2 * m, norms);
+        k_colsum_reduce<<<colsum_blocks(2 * m), 256, 0, st>>>(norm_partial, norm_ctas, 2 * m, norms);
         DS_LAUNCH_CHECK(); }
         DS_CUDA(cudaMemcpyAsync(hn.data(), norms, 2 * m * sizeof(double), cudaMemcpyDeviceToHost, st));
         DS_CUDA(cudaMemcpyAsync(lam.data(), lam_d, m * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -669,7 +675,7 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
             const int threads = (1024 / na) * na;
             k_coldot_rw<<<norm_ctas, threads, (size_t)(threads / na) * na * sizeof(double), st>>>(R, m, ci, na, Wb(cur), ld, n, norm_partial);
             DS_LAUNCH_CHECK();
-            k_colsum_reduce<<<1, 128, 0, st>>>(norm_partial, norm_ctas, na, norms);
+            k_colsum_reduce<<<colsum_blocks(na), 256, 0, st>>>(norm_partial, norm_ctas, na, norms);
             DS_LAUNCH_CHECK();
             std::vector<double> en(na);
             DS_CUDA(cudaMemcpyAsync(en.data(), norms, na * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -791,7 +797,7 @@ extern "C" int ds_lobpcg_residual(const double* KX, const double* MX, int64_t ld
     const int ctas = 296, threads = (1024 / m) * m;
     k_residual<<<ctas, threads, (size_t)(threads / m) * 2 * m * sizeof(double), st>>>(KX, MX, ld, m, n, lam, R, ldr, partial);
     DS_LAUNCH_CHECK();
-    k_colsum_reduce<<<1, 256, 0, st>>>(partial, ctas, 2 * m, sums);
+    k_colsum_reduce<<<colsum_blocks(2 * m), 256, 0, st>>>(partial, ctas, 2 * m, sums);
     DS_LAUNCH_CHECK();
     return DS_OK;
 }

@@ -663,43 +663,15 @@ __global__ void k_invert_perm(const int32_t* __restrict__ perm, int64_t n, int32
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) inv[perm[i]] = (int32_t)i;
 }
-// out[r] = sum_{q < r} deg(perm[q]), out[n] = total: one CTA, block scans of 1024 rows
-__global__ void __launch_bounds__(1024) k_perm_brow(const int32_t* __restrict__ brow, const int32_t* __restrict__ perm,
-                                                    int n, int32_t* __restrict__ out) {
-    __shared__ int s_warp[32];
-    __shared__ int s_carry;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_carry = 0;
-    __syncthreads();
-    for (int base = 0; base < n; base += 1024) {
-        const int i = base + tid;
-        int v = 0;
-        if (i < n) { const int s = perm[i]; v = brow[s + 1] - brow[s]; }
-        int x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
-        }
-        if (lane == 31) s_warp[warp] = x;
-        __syncthreads();
-        if (warp == 0) {
-            int w = s_warp[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int y = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += y;
-            }
-            s_warp[lane] = w;
-        }
-        __syncthreads();
-        const int excl = x - v + (warp ? s_warp[warp - 1] : 0) + s_carry;
-        if (i < n) out[i] = excl;
-        __syncthreads();
-        if (tid == 1023) s_carry = excl + v;
-        __syncthreads();
-    }
-    if (tid == 0) out[n] = s_carry;
+// out[r] = deg(perm[r]), out[n] = 0: the input of the exclusive scan that gives the row pointers of the renumbered level
+// (a device-wide CUB scan; the single-CTA scan it replaces took 0.37 ms on the 274 625 rows of the bench mesh)
+__global__ void __launch_bounds__(256) k_perm_deg(const int32_t* __restrict__ brow, const int32_t* __restrict__ perm,
+                                                  int n, int32_t* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    int v = 0;
+    if (i < n) { const int s = perm[i]; v = brow[s + 1] - brow[s]; }
+    out[i] = v;
 }
 
 // Out = cc * invD R   (first Chebyshev step from a zero initial guess); one thread per (node, 4 columns)
@@ -1084,7 +1056,9 @@ static size_t morton_sort_temp(int64_t n_nodes) {
     size_t t = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, t, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
                                     (uint32_t*)nullptr, (int)n_nodes, 0, 30);
-    return t;
+    size_t u = 0;           // the scan of the permuted row lengths reuses the same scratch
+    cub::DeviceScan::ExclusiveSum(nullptr, u, (int32_t*)nullptr, (int32_t*)nullptr, (int)n_nodes + 1);
+    return std::max(t, u);
 }
 
 // bcolP[browP[r] + p] = inv[bcol[brow[perm[r]] + p]]: the level's column ids as a plain int32 array (the FP64 SpMM on
@@ -1158,8 +1132,10 @@ int Level32::setup(Arena& a, const int32_t* brow_, const int32_t* bcol, int64_t 
         count_launch();
         k_invert_perm<<<blocks, 256, 0, st>>>(perm_w, n_nodes, inv_w);
         DS_LAUNCH_CHECK();
-        k_perm_brow<<<1, 1024, 0, st>>>(brow_, perm_w, (int)n_nodes, brow_w);
+        k_perm_deg<<<(unsigned)ceil_div(n_nodes + 1, 256), 256, 0, st>>>(brow_, perm_w, (int)n_nodes, brow_w);
         DS_LAUNCH_CHECK();
+        DS_CUDA(cub::DeviceScan::ExclusiveSum(scratch, tmp, brow_w, brow_w, (int)n_nodes + 1, st));
+        count_launch();
         perm = perm_w;
         inv = inv_w;
         brow = brow_w;

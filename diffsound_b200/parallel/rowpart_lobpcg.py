@@ -260,6 +260,26 @@ class RowPartLOBPCG:
                 prev = est
         return 1.1 * est
 
+    def _coarse_solve(self, rc, w):
+        """Chebyshev solve on the (replicated) P1 operator.  Its columns are independent, so with several ranks each rank
+        solves ceil(w / world) of them (padded to the kernel's 16-column granularity) and the slices are all-gathered:
+        the persistent kernel costs 0.62 ms at 16 columns against 1.34 ms at 48, the all-gather of 20 MB ~0.1 ms."""
+        co = self.coarse
+        if self.world == 1 or w < 32:
+            return native.cheb32_solve(co.pattern, self.rec_c, self.invD_c, rc, self.cdeg, self.lmax_c, self.cratio)
+        nc3 = rc.shape[0]
+        per = -(-w // self.world)
+        per16 = -(-per // 16) * 16
+        c0 = min(self.rank * per, w)
+        c1 = min(c0 + per, w)
+        loc = torch.zeros(nc3, per16, dtype=torch.float32, device=self.dev)
+        if c1 > c0:
+            loc[:, :c1 - c0] = rc[:, c0:c1]
+        zloc = native.cheb32_solve(co.pattern, self.rec_c, self.invD_c, loc, self.cdeg, self.lmax_c, self.cratio)
+        allz = torch.empty(self.world, nc3, per16, dtype=torch.float32, device=self.dev)
+        dist.all_gather_into_tensor(allz, zloc.contiguous(), group=self.group)
+        return allz[:, :, :per].permute(1, 0, 2).reshape(nc3, self.world * per)[:, :w].contiguous()
+
     def _vcycle(self, r32, w):
         """two-level V(nu, nu) cycle on the slab; returns the peer-block index holding z (rows of this rank)."""
         lib = self.lib
@@ -273,7 +293,7 @@ class RowPartLOBPCG:
             _lib.check(lib.ds_pmg_restrict32_range(_p(co.rptr), _p(co.rlist), co.n_nodes, _p(res), w, self.r0, self.r1, _p(rc),
                                                    native._stream()), "ds_pmg_restrict32_range")
         self._allreduce(rc)
-        zc = native.cheb32_solve(co.pattern, self.rec_c, self.invD_c, rc, self.cdeg, self.lmax_c, self.cratio)
+        zc = self._coarse_solve(rc, w)
         z = self.peers.block(cur, 3 * self.nl, w)
         with torch.cuda.device(self.dev):
             par = C.c_void_p(co.parents.data_ptr() + 8 * self.r0)
