@@ -511,7 +511,7 @@ struct Driver {
         dc.o.maxit = 40;
         const int deg = o.nested_degree > 0
                             ? o.nested_degree
-                            : (int)std::min(48.0, std::max(24.0, std::round(std::cbrt((double)dc.n) / 1.5)));   // floor: thin shells
+                            : (int)std::min(48.0, std::max(24.0, std::round(std::cbrt((double)dc.n) / 1.2)));   // floor: thin shells; 1.2: one nested iteration fewer than 1.5 at n_c = 107 811 (r2t tuning)
         dc.o.cheb_degree = deg;
         dc.o.cheb_ratio = 0.4 * deg * deg;
         int64_t cstats[12] = {0};

@@ -332,7 +332,7 @@ class RowPartLOBPCG:
             rows = (3 * co.corner_nodes[:, None] + torch.arange(3, device=dev)[None, :]).reshape(-1)
             Xc = X0[rows].contiguous()
             nc = 3 * co.n_nodes
-            deg = int(min(48, max(24, round(nc ** (1.0 / 3.0) / 1.5))))
+            deg = int(min(48, max(24, round(nc ** (1.0 / 3.0) / 1.2))))
             _, _, st = native.lobpcg(co.pattern, co.Kval, co.Mblk, Xc, nev=nev, tol=self.nested_tol, maxit=40, cheb_degree=deg,
                                      cheb_ratio=0.4 * deg * deg, n_rigid=n_rigid, coords=co.verts)
             nested_its = st["iterations"]
