@@ -5,7 +5,8 @@ thickness coefficient.  Candidates are independent modal solves: rank r takes ca
 diffsound_b200.parallel.sweep (no data-path collective; NCCL only for the barrier, the max-over-ranks time and the final
 gather of 32 eigenvalues + one gradient per candidate).  Prints one JSON line (rank 0).
 
-usage: python scripts/bench_sweep.py [n_candidates] [reps]
+usage: python scripts/bench_sweep.py [n_candidates] [reps] [dynamic|roundrobin]   (assignment of candidates to ranks;
+       default dynamic: a shared counter hands out the next candidate, parallel/sweep.py WorkQueue)
        python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 scripts/bench_sweep.py"""
 import json
 import os
@@ -19,10 +20,11 @@ import torch
 import torch.distributed as dist
 
 from diffsound_b200.dmtet.geometry.dmtet_thickness import DMTetGeometry
-from diffsound_b200.parallel.sweep import gather_ordered, shard_indices
+from diffsound_b200.parallel.sweep import WorkQueue, gather_indexed, gather_ordered, shard_indices
 
 n_cand = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+assign = sys.argv[3] if len(sys.argv) > 3 else "dynamic"
 rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
@@ -60,9 +62,10 @@ barrier()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(reps):
-    results, sizes = [], []
-    for i in mine:
+    results, sizes, taken = [], [], []
+    for i in (WorkQueue(n_cand) if assign == "dynamic" else mine):
         obj, tc = solve(coefs[i])
+        taken.append(i)
         results.append((obj.eigenvalues.cpu().tolist(), float(tc.grad)))
         sizes.append((int(obj.tetmesh.tets.shape[0]), int(obj.deform.pattern.n), int(obj.eig_stats["iterations"])))
 e1.record()
@@ -73,11 +76,11 @@ tmin = t.clone()
 if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
-all_res = gather_ordered(results, n_cand, rank, world)
-all_sizes = gather_ordered(sizes, n_cand, rank, world)
+all_res = gather_indexed(list(zip(taken, results)), n_cand)
+all_sizes = gather_indexed(list(zip(taken, sizes)), n_cand)
 if rank == 0:
     lam0 = [r[0][0] for r in all_res]
-    line = {"what": "thickness sweep (BASELINE configs[3])", "n_gpus": world, "candidates": n_cand, "scaling": "strong (candidates sharded)",
+    line = {"what": "thickness sweep (BASELINE configs[3])", "n_gpus": world, "candidates": n_cand, "scaling": "strong (candidates sharded)", "assignment": assign,
             "value": n_cand / (float(t.item()) * 1e-3), "unit": "solves/s", "ms_sweep_max_rank": float(t.item()),
             "ms_sweep_min_rank": float(tmin.item()), "load_imbalance_max_over_min": float(t.item()) / float(tmin.item()),
             "tets_min_max": [min(s[0] for s in all_sizes), max(s[0] for s in all_sizes)],

@@ -10,7 +10,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from diffsound_b200.parallel import gather_ordered, owner_of, shard_indices, slab_bounds, sweep_modal_solves
+from diffsound_b200.parallel import (gather_ordered, owner_of, shard_indices, slab_bounds, sweep_modal_solves,
+                                     sweep_modal_solves_dynamic, WorkQueue, gather_indexed)
 from diffsound_b200.parallel.rowpart import packed_column_map
 from diffsound_b200.parallel.synth import ShardedModalSynth, batch_slice
 
@@ -31,6 +32,18 @@ def _worker(rank, world, port, q):
         res = sweep_modal_solves(cands, lambda c: (c, [c + 1.0, c + 2.0]))
         assert [r[0] for r in res] == cands
         assert all(r[1] == [c + 1.0, c + 2.0] for r, c in zip(res, cands))
+        # dynamic assignment (work queue in the group's store): every candidate exactly once whatever the pace of the ranks
+        import time
+
+        def slow(c):
+            time.sleep(0.02 if (int(c) // 10 + rank) % 2 else 0.001)
+            return (c, rank)
+        res = sweep_modal_solves_dynamic(cands, slow)
+        assert [r[0] for r in res] == cands and {r[1] for r in res} <= {0, 1}
+        mine_idx = list(WorkQueue(5))              # a second queue (same construction order on both ranks) starts at zero
+        both = [None] * world
+        dist.all_gather_object(both, mine_idx)
+        assert sorted(i for part in both for i in part) == list(range(5))
         # a rank that reports the wrong number of results is an error, not a silent mis-ordering
         try:
             gather_ordered([1], 7)
@@ -75,6 +88,11 @@ def test_shard_indices_cover_everything():
     with pytest.raises(ValueError):
         shard_indices(4, 2, 2)
     assert gather_ordered([3, 4], 2) == [3, 4]          # no process group: identity
+    assert list(WorkQueue(3)) == [0, 1, 2]
+    assert gather_indexed([(1, "b"), (0, "a")], 2) == ["a", "b"]
+    with pytest.raises(ValueError):
+        gather_indexed([(0, "a"), (0, "b")], 2)
+    assert sweep_modal_solves_dynamic([5, 6], lambda c: c * 2) == [10, 12]
 
 
 @pytest.mark.parametrize("n,world", [(10, 3), (274625, 8), (8, 8), (1001, 2)])
