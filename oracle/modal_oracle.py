@@ -146,16 +146,38 @@ def transform_matrix(verts, tets, order):
     return torch.stack([v1 - v4, v2 - v4, v3 - v4], dim=2).to(torch.float32)
 
 
+# The reference inverts A and takes det A in fp32 (torch.inverse / torch.det on the fp32 transform matrix).  INVERSE_DTYPE =
+# torch.float64 evaluates the SAME formulas with the inverse and the determinant in fp64 on the same fp32 A -- not the
+# reference's arithmetic; the tests use it only to measure how far the reference's fp32 inverse is from the exact one on a
+# given mesh (its own accuracy floor: thin shell elements are ill-conditioned), see `inverse_precision`.
+INVERSE_DTYPE = torch.float32
+
+
+class inverse_precision:
+    """with inverse_precision(torch.float64): ... -- A^-1 and det A of the element geometry in that precision."""
+
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+    def __enter__(self):
+        global INVERSE_DTYPE
+        self.prev, INVERSE_DTYPE = INVERSE_DTYPE, self.dtype
+
+    def __exit__(self, *exc):
+        global INVERSE_DTYPE
+        INVERSE_DTYPE = self.prev
+
+
 def shape_func_deriv(verts, tets, order):
     """grad_x N_a at every Gauss point: (T, G, npe, 3) fp32
     = (dN/dL . dL/dxi) . A^-1   (src/diffelastic/deform.py:35-68)."""
     A = transform_matrix(verts, tets, order)
-    Ainv = torch.inverse(A)
+    Ainv = torch.inverse(A.to(INVERSE_DTYPE))
     pts, _ = gauss_rule(order + 2)
     dN = shape_fn_grad(torch.from_numpy(pts), order)          # (G,npe,4) fp32
     dLdxi = torch.tensor([[1, 0, 0], [0, 1, 0], [0, 0, 1], [-1, -1, -1]],
                          dtype=torch.float32)
-    dNdxi = dN @ dLdxi                                          # (G,npe,3)
+    dNdxi = (dN @ dLdxi).to(INVERSE_DTYPE)                      # (G,npe,3)
     return dNdxi.unsqueeze(0) @ Ainv.unsqueeze(1)               # (T,G,npe,3)
 
 
@@ -163,7 +185,7 @@ def integration_weights(verts, tets, order):
     """w_g |det A|, (T, G) fp32 (src/diffelastic/deform.py:136-147)."""
     A = transform_matrix(verts, tets, order)
     _, wts = gauss_rule(order + 2)
-    return torch.abs(torch.det(A)).unsqueeze(1) * torch.from_numpy(wts).unsqueeze(0)
+    return torch.abs(torch.det(A.to(INVERSE_DTYPE))).unsqueeze(1) * torch.from_numpy(wts).to(INVERSE_DTYPE).unsqueeze(0)
 
 
 def lame(youngs, poisson):

@@ -64,7 +64,12 @@ def test_shape_gradient_vs_reference_golden(meshes, name, order):
     assert err <= 1e-5, err
 
 
-@pytest.mark.parametrize("name,order,k", [("cube3", 2, 16), ("grid16", 2, 16), ("bowl", 1, 16), ("grid16", 1, 38)])
+# bowl order 2 (n = 53 574): the reference itself runs out of memory differentiating it (no golden), the oracle port does not.
+# Tolerance: 1e-5 rel-L2 against the oracle in the REFERENCE's arithmetic (A^-1 and det A in fp32), unless the reference's own
+# fp32 inverse is further than that from the exact inverse on the mesh: the kernel inverts the same fp32 A in fp64, so it is
+# compared (a) with the oracle evaluated with an fp64 inverse, <= 5e-6, and (b) with the fp32 oracle within the measured
+# distance between the two oracles (bowl order 2, flat shell elements: 1.8e-5; bowl order 1: 6e-6; grid16: 2e-7).
+@pytest.mark.parametrize("name,order,k", [("cube3", 2, 16), ("grid16", 2, 16), ("bowl", 1, 16), ("grid16", 1, 38), ("bowl", 2, 16)])
 def test_shape_gradient_vs_oracle(meshes, name, order, k):
     from diffsound_b200 import native
     rho, E, nu = 7850.0, 2.0e11, 0.29
@@ -73,6 +78,9 @@ def test_shape_gradient_vs_oracle(meshes, name, order, k):
     lam_h, U_h, _, _ = mo.eig_arpack(K, M, k)
     gvec = 1.0 / lam_h
     ref = mo.eigval_grad_shape(pv, pt, order, E, nu, rho, U_h, lam_h, gvec).numpy()
+    with mo.inverse_precision(torch.float64):
+        ref64 = mo.eigval_grad_shape(pv, pt, order, E, nu, rho, U_h, lam_h, gvec).numpy()
+    floor = np.linalg.norm(ref - ref64) / np.linalg.norm(ref64)        # the reference's own fp32-inverse error on this mesh
     verts = pv.to(DEV).contiguous()
     tets = pt.to(torch.int32).to(DEV).contiguous()
     ctab, mtab = _tables(order, rho)
@@ -85,7 +93,9 @@ def test_shape_gradient_vs_oracle(meshes, name, order, k):
                                    torch.tensor(lam_h, device=DEV), torch.tensor(gvec, device=DEV), inc_ptr,
                                    inc).cpu().numpy()
     err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
-    assert err <= 1e-5, err
+    err64 = np.linalg.norm(got - ref64) / np.linalg.norm(ref64)
+    assert err64 <= 5e-6, (err64, floor)          # measured: 2.6e-6 on bowl order 2 (fp32 output, fp32 Gauss tables)
+    assert err <= max(1e-5, 1.2 * floor + 5e-6), (err, floor)
     # incidence lists: every (tet, corner) exactly once, grouped by node
     incn = inc.cpu().numpy()
     assert np.array_equal(np.sort(incn), np.arange(4 * pt.shape[0]))
