@@ -779,7 +779,10 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
     stats[7] = coarse.cols;
     stats[8] = nested_iters;
     stats[9] = nested_status;
-    stats[10] = stats[11] = 0;
+    // spectral-radius estimates lmax(invD K) of the fine and the coarse level, as round(1e9 * estimate): a caller that runs
+    // its own cycle on the same operator (the row-slab driver's replicated coarse level) takes them over
+    stats[10] = (int64_t)std::llround(1e9 * fine.lmax);
+    stats[11] = (int64_t)std::llround(1e9 * coarse.lmax);
     return DS_OK;
 }
 

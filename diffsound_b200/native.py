@@ -470,7 +470,8 @@ def lobpcg(pattern, Kval, Mblk, X, nev, tol=1e-4, maxit=200, cheb_degree=8, sigm
     return lam, res, dict(iterations=int(stats[0]), converged=int(stats[1]), spmm=int(stats[2]), status=int(stats[3]),
                           cheb_steps=int(stats[4]), cheb_cols_avg=(stats[5] / stats[4] if stats[4] else 0.0),
                           coarse_steps=int(stats[6]), coarse_cols_avg=(stats[7] / stats[6] if stats[6] else 0.0),
-                          two_level=coarse is not None, nested_iterations=int(stats[8]), nested_status=int(stats[9]))
+                          two_level=coarse is not None, nested_iterations=int(stats[8]), nested_status=int(stats[9]),
+                          lmax_fine=stats[10] * 1e-9, lmax_coarse=stats[11] * 1e-9)
 
 
 def corner_incidence(tets_i32, order, n_nodes):

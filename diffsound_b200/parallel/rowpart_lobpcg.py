@@ -308,25 +308,12 @@ class RowPartLOBPCG:
         co = self.coarse
         f64 = dict(dtype=torch.float64, device=dev)
         stream = native._stream
-        self._tick("lmax")
-        # ---- spectral bounds (coarse: replicated, local kernel; fine: through the slab SpMM)
-        zc0 = torch.zeros(3 * co.n_nodes, 16, dtype=torch.float32, device=dev)
-        g = torch.Generator(device=dev).manual_seed(99)
-        a = torch.rand(3 * co.n_nodes, 16, device=dev, generator=g) * 2 - 1
-        est = None
-        for it in range(16):
-            b = native.spmm32(co.pattern, self.rec_c, a, mode=2, R=zc0, invD=self.invD_c, Zprev=zc0, ab=-1.0, cc=-1.0)
-            if it >= 11:      # the ratio grows monotonically towards lmax; kept on the device, read back once
-                r = torch.sqrt((b.double() ** 2).sum(0) / (a.double() ** 2).sum(0)).max()
-                est = r if est is None else torch.maximum(est, r)
-            a = b
-        est = float(est)
-        self.lmax_c = 1.1 * est
-        self.lmax_f = self._estimate_lmax()
         # ---- nested iteration: the P1 eigen-problem, replicated, then prolonged (every rank prolongs all rows: the initial
-        #      K X, M X products need the whole block as gather source)
+        #      K X, M X products need the whole block as gather source).  It runs first: its fine level IS this solve's
+        #      coarse level, so the spectral-radius estimate of the coarse Chebyshev interval is taken over from it.
         X = X0
         nested_its = 0
+        self.lmax_c = None
         self._tick("nested")
         if nested and co.Mblk is not None:
             rows = (3 * co.corner_nodes[:, None] + torch.arange(3, device=dev)[None, :]).reshape(-1)
@@ -336,9 +323,26 @@ class RowPartLOBPCG:
             _, _, st = native.lobpcg(co.pattern, co.Kval, co.Mblk, Xc, nev=nev, tol=self.nested_tol, maxit=40, cheb_degree=deg,
                                      cheb_ratio=0.4 * deg * deg, n_rigid=n_rigid, coords=co.verts)
             nested_its = st["iterations"]
+            if st.get("lmax_fine", 0.0) > 0.0:
+                self.lmax_c = st["lmax_fine"]
             X = torch.empty_like(X0)
             with torch.cuda.device(dev):
                 _lib.check(lib.ds_pmg_prolong64(_p(co.parents), self.pat.n_nodes, _p(Xc), m, m, _p(X), m, stream()), "ds_pmg_prolong64")
+        self._tick("lmax")
+        # ---- spectral bounds (coarse: replicated, local kernel, only without a nested solve; fine: through the slab SpMM)
+        if self.lmax_c is None:
+            zc0 = torch.zeros(3 * co.n_nodes, 16, dtype=torch.float32, device=dev)
+            g = torch.Generator(device=dev).manual_seed(99)
+            a = torch.rand(3 * co.n_nodes, 16, device=dev, generator=g) * 2 - 1
+            est = None
+            for it in range(16):
+                b = native.spmm32(co.pattern, self.rec_c, a, mode=2, R=zc0, invD=self.invD_c, Zprev=zc0, ab=-1.0, cc=-1.0)
+                if it >= 11:      # the ratio grows monotonically towards lmax; kept on the device, read back once
+                    r = torch.sqrt((b.double() ** 2).sum(0) / (a.double() ** 2).sum(0)).max()
+                    est = r if est is None else torch.maximum(est, r)
+                a = b
+            self.lmax_c = 1.1 * float(est)
+        self.lmax_f = self._estimate_lmax()
         self._tick("alloc")
         # ---- local buffers
         S = [torch.zeros(nl3, ld, **f64) for _ in range(2)]

@@ -158,7 +158,8 @@ int ds_eigh_generalized_f64(const double* GK, const double* GM, int N, int64_t l
  * residuals; stats_host (host int64[12]) = {iterations, converged, spmm_count, status,
  * fine-level FP32 SpMM launches, sum over those launches of the column count,
  * coarse-level launches, sum of their column counts, iterations of the nested coarse eigen-solve,
- * its status, 0, 0}.
+ * its status, round(1e9 * lmax) of the fine level's Chebyshev interval (the estimate of the largest eigenvalue of invD K,
+ * safety factor included), the same for the coarse level (0 without one)}.
  * Preconditioner (FP32, see ds_spmm32): `cheb_degree` steps of block-Jacobi Chebyshev on
  * K + sigma*M, or, when `coarse` is given (quadratic meshes), a two-level p-multigrid V-cycle:
  * `smooth_steps` Chebyshev-Jacobi steps on [lmax/smooth_ratio, lmax] before and after a
