@@ -319,12 +319,17 @@ def run_rowpart(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = lib.ds_launch_count()
     e0.record()
+    marks = []
     for _ in range(args.steps):
         stats = solve()
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        marks.append(ev)
     e1.record()
     barrier()
     launches = int(lib.ds_launch_count() - launches0)
     sampler.stop_flag = True
+    each_ms = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
     tms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -355,7 +360,7 @@ def run_rowpart(args):
     pat = obj.deform.pattern
     line = {"metric": METRIC, "value": args.steps / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "mode": "rowpart",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "mode": "rowpart", "ms_each_step_rank0": each_ms,
             "config": {"workload": workload_name(args.cube),
                        "sizes": f"n={pat.n} dofs, nnz={9 * pat.nnzb}; ONE mesh, rows split over {world} GPU(s)",
                        "eig_tol": DiffSoundObj.eig_tol, "lobpcg_iterations": stats["iterations"],

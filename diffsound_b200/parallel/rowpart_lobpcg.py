@@ -21,6 +21,7 @@ The nested P1 eigen-solve for the start block is replicated as well.  What does 
 therefore: nested solve + coarse solves + small eigen-solves (see DESIGN.md section 6 for the measured split).
 """
 import ctypes as C
+import types
 import math
 from typing import List, Optional
 
@@ -116,8 +117,16 @@ class RowPartLOBPCG:
     assembly; 1 ms at config 3).  X0: (n, m) fp64 start block, identical on every rank."""
 
     def __init__(self, pattern, Kval, Mblk, coarse, group=None, smooth_steps=3, smooth_ratio=8.0, coarse_degree=40,
-                 coarse_ratio=None, nested_tol=3e-2, verbose=False):
+                 coarse_ratio=None, nested_tol=3e-2, verbose=False, coords=None):
         self.lib = _lib.load()
+        # coords (fp32 [n_nodes, 3], optional): the solver works in a private Morton numbering of the nodes -- the slabs are
+        # contiguous ranges of the space-filling curve (compact sub-domains: shorter halos) and consecutive rows of a slab
+        # gather overlapping sets of X rows, the locality the L1-resident SpMM kernels are built for (single-GPU level:
+        # 0.31 ms per smoothing step against 0.46 ms in lexicographic order).  X0 / the returned block stay in the caller's
+        # numbering.
+        self.perm = None
+        if coords is not None:
+            pattern = self._setup_morton(pattern, coords)
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -156,9 +165,50 @@ class RowPartLOBPCG:
         self._tok = torch.zeros(1, device=dev)
         self.set_operators(Kval, Mblk, coarse)
 
+    def _setup_morton(self, pattern, coords):
+        """perm (new node -> old node) along a 30-bit Morton curve, the permuted block pattern and the gather indices that
+        carry K / M values, the fine-node tables of the coarse level and the iterate blocks into that numbering."""
+        dev = coords.device
+        n = pattern.n_nodes
+        c = coords.detach().to(torch.float32)
+        lo, hi = c.min(0).values, c.max(0).values
+        q = ((c - lo) / (hi - lo).clamp_min(1e-30) * 1023.0).long().clamp_(0, 1023)
+        code = torch.zeros(n, dtype=torch.int64, device=dev)
+        for b in range(10):
+            for d in range(3):
+                code |= ((q[:, d] >> b) & 1) << (3 * b + d)
+        perm = torch.argsort(code, stable=True)
+        inv = torch.empty_like(perm)
+        inv[perm] = torch.arange(n, device=dev)
+        brow = pattern.brow.long()
+        deg_p = (brow[1:] - brow[:-1])[perm]
+        brow_p = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        brow_p[1:] = torch.cumsum(deg_p, 0)
+        shift = brow[:-1][perm] - brow_p[:-1]                          # old start - new start of every (new) row
+        nnzb = int(brow_p[-1])
+        midx = torch.repeat_interleave(shift, deg_p) + torch.arange(nnzb, device=dev)
+        kidx = torch.repeat_interleave(9 * shift, 9 * deg_p) + torch.arange(9 * nnzb, device=dev)
+        self.perm, self.inv = perm, inv
+        self._midx, self._kidx = midx.to(torch.int32), kidx.to(torch.int32)
+        ar3 = torch.arange(3, device=dev)[None, :]
+        self._perm3 = (3 * perm[:, None] + ar3).reshape(-1)
+        self._inv3 = (3 * inv[:, None] + ar3).reshape(-1)
+        return types.SimpleNamespace(n_nodes=n, n=3 * n, nnzb=nnzb, nnz=9 * nnzb, brow=brow_p.to(torch.int32).contiguous(),
+                                     bcol=inv[pattern.bcol.long()[midx]].to(torch.int32).contiguous())
+
+    def _coarse_view(self, coarse):
+        """the coarse level with its fine-node tables (parents per fine node, gather lists of fine ids, corner ids) relabelled"""
+        v = types.SimpleNamespace(**vars(coarse))
+        v.parents = coarse.parents.view(-1, 2)[self.perm].reshape(-1).contiguous()
+        v.rlist = self.inv[coarse.rlist.long()].to(torch.int32).contiguous()
+        v.corner_nodes = self.inv[coarse.corner_nodes]
+        return v
+
     def set_operators(self, Kval, Mblk, coarse):
         """New values on the same pattern (a shape / material step): slab views of K, M, the FP32 records of the slab with
         packed (owner, local) column ids for the peer-gather SpMM, and the replicated coarse level."""
+        if self.perm is not None:
+            Kval, Mblk, coarse = torch.index_select(Kval, 0, self._kidx), torch.index_select(Mblk, 0, self._midx), self._coarse_view(coarse)
         self.Kval, self.Mblk, self.coarse = Kval, Mblk, coarse
         b0, b1 = self.b0, self.b1
         self.K_l = Kval[9 * b0:9 * b1]
@@ -304,6 +354,8 @@ class RowPartLOBPCG:
     def solve(self, X0, nev, tol=1e-5, maxit=200, n_rigid=6, nested=True):
         lib, dev, m = self.lib, self.dev, X0.shape[1]
         assert X0.dtype == torch.float64 and X0.shape[0] == self.pat.n and m in (16, 32, 48)
+        if self.perm is not None:
+            X0 = X0[self._perm3]
         nl3, ld = 3 * self.nl, 3 * m
         co = self.coarse
         f64 = dict(dtype=torch.float64, device=dev)
@@ -511,6 +563,8 @@ class RowPartLOBPCG:
                                for r in range(self.world)], dim=0)
         else:
             Xfull = Xl
+        if self.perm is not None:
+            Xfull = Xfull[self._inv3]
         self._tick("end")
         self._t_last = None
         stats = dict(iterations=it, converged=nconv, status=status, nested_iterations=nested_its, world=self.world,
@@ -540,7 +594,7 @@ def eigen_decomposition_rowpart(obj, group=None, verbose=False, solver=None, kee
     if solver is None:
         solver = RowPartLOBPCG(obj.deform.pattern, obj._Kval, obj._Mblk, coarse, group=group, smooth_steps=obj.smooth_steps,
                                smooth_ratio=obj.smooth_ratio, coarse_degree=cdeg, coarse_ratio=float(obj.coarse_ratio) or None,
-                               nested_tol=obj.nested_tol, verbose=verbose)
+                               nested_tol=obj.nested_tol, verbose=verbose, coords=obj._verts32 if obj.morton else None)
     else:
         solver.set_operators(obj._Kval, obj._Mblk, coarse)
     try:
