@@ -57,6 +57,11 @@ struct Arena {
     char* base = nullptr;
     size_t cap = 0;
     size_t used = 0;
+    // stream of the previous reserve(): a call on a different stream is ordered behind everything queued there (one event),
+    // so two torch streams of one host thread cannot race on the scratch.  (Concurrent host threads need one workspace each.)
+    cudaStream_t last_stream = nullptr;
+    bool have_stream = false;
+    cudaEvent_t order_ev = nullptr;
     int reserve(size_t bytes, cudaStream_t s);
     void reset() { used = 0; }
     template <typename T>

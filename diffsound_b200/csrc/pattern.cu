@@ -24,6 +24,13 @@ void set_error(const char* fmt, ...) {
 
 int Arena::reserve(size_t bytes, cudaStream_t s) {
     used = 0;
+    if (have_stream && last_stream != s) {          // the scratch changes hands between streams: order the new user behind the old
+        if (!order_ev) DS_CUDA(cudaEventCreateWithFlags(&order_ev, cudaEventDisableTiming));
+        DS_CUDA(cudaEventRecord(order_ev, last_stream));
+        DS_CUDA(cudaStreamWaitEvent(s, order_ev, 0));
+    }
+    last_stream = s;
+    have_stream = true;
     if (bytes <= cap) return DS_OK;
     if (base) {
         DS_CUDA(cudaStreamSynchronize(s));
@@ -44,7 +51,10 @@ int Arena::reserve(size_t bytes, cudaStream_t s) {
 
 void Arena::release() {
     if (base) cudaFree(base);
+    if (order_ev) cudaEventDestroy(order_ev);
     base = nullptr;
+    order_ev = nullptr;
+    have_stream = false;
     cap = used = 0;
 }
 

@@ -37,7 +37,9 @@ typedef struct ds_workspace ds_workspace;
 int ds_version(void);
 const char* ds_last_error(void);
 /* scratch arena; replaces the implicit temporaries torch allocates inside
- * coalesce()/sparse.mm on the reference path (diff_model.py:217-220). */
+ * coalesce()/sparse.mm on the reference path (diff_model.py:217-220).  One workspace may be used from several
+ * streams of ONE host thread (a call on another stream than the previous one is ordered behind it with an event);
+ * concurrent host threads need a workspace each. */
 int ds_workspace_create(ds_workspace** ws);
 int ds_workspace_destroy(ds_workspace* ws);
 int64_t ds_workspace_bytes(const ds_workspace* ws);
