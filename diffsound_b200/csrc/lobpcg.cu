@@ -723,6 +723,7 @@ int Driver::run(double* X, double* lambda_out, double* resid_out, int64_t* stats
             DS_TRY(eig(slots));
             DS_CUDA(cudaMemcpyAsync(info_h, info_d, sizeof(info_h), cudaMemcpyDeviceToHost, st));
             DS_CUDA(cudaStreamSynchronize(st));
+            if (o.verbose) fprintf(stderr, "[ds_lobpcg]        small eigen-solve: N = %d, %d Jacobi sweeps\n", (int)slots.size(), info_h[1]);
             if (info_h[0] == 0) break;
             if (o.verbose) fprintf(stderr, "[ds_lobpcg] it %d: RR Cholesky failed (info %d, attempt %d)\n", it, info_h[0], attempt);
             if (!fresh) {                      // first suspect: drift of the Gram recurrences
