@@ -80,6 +80,8 @@ class ClockSampler(threading.Thread):
             except Exception:
                 self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.nvml = pynvml
+            for _ in range(2):                  # the first query of each kind is slow and can hold a driver lock: do it here
+                self._sample_nvml()
         except Exception:
             self.nvml = None
 

@@ -221,21 +221,38 @@ k_eigh_solve(int N, double* __restrict__ scratch, int* __restrict__ info) {
     double y[JC_E];
 #pragma unroll
     for (int t = 0; t < JC_E; ++t) y[t] = 0.0;
+    // The substitution is a chain of N - j warp reductions; the row of L, the R entry and the reciprocal pivot of step i do not
+    // depend on it, so they are fetched two steps ahead (an L2 round trip is longer than one reduction).
+    double l0[JC_E], l1[JC_E], l2[JC_E], r0 = 0.0, r1 = 0.0, r2 = 0.0, d0 = 0.0, d1 = 0.0, d2 = 0.0;
+    auto load_row = [&](int i, double (&l)[JC_E], double& r, double& d) {
+        if (i < N) {
+            const double* Li = L + (size_t)i * N;
+#pragma unroll
+            for (int t = 0; t < JC_E; ++t) { const int k = lane + 32 * t; l[t] = k < i ? __ldg(Li + k) : 0.0; }
+            r = __ldg(R + (size_t)i * N + j);
+            d = __ldg(invL + i);
+        }
+    };
+    load_row(j, l0, r0, d0);
+    load_row(j + 1, l1, r1, d1);
 #pragma unroll
     for (int ti = 0; ti < JC_E; ++ti) {          // i = 32 ti + ii: the register that receives y_i is static
         for (int ii = 0; ii < 32; ++ii) {
             const int i = 32 * ti + ii;
             if (i < j || i >= N) continue;       // warp-uniform
-            const double* Li = L + (size_t)i * N;
+            load_row(i + 2, l2, r2, d2);
             double s = 0.0;
 #pragma unroll
             for (int t = 0; t < JC_E; ++t) {
                 const int k = lane + 32 * t;
-                if (k >= j && k < i) s = fma(__ldg(Li + k), y[t], s);
+                if (k >= j && k < i) s = fma(l0[t], y[t], s);
             }
             s = warp_sum(s);
-            const double yi = (__ldg(R + (size_t)i * N + j) - s) * __ldg(invL + i);
+            const double yi = (r0 - s) * d0;
             if (lane == ii) y[ti] = yi;
+#pragma unroll
+            for (int t = 0; t < JC_E; ++t) { l0[t] = l1[t]; l1[t] = l2[t]; }
+            r0 = r1; r1 = r2; d0 = d1; d1 = d2;
         }
     }
 #pragma unroll
@@ -499,20 +516,32 @@ k_eigh_finish(int N, const __grid_constant__ EigIdx ix, double* __restrict__ the
         double x[JC_E];
 #pragma unroll
         for (int t = 0; t < JC_E; ++t) { const int k = lane + 32 * t; x[t] = k < N ? yrow[k] : 0.0; }
-        // x_k = (y_k - sum_{q > k} x_q R[q][k]) / R[k][k], k = N-1 .. 0; at step k the lanes hold final x_q for q > k
+        // x_k = (y_k - sum_{q > k} x_q R[q][k]) / R[k][k], k = N-1 .. 0; at step k the lanes hold final x_q for q > k.
+        // Row k of R^T and the reciprocal pivot are fetched two steps ahead of the reduction chain.
+        double c0[JC_E], c1[JC_E], c2[JC_E], p0 = 0.0, p1 = 0.0, p2 = 0.0;
+        auto load_row = [&](int k, double (&c)[JC_E], double& pv) {
+            if (k >= 0) {
+#pragma unroll
+                for (int t = 0; t < JC_E; ++t) { const int q = lane + 32 * t; c[t] = (q > k && q < N) ? __ldg(RT + (size_t)k * N + q) : 0.0; }
+                pv = __ldg(invR + k);
+            }
+        };
+        load_row(N - 1, c0, p0);
+        load_row(N - 2, c1, p1);
 #pragma unroll
         for (int tk = JC_E - 1; tk >= 0; --tk) {     // k = 32 tk + kk: the register that holds x_k is static
             for (int kk = 31; kk >= 0; --kk) {
                 const int k = 32 * tk + kk;
                 if (k >= N) continue;                // warp-uniform
+                load_row(k - 2, c2, p2);
                 double s = 0.0;
 #pragma unroll
-                for (int t = 0; t < JC_E; ++t) {
-                    const int q = lane + 32 * t;
-                    if (q > k && q < N) s = fma(x[t], __ldg(RT + (size_t)k * N + q), s);
-                }
+                for (int t = 0; t < JC_E; ++t) s = fma(x[t], c0[t], s);      // c0 is zero outside q in (k, N)
                 s = warp_sum(s);
-                if (lane == kk) x[tk] = (x[tk] - s) * __ldg(invR + k);
+                if (lane == kk) x[tk] = (x[tk] - s) * p0;
+#pragma unroll
+                for (int t = 0; t < JC_E; ++t) { c0[t] = c1[t]; c1[t] = c2[t]; }
+                p0 = p1; p1 = p2;
             }
         }
         const int col = s_rank[j];
