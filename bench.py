@@ -80,8 +80,15 @@ class ClockSampler(threading.Thread):
             except Exception:
                 self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.nvml = pynvml
-            for _ in range(2):                  # the first query of each kind is slow and can hold a driver lock: do it here
+            # The first queries made while the GPU is busy are slow and hold a driver lock that kernel launches wait on (one
+            # 96 .. 198 ms step among 88 ms steps, always the one in which the second sample fell): take them here, under load.
+            busy = torch.empty(1 << 26, device=f"cuda:{index}")
+            for _ in range(40):
+                busy.add_(1.0)
+            for _ in range(3):
                 self._sample_nvml()
+            torch.cuda.synchronize(index)
+            del busy
         except Exception:
             self.nvml = None
 
@@ -89,10 +96,8 @@ class ClockSampler(threading.Thread):
         n, h = self.nvml, self.handle
         sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
         mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
-        try:
-            pw = n.nvmlDeviceGetPowerUsage(h) / 1000.0
-        except Exception:
-            pw = 0.0
+        pw = 0.0            # power is not sampled: the PMU read behind nvmlDeviceGetPowerUsage can take tens of milliseconds and
+                            # holds a driver lock that kernel launches wait on (one 96 .. 198 ms step among 88 ms steps)
         get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
         r = int(get(h))
         flag = lambda bit: "Active" if r & bit else "Not Active"      # noqa: E731
@@ -111,7 +116,7 @@ class ClockSampler(threading.Thread):
                         self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.05 if self.nvml is not None else 0.2)
+            time.sleep(0.1 if self.nvml is not None else 0.2)
 
     def summary(self):
         import statistics
