@@ -121,6 +121,7 @@ SIGNATURES = {
     "ds_sym_upper_f64": (cint, [f64p, f64p, i64, cint, ptr]),
     "ds_eigh_generalized_idx_f64": (cint, [f64p, f64p, cint, i64, C.POINTER(C.c_int), dbl, f64p, f64p, i64, f64p, ptr, ptr]),
     "ds_prof_enable": (cint, [cint]),
+    "ds_prof_reserve": (cint, [cint]),
     "ds_prof_enable_classes": (cint, [C.c_uint32]),
     "ds_prof_reset": (cint, []),
     "ds_prof_num_classes": (cint, []),

@@ -104,6 +104,19 @@ extern "C" int ds_prof_reset(void) {
     return DS_OK;
 }
 
+// Create `n` events up front.  cudaEventCreate inside a timed region is not free: when the driver's event pool runs out it
+// allocates, which waits for the device -- one 100-220 ms step among 88 ms steps, always the step in which the ~128th event
+// of the process was created (bench.py reserves before its timed regions).
+extern "C" int ds_prof_reserve(int n) {
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    while ((int)g_prof.pool.size() < n) {
+        cudaEvent_t e;
+        DS_CUDA(cudaEventCreate(&e));
+        g_prof.pool.push_back(e);
+    }
+    return DS_OK;
+}
+
 extern "C" int64_t ds_launch_count(void) { return g_launches.load(); }
 
 extern "C" int ds_prof_num_classes(void) { return PROF_NCLASS; }

@@ -428,6 +428,8 @@ int ds_tet_components_fill(ds_workspace* ws, const int64_t* tets, int64_t* kept_
  * accumulated per class ("spmm", "cheb_step", "gram", ...).  Off by default.  ds_prof_read
  * synchronises on the recorded events. */
 int ds_prof_enable(int on);
+/* create n timing events up front (event creation inside a timed region can stall on a driver allocation) */
+int ds_prof_reserve(int n);
 /* time only the classes whose bit (1 << class index, see ds_prof_class_name) is set; 0 turns timing off */
 int ds_prof_enable_classes(uint32_t mask);
 int ds_prof_reset(void);
