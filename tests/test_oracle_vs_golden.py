@@ -84,6 +84,36 @@ def test_shape_gradient(meshes, name, order):
     assert np.linalg.norm(got - ref) / np.linalg.norm(ref) <= 1e-6
 
 
+def test_inverse_precision_switch_measures_the_fp32_floor(meshes):
+    """mo.inverse_precision(torch.float64) evaluates the same formulas with A^-1 and det A in fp64 on the same fp32 A.  It is
+    NOT the reference's arithmetic (the default is, and stays pinned to the goldens above); the GPU tests use it to show how
+    far the reference's own fp32 inverse is from the exact one on a mesh: almost nothing on the regular grid, 6e-6 on the
+    thin bowl at order 1 (1.8e-5 at order 2, tests/test_grad_synth_gpu.py)."""
+    g = golden("modal_grid16_o1")
+    rho, E, nu = g["material"][:3]
+    up = g["upstream"].astype(np.float64)
+    v, t = meshes["grid16"]
+    pv, pt = mo.promote(torch.tensor(v), torch.tensor(t), 1)
+    a = mo.eigval_grad_shape(pv, pt, 1, E, nu, rho, g["U_hat"], g["eigenvalues"], up).numpy()
+    with mo.inverse_precision(torch.float64):
+        assert mo.INVERSE_DTYPE == torch.float64
+        b = mo.eigval_grad_shape(pv, pt, 1, E, nu, rho, g["U_hat"], g["eigenvalues"], up).numpy()
+    assert mo.INVERSE_DTYPE == torch.float32                      # restored
+    d = np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert 0.0 < d <= 2e-6
+    assert np.linalg.norm(a - g["grad_verts"]) / np.linalg.norm(g["grad_verts"]) <= 1e-6      # the default is the reference
+    # the thin shell: the fp32 inverse is visibly off (same eigenpairs in both evaluations, from the oracle's own ARPACK)
+    vb, tb = meshes["bowl"]
+    pvb, ptb = mo.promote(torch.tensor(vb), torch.tensor(tb), 1)
+    K, M = mo.assemble(pvb, ptb, 1, E, nu, rho)
+    lam, U, _, _ = mo.eig_arpack(K, M, 8)
+    a = mo.eigval_grad_shape(pvb, ptb, 1, E, nu, rho, U, lam, 1.0 / lam).numpy()
+    with mo.inverse_precision(torch.float64):
+        b = mo.eigval_grad_shape(pvb, ptb, 1, E, nu, rho, U, lam, 1.0 / lam).numpy()
+    d = np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert 1e-6 <= d <= 5e-5, d
+
+
 @pytest.mark.parametrize("name,order", [("cube3", 2), ("grid16", 1), ("bowl", 1)])
 def test_material_path(meshes, name, order):
     """lambda_i(E, nu) = mu q_mu + lam q_lam reproduces the reference's get_undamped_freqs."""
