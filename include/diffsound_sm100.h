@@ -71,9 +71,9 @@ int ds_pattern_expand_csr(const int32_t* brow, const int32_t* bcol, int64_t n_no
  * [npe*npe] = double(float(m_ab)*float(rho)) (diff_model.py:299-303).
  * Kval: fp64 [9*nnzb] in the reference's scalar-CSR (row, col) order.
  * Mblk: fp64 [nnzb], M = Mblk (x) I3 (the expanded reference values come from
- * ds_mass_expand).  geom: fp64 scratch [T*14].  Owner-computes: one thread per
- * block slot sums its contributors in ascending order -- no atomics,
- * deterministic. */
+ * ds_mass_expand).  geom: fp64 scratch [T*14].  Owner-computes: the warp that owns
+ * a node row sums the contributors of its block slots in ascending order, the
+ * work split evenly over its lanes -- no atomics, deterministic. */
 int ds_assemble_km(const float* verts, const int32_t* tets, int64_t T, int order,
                    int64_t n_nodes, double mu, double lam, const double* ctab,
                    const double* mtab, const int32_t* brow, const int32_t* bcol,
