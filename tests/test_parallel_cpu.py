@@ -179,3 +179,47 @@ def test_batch_slice_tiles_the_batch():
         for world in (1, 2, 3, 8):
             rows = [i for r in range(world) for i in range(B)[batch_slice(B, r, world)]]
             assert rows == list(range(B))
+
+
+def test_slab_solver_morton_numbering_is_a_symmetric_permutation():
+    """The private Morton numbering of the slab solver (RowPartLOBPCG._setup_morton): the permuted pattern and the gather
+    indices of the K / M values describe P K P^T, P M P^T for the node permutation P, and perm3 / inv3 carry iterate blocks
+    there and back.  Pure index arithmetic: checked on the CPU against dense matrices."""
+    import types
+    from diffsound_b200.parallel.rowpart_lobpcg import RowPartLOBPCG
+    rng = np.random.default_rng(0)
+    n = 23
+    coords = torch.tensor(rng.random((n, 3)), dtype=torch.float32)
+    # a random symmetric block pattern with full diagonal; rows of different lengths
+    adj = rng.random((n, n)) < 0.2
+    adj = adj | adj.T | np.eye(n, dtype=bool)
+    brow = np.concatenate([[0], np.cumsum(adj.sum(1))]).astype(np.int32)
+    bcol = np.concatenate([np.nonzero(adj[i])[0] for i in range(n)]).astype(np.int32)
+    nnzb = int(brow[-1])
+    Kval = rng.standard_normal(9 * nnzb)
+    Mblk = rng.standard_normal(nnzb)
+
+    def dense(brow, bcol, Kval, Mblk):
+        K, M = np.zeros((3 * n, 3 * n)), np.zeros((3 * n, 3 * n))
+        for i in range(n):
+            b0, deg = int(brow[i]), int(brow[i + 1] - brow[i])
+            for p in range(deg):
+                j = int(bcol[b0 + p])
+                for c in range(3):
+                    for d in range(3):
+                        K[3 * i + c, 3 * j + d] = Kval[9 * b0 + c * 3 * deg + 3 * p + d]     # the reference's value order
+                    M[3 * i + c, 3 * j + c] = Mblk[b0 + p]
+        return K, M
+
+    pat = types.SimpleNamespace(n_nodes=n, brow=torch.tensor(brow), bcol=torch.tensor(bcol))
+    me = types.SimpleNamespace()
+    pp = RowPartLOBPCG._setup_morton(me, pat, coords)
+    perm = me.perm.numpy()
+    assert sorted(perm.tolist()) == list(range(n)) and np.array_equal(me.inv.numpy()[perm], np.arange(n))
+    Kp, Mp = dense(pp.brow.numpy(), pp.bcol.numpy(), Kval[me._kidx.numpy()], Mblk[me._midx.numpy()])
+    K, M = dense(brow, bcol, Kval, Mblk)
+    p3 = me._perm3.numpy()
+    assert np.array_equal(Kp, K[np.ix_(p3, p3)]) and np.array_equal(Mp, M[np.ix_(p3, p3)])
+    X = rng.standard_normal((3 * n, 4))
+    assert np.array_equal(X[p3][me._inv3.numpy()], X)
+    assert pp.nnzb == nnzb and int(pp.brow[-1]) == nnzb
