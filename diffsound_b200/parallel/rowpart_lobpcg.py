@@ -110,6 +110,27 @@ def _cheb_coefs(lmax, ratio, degree):
     return 1.0 / theta, out
 
 
+def coarse_column_slice(rc, w, rank, world):
+    """Columns [rank * per, rank * per + per) of the first w columns of rc, per = ceil(w / world), zero-padded to the
+    16-column granularity of the Chebyshev kernels: what rank `rank` solves of a column-sharded coarse solve."""
+    per = -(-w // world)
+    per16 = -(-per // 16) * 16
+    c0 = min(rank * per, w)
+    c1 = min(c0 + per, w)
+    loc = torch.zeros(rc.shape[0], per16, dtype=rc.dtype, device=rc.device)
+    if c1 > c0:
+        loc[:, :c1 - c0] = rc[:, c0:c1]
+    return loc
+
+
+def coarse_column_merge(allz, w):
+    """Inverse of coarse_column_slice over all ranks: allz [world, rows, per16] (rank-major, as all_gather_into_tensor
+    delivers it) -> [rows, w]."""
+    world, rows, _ = allz.shape
+    per = -(-w // world)
+    return allz[:, :, :per].permute(1, 0, 2).reshape(rows, world * per)[:, :w].contiguous()
+
+
 class RowPartLOBPCG:
     """Lowest pairs of K u = lam M u with the rows of K, M, X split over the ranks of `group`.
 
@@ -317,18 +338,11 @@ class RowPartLOBPCG:
         co = self.coarse
         if self.world == 1 or w < 32:
             return native.cheb32_solve(co.pattern, self.rec_c, self.invD_c, rc, self.cdeg, self.lmax_c, self.cratio)
-        nc3 = rc.shape[0]
-        per = -(-w // self.world)
-        per16 = -(-per // 16) * 16
-        c0 = min(self.rank * per, w)
-        c1 = min(c0 + per, w)
-        loc = torch.zeros(nc3, per16, dtype=torch.float32, device=self.dev)
-        if c1 > c0:
-            loc[:, :c1 - c0] = rc[:, c0:c1]
+        loc = coarse_column_slice(rc, w, self.rank, self.world)
         zloc = native.cheb32_solve(co.pattern, self.rec_c, self.invD_c, loc, self.cdeg, self.lmax_c, self.cratio)
-        allz = torch.empty(self.world, nc3, per16, dtype=torch.float32, device=self.dev)
+        allz = torch.empty(self.world, rc.shape[0], loc.shape[1], dtype=torch.float32, device=self.dev)
         dist.all_gather_into_tensor(allz, zloc.contiguous(), group=self.group)
-        return allz[:, :, :per].permute(1, 0, 2).reshape(nc3, self.world * per)[:, :w].contiguous()
+        return coarse_column_merge(allz, w)
 
     def _vcycle(self, r32, w):
         """two-level V(nu, nu) cycle on the slab; returns the peer-block index holding z (rows of this rank)."""

@@ -223,3 +223,19 @@ def test_slab_solver_morton_numbering_is_a_symmetric_permutation():
     X = rng.standard_normal((3 * n, 4))
     assert np.array_equal(X[p3][me._inv3.numpy()], X)
     assert pp.nnzb == nnzb and int(pp.brow[-1]) == nnzb
+
+
+@pytest.mark.parametrize("w,world", [(48, 2), (48, 4), (48, 8), (32, 3), (32, 8), (48, 5)])
+def test_column_sharded_coarse_solve_slices_and_merges(w, world):
+    """The slab solver splits the columns of the (replicated) P1 coarse solve over the ranks: every column is solved by
+    exactly one rank, padding columns are zero, and the merge restores the column order."""
+    from diffsound_b200.parallel.rowpart_lobpcg import coarse_column_merge, coarse_column_slice
+    rc = torch.arange(7 * 64, dtype=torch.float32).reshape(7, 64) + 1.0
+    parts = [coarse_column_slice(rc, w, r, world) for r in range(world)]
+    assert all(p.shape == parts[0].shape and p.shape[1] % 16 == 0 for p in parts)
+    per = -(-w // world)
+    for r, p in enumerate(parts):
+        c0, c1 = min(r * per, w), min(r * per + per, w)
+        assert torch.equal(p[:, :c1 - c0], rc[:, c0:c1]) and not p[:, c1 - c0:].any()
+    merged = coarse_column_merge(torch.stack(parts), w)          # "solve" = identity
+    assert torch.equal(merged, rc[:, :w])
