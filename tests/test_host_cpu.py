@@ -154,3 +154,21 @@ def test_material_models_cpu_side():
     P = fl.get_stress(F.double())
     ref = mu * (F.double() + F.double().transpose(1, 2)) + lam * torch.einsum("bii->b", F.double())[:, None, None] * torch.eye(3).double()
     assert torch.allclose(P, ref)
+
+
+def test_bench_clock_sampler_summary():
+    """bench.py's clocks field: median SM clock, maximum clock and the throttle reasons seen in any sample -- same record
+    layout from the NVML path and from the nvidia-smi fallback (clocks.sm, clocks.max.sm, power, hw_slowdown,
+    hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap)."""
+    import bench
+    s = bench.ClockSampler(0)          # no driver in the build container: falls back to the command-line path, no samples
+    s.samples = [["1965", "1965", "0.0", "Not Active", "Not Active", "Not Active", "Not Active"],
+                 ["1950", "1965", "0.0", "Not Active", "Not Active", "Not Active", "Active"],
+                 ["1965", "1965", "0.0", "Not Active", "Not Active", "Not Active", "Not Active"]]
+    out = s.summary()
+    assert out["sm_mhz"] == 1965.0 and out["sm_max_mhz"] == 1965.0 and out["samples"] == 3
+    assert out["reasons"] == ["sw_power_cap"]
+    s.samples.append(["1200", "1965", "0.0", "Active", "Not Active", "Active", "Not Active"])
+    assert s.summary()["reasons"] == ["hw_slowdown", "sw_thermal_slowdown"] + ["sw_power_cap"]
+    s.samples = []
+    assert s.summary()["sm_mhz"] is None and s.summary()["reasons"] == []
